@@ -83,9 +83,19 @@ def full_state_pu(sim, aux=()):
 
 def gen_anm6easy(seed, T):
     env = ANM6Easy()
-    rec = {k: [] for k in ("actions", "obs", "state", "reward", "terminated", "e_loss", "penalty", "n_iter",
+    drawn = []
+    _init = env.init_state
+
+    def spy_init():
+        s0 = _init()
+        drawn.append(s0.copy())
+        return s0
+
+    env.init_state = spy_init
+    rec = {k: [] for k in ("reset_s0", "reset_attempts", "actions", "obs", "state", "reward", "terminated", "e_loss", "penalty", "n_iter",
                            "full_state", "reset_before_step", "reset_obs", "reset_state", "soc_before")}  # fmt: skip
     obs, _ = env.reset(seed=seed)
+    rec["reset_s0"].append(drawn[-1]), rec["reset_attempts"].append(len(drawn))
     rec["reset_before_step"].append(0)
     rec["reset_obs"].append(obs)
     rec["reset_state"].append(env.state.copy())
@@ -106,7 +116,9 @@ def gen_anm6easy(seed, T):
         rec["full_state"].append(full_state_pu(env.simulator, aux=[float(env.state[-1])]) if not term
                                  else np.zeros(6 * 6 + 4 * 7 + 5 * 5 + 1))  # fmt: skip
         if term:
+            n0 = len(drawn)
             obs, _ = env.reset()  # continues the same np_random stream
+            rec["reset_s0"].append(drawn[-1]), rec["reset_attempts"].append(len(drawn) - n0)
             rec["reset_before_step"].append(t + 1)
             rec["reset_obs"].append(obs)
             rec["reset_state"].append(env.state.copy())
