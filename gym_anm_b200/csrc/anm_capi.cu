@@ -1,0 +1,529 @@
+/*
+ * anm_capi.cu -- host side of the C ABI declared in include/anm_b200.h.
+ *
+ * Builds the per-network constant blob (layout: anm_layout.h) from the caller's
+ * anm_network_desc / anm_env_desc, owns the carried per-env state (SoC, aux, terminated)
+ * and launches the fused step kernel (anm_kernels.cuh).  No torch types, no exceptions
+ * across the ABI, no host synchronisation except in the *_host convenience calls.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <complex>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "anm_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) return fail(ANM_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));   \
+  } while (0)
+
+typedef std::complex<double> cd;
+
+struct BlobBuilder {
+  std::vector<unsigned char> buf;
+  explicit BlobBuilder(size_t header) : buf((header + 15) / 16 * 16, 0) {}
+  template <typename T>
+  int32_t add(const std::vector<T>& v) {
+    size_t off = buf.size();
+    size_t bytes = (v.size() * sizeof(T) + 15) / 16 * 16;
+    if (bytes == 0) bytes = 16;
+    buf.resize(off + bytes, 0);
+    if (!v.empty()) memcpy(buf.data() + off, v.data(), v.size() * sizeof(T));
+    return (int32_t)off;
+  }
+};
+
+int full_offset(const AnmConstHeader& H, int quantity) {
+  const int N = H.n_bus, D = H.n_dev, L = H.n_branch;
+  if (quantity <= ANM_Q_BUS_I_ANG) return quantity * N;
+  if (quantity <= ANM_Q_GEN_P_MAX) return 6 * N + (quantity - ANM_Q_DEV_P) * D;
+  if (quantity <= ANM_Q_BRANCH_I_ANG) return 6 * N + 4 * D + (quantity - ANM_Q_BRANCH_P) * L;
+  return 6 * N + 4 * D + 5 * L;
+}
+
+int var_limit(const AnmConstHeader& H, int quantity) {
+  if (quantity <= ANM_Q_BUS_I_ANG) return H.n_bus;
+  if (quantity <= ANM_Q_GEN_P_MAX) return H.n_dev;
+  if (quantity <= ANM_Q_BRANCH_I_ANG) return H.n_branch;
+  return H.K;
+}
+
+}  // namespace
+
+struct anm_handle_s {
+  int device = 0;
+  int64_t B = 0;
+  AnmConstHeader H;
+  unsigned char* d_blob = nullptr;
+  int blob_bytes = 0;
+  double* d_soc = nullptr;
+  double* d_aux = nullptr;
+  uint8_t* d_term = nullptr;
+  uint32_t* d_episode = nullptr;
+  const double* pool = nullptr;
+  int64_t pool_size = 0;
+  /* launch geometry */
+  int lpe = 32, gpb = 4, grid = 1, smem = 0, num_sms = 1;
+  /* host-buffer path */
+  cudaStream_t stream = nullptr;
+  double *s_action = nullptr, *s_nv = nullptr, *s_obs = nullptr, *s_reward = nullptr, *s_s0 = nullptr, *s_state = nullptr;
+  uint8_t *s_term = nullptr, *s_mask = nullptr;
+  int64_t launches = 0;
+};
+
+namespace {
+
+int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHeader& H, std::vector<unsigned char>& out) {
+  const int N = net->n_bus, D = net->n_dev, L = net->n_branch, K = env->K;
+  if (N < 2 || N > 64) return fail(ANM_E_UNSUPPORTED, "n_bus=%d not in [2, 64]", N);
+  if (D < 1 || D > 255 || L < 1 || L > 1024) return fail(ANM_E_UNSUPPORTED, "n_dev=%d / n_branch=%d out of range", D, L);
+  if (K < 0 || K > 16) return fail(ANM_E_UNSUPPORTED, "K=%d not in [0, 16]", K);
+  if (!(net->base_mva > 0) || !(net->delta_t > 0)) return fail(ANM_E_INVALID, "baseMVA and delta_t must be > 0");
+  memset(&H, 0, sizeof(H));
+  H.n_bus = N; H.n_dev = D; H.n_branch = L; H.K = K;
+  H.n_unk = 2 * (N - 1);
+  H.base_mva = net->base_mva; H.delta_t = net->delta_t; H.lamb = net->lamb; H.gamma = env->gamma;
+  H.clip_e = env->clip_e_loss; H.clip_pen = env->clip_penalty;
+  H.term_reward = -env->clip_penalty / (1.0 - env->gamma); /* anm_env.py:430 */
+
+  std::vector<int> dev_bus(D), dev_type(D), dev_slot(D);
+  std::vector<int> gens, dess;
+  int n_slack = 0;
+  for (int d = 0; d < D; ++d) {
+    dev_bus[d] = net->dev_bus[d];
+    dev_type[d] = net->dev_type[d];
+    if (dev_bus[d] < 0 || dev_bus[d] >= N) return fail(ANM_E_INVALID, "device %d: bad bus %d", d, dev_bus[d]);
+    switch (dev_type[d]) {
+      case ANM_DEV_LOAD: dev_slot[d] = H.n_load++; break;
+      case ANM_DEV_GEN:
+      case ANM_DEV_RENEWABLE: dev_slot[d] = H.n_gen++; gens.push_back(d); break;
+      case ANM_DEV_STORAGE: dev_slot[d] = H.n_des++; dess.push_back(d); break;
+      case ANM_DEV_SLACK:
+        dev_slot[d] = 0; ++n_slack;
+        if (dev_bus[d] != 0) return fail(ANM_E_INVALID, "the slack device must sit at bus 0 (solve_load_flow.py:64)");
+        break;
+      default: return fail(ANM_E_INVALID, "device %d: unknown DEV_TYPE %d", d, dev_type[d]);
+    }
+  }
+  if (n_slack != 1) return fail(ANM_E_INVALID, "exactly one slack device expected, got %d", n_slack);
+  H.n_ctrl = H.n_gen + H.n_des;
+  H.n_action = 2 * H.n_ctrl;
+  H.n_next_vars = H.n_load + H.n_gen + K;
+  H.n_full = 6 * N + 4 * D + 5 * L + K;
+  H.n_state = env->n_state; H.n_obs = env->n_obs;
+  if (H.n_state != 2 * D + H.n_des + H.n_gen + K)
+    return fail(ANM_E_INVALID, "n_state=%d but 2*n_dev+n_des+n_gen+K=%d (anm_env.py:274)", H.n_state,
+                2 * D + H.n_des + H.n_gen + K);
+  if (H.n_obs < 1) return fail(ANM_E_INVALID, "n_obs must be >= 1");
+  H.table_len = env->table_len;
+  if (H.table_len < 0 || (H.table_len > 0 && (K < 1 || !env->table)))
+    return fail(ANM_E_INVALID, "built-in next_vars table needs K >= 1 and a table pointer");
+
+  BlobBuilder bb(sizeof(AnmConstHeader));
+  H.o_vmin = bb.add(std::vector<double>(net->bus_vmin, net->bus_vmin + N));
+  H.o_vmax = bb.add(std::vector<double>(net->bus_vmax, net->bus_vmax + N));
+  H.o_dev_bus = bb.add(dev_bus);
+  H.o_dev_type = bb.add(dev_type);
+  H.o_dev_slot = bb.add(dev_slot);
+  H.o_dev_param = bb.add(std::vector<double>(net->dev_param, net->dev_param + (size_t)D * ANM_DEV_NPARAM));
+  {
+    std::vector<int> ptr(N + 1, 0), idx;
+    for (int b = 0; b < N; ++b) {
+      for (int d = 0; d < D; ++d)
+        if (dev_bus[d] == b) idx.push_back(d);
+      ptr[b + 1] = (int)idx.size();
+    }
+    H.o_bus_dev_ptr = bb.add(ptr);
+    H.o_bus_dev_idx = bb.add(idx);
+  }
+  {
+    std::vector<int> bf(L), bt(L);
+    std::vector<double> coef((size_t)L * 10, 0.0);
+    for (int l = 0; l < L; ++l) {
+      bf[l] = net->br_from[l]; bt[l] = net->br_to[l];
+      if (bf[l] < 0 || bf[l] >= N || bt[l] < 0 || bt[l] >= N) return fail(ANM_E_INVALID, "branch %d: bad endpoints", l);
+      const double* B = net->br_param + (size_t)l * ANM_BR_NPARAM;
+      const cd y(B[ANM_BP_SERIES_RE], B[ANM_BP_SERIES_IM]), ysh(B[ANM_BP_SHUNT_RE], B[ANM_BP_SHUNT_IM]);
+      const cd tap(B[ANM_BP_TAP_RE], B[ANM_BP_TAP_IM]);
+      const double t2 = std::abs(tap) * std::abs(tap);
+      const cd aff = (y + ysh) / t2, aft = -y / std::conj(tap), atf = -y / tap, att = y + ysh; /* branch.py:165-173 */
+      double* c = &coef[(size_t)l * 10];
+      c[0] = aff.real(); c[1] = aff.imag(); c[2] = aft.real(); c[3] = aft.imag();
+      c[4] = atf.real(); c[5] = atf.imag(); c[6] = att.real(); c[7] = att.imag();
+      c[8] = B[ANM_BP_RATE];
+    }
+    H.o_br_from = bb.add(bf);
+    H.o_br_to = bb.add(bt);
+    H.o_br_coef = bb.add(coef);
+  }
+  {
+    std::vector<int> ptr(N + 1, 0), col, jr, jc, jy;
+    std::vector<double> val;
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < N; ++j) {
+        const double re = net->ybus[2 * ((size_t)i * N + j)], im = net->ybus[2 * ((size_t)i * N + j) + 1];
+        if (i != j && re == 0.0 && im == 0.0) continue;
+        if (i >= 1 && j >= 1) { jr.push_back(i); jc.push_back(j); jy.push_back((int)col.size()); }
+        col.push_back(j);
+        val.push_back(re);
+        val.push_back(im);
+      }
+      ptr[i + 1] = (int)col.size();
+    }
+    H.y_nnz = (int)col.size();
+    H.n_jac = (int)jr.size();
+    H.o_y_ptr = bb.add(ptr);
+    H.o_y_col = bb.add(col);
+    H.o_y_val = bb.add(val);
+    H.o_jac_row = bb.add(jr);
+    H.o_jac_col = bb.add(jc);
+    H.o_jac_y = bb.add(jy);
+  }
+  {
+    const double inf = std::numeric_limits<double>::infinity();
+    std::vector<int> ctrl;
+    ctrl.insert(ctrl.end(), gens.begin(), gens.end());
+    ctrl.insert(ctrl.end(), dess.begin(), dess.end());
+    std::vector<double> rows((size_t)H.n_ctrl * 3 * ANM_MAX_ROWS, 0.0);
+    for (int c = 0; c < H.n_ctrl; ++c) {
+      const double* P = net->dev_param + (size_t)ctrl[c] * ANM_DEV_NPARAM;
+      double* a = &rows[(size_t)c * 3 * ANM_MAX_ROWS];
+      double* b = a + ANM_MAX_ROWS;
+      double* h = b + ANM_MAX_ROWS;
+      for (int k = 0; k < ANM_MAX_ROWS; ++k) h[k] = inf;
+      if (c < H.n_gen) { /* Generator.map_pq rows, devices.py:294-296 */
+        const double A[7][3] = {{-1, 0, -P[ANM_DP_PMIN]}, {1, 0, P[ANM_DP_PMAX]}, {1, 0, P[ANM_DP_PMAX]},
+                                {0, -1, -P[ANM_DP_QMIN]}, {0, 1, P[ANM_DP_QMAX]},
+                                {-P[ANM_DP_TAU1], 1, P[ANM_DP_RHO1]}, {P[ANM_DP_TAU2], -1, -P[ANM_DP_RHO2]}};
+        for (int k = 0; k < 7; ++k) a[k] = A[k][0], b[k] = A[k][1], h[k] = A[k][2];
+      } else { /* StorageUnit.map_pq rows, devices.py:486-514 (rows 8, 9 depend on the SoC) */
+        const double A[10][3] = {{-1, 0, -P[ANM_DP_PMIN]}, {1, 0, P[ANM_DP_PMAX]}, {0, -1, -P[ANM_DP_QMIN]},
+                                 {0, 1, P[ANM_DP_QMAX]}, {-P[ANM_DP_TAU1], 1, P[ANM_DP_RHO1]},
+                                 {P[ANM_DP_TAU2], -1, -P[ANM_DP_RHO2]}, {P[ANM_DP_TAU3], -1, -P[ANM_DP_RHO3]},
+                                 {-P[ANM_DP_TAU4], 1, P[ANM_DP_RHO4]}, {-1, 0, 0.0}, {1, 0, 0.0}};
+        for (int k = 0; k < 10; ++k) a[k] = A[k][0], b[k] = A[k][1], h[k] = A[k][2];
+      }
+    }
+    H.o_ctrl_dev = bb.add(ctrl);
+    H.o_ctrl_rows = bb.add(rows);
+  }
+  {
+    auto pack = [&](int n, const anm_var_spec* v, std::vector<int>& off, std::vector<double>& mul,
+                    std::vector<double>& dv, std::vector<double>& lo, std::vector<double>& hi) -> int {
+      for (int k = 0; k < n; ++k) {
+        if (v[k].quantity < 0 || v[k].quantity >= ANM_NQUANTITY) return fail(ANM_E_INVALID, "var %d: bad quantity", k);
+        if (v[k].index < 0 || v[k].index >= var_limit(H, v[k].quantity)) return fail(ANM_E_INVALID, "var %d: bad index", k);
+        if (v[k].quantity == ANM_Q_BUS_V_ANG || v[k].quantity == ANM_Q_BUS_I_ANG || v[k].quantity == ANM_Q_BRANCH_I_ANG)
+          H.need_angles = 1;
+        off.push_back(full_offset(H, v[k].quantity) + v[k].index);
+        mul.push_back(v[k].mul); dv.push_back(v[k].div); lo.push_back(v[k].low); hi.push_back(v[k].high);
+      }
+      return 0;
+    };
+    std::vector<int> so, oo;
+    std::vector<double> sm, sd, sl, sh, om, od, ol, oh;
+    if (int rc = pack(env->n_state, env->state_vars, so, sm, sd, sl, sh)) return rc;
+    if (int rc = pack(env->n_obs, env->obs_vars, oo, om, od, ol, oh)) return rc;
+    H.o_sv_off = bb.add(so); H.o_sv_mul = bb.add(sm); H.o_sv_div = bb.add(sd);
+    H.o_ov_off = bb.add(oo); H.o_ov_mul = bb.add(om); H.o_ov_div = bb.add(od);
+    H.o_ov_low = bb.add(ol); H.o_ov_high = bb.add(oh);
+  }
+  {
+    std::vector<double> table;
+    if (H.table_len > 0) table.assign(env->table, env->table + (size_t)H.table_len * (H.n_load + H.n_gen));
+    H.o_table = bb.add(table);
+    std::vector<int> pi, pj;
+    for (int j = 1; j < ANM_MAX_ROWS; ++j)
+      for (int i = 0; i < j; ++i) pi.push_back(i), pj.push_back(j);
+    H.o_pair_i = bb.add(pi);
+    H.o_pair_j = bb.add(pj);
+  }
+  /* per-env shared-memory workspace (doubles) */
+  {
+    int w = 0;
+    auto take = [&](int n) { int o = w; w += (n + 1) / 2 * 2; return o; };
+    const int M = H.n_unk;
+    H.w_in_pl = take(H.n_load); H.w_in_pp = take(H.n_gen); H.w_in_ps = take(H.n_ctrl); H.w_in_qs = take(H.n_ctrl);
+    H.w_soc = take(H.n_des); H.w_aux = take(K);
+    H.w_devp = take(D); H.w_devq = take(D); H.w_ppot = take(D); H.w_busp = take(N); H.w_busq = take(N);
+    H.w_x = take(M); H.w_vre = take(N); H.w_vim = take(N); H.w_ere = take(N); H.w_eim = take(N);
+    H.w_ire = take(N); H.w_iim = take(N);
+    H.w_J = take(M * (M + 1)); H.w_rowh = take(ANM_MAX_ROWS);
+    H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
+    H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
+    H.ws_doubles = (w + 15) / 16 * 16;
+  }
+  bb.buf.resize((bb.buf.size() + 127) / 128 * 128, 0);
+  H.blob_bytes = (int)bb.buf.size();
+  memcpy(bb.buf.data(), &H, sizeof(H));
+  out.swap(bb.buf);
+  return 0;
+}
+
+typedef void (*kernel_fn)(const AnmLaunch);
+kernel_fn kernel_for(int lpe) {
+  switch (lpe) {
+    case 8: return anm::anm_env_kernel<8>;
+    case 16: return anm::anm_env_kernel<16>;
+    default: return anm::anm_env_kernel<32>;
+  }
+}
+
+int choose_geometry(anm_handle h) {
+  const int M = h->H.n_unk;
+  h->lpe = (M <= 8) ? 8 : (M <= 16 ? 16 : 32);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+  h->num_sms = prop.multiProcessorCount;
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  const size_t fixed = ANM_BLOB_SMEM_OFF + (size_t)h->blob_bytes;
+  const size_t per_env = (size_t)h->H.ws_doubles * sizeof(double);
+  int gpb = ANM_THREADS / h->lpe;
+  while (gpb > 1 && fixed + gpb * per_env > max_smem) gpb /= 2;
+  if (fixed + gpb * per_env > max_smem)
+    return fail(ANM_E_UNSUPPORTED, "network too large: %zu B of shared memory per CTA needed, %zu available",
+                fixed + gpb * per_env, max_smem);
+  h->gpb = gpb;
+  h->smem = (int)(fixed + gpb * per_env);
+  kernel_fn fn = kernel_for(h->lpe);
+  CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, gpb * h->lpe, h->smem));
+  if (per_sm < 1) return fail(ANM_E_UNSUPPORTED, "kernel does not fit on an SM (smem %d B)", h->smem);
+  const int64_t need = (h->B + gpb - 1) / gpb;
+  const int64_t resident = (int64_t)per_sm * h->num_sms;
+  h->grid = (int)(need < resident ? need : resident);
+  return 0;
+}
+
+int launch(anm_handle h, AnmLaunch& p, cudaStream_t st) {
+  p.blob = h->d_blob;
+  p.blob_bytes = h->blob_bytes;
+  p.B = h->B;
+  p.soc = h->d_soc; p.aux = h->d_aux; p.terminated = h->d_term; p.episode = h->d_episode;
+  p.pool = h->pool; p.pool_size = h->pool_size;
+  kernel_for(h->lpe)<<<h->grid, h->gpb * h->lpe, h->smem, st>>>(p);
+  ++h->launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(ANM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int anm_abi_version(void) { return ANM_ABI_VERSION; }
+const char* anm_last_error(void) { return g_err; }
+
+int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num_envs, int device, anm_handle* out) {
+  if (!net || !env || !out) return fail(ANM_E_INVALID, "null argument");
+  if (num_envs < 1) return fail(ANM_E_INVALID, "num_envs must be >= 1");
+  *out = nullptr;
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ANM_E_INVALID, "device %d out of range (%d visible)", device, ndev);
+  anm_handle h = new (std::nothrow) anm_handle_s();
+  if (!h) return fail(ANM_E_NOMEM, "out of host memory");
+  h->device = device;
+  h->B = num_envs;
+  std::vector<unsigned char> blob;
+  int rc = build_blob(net, env, h->H, blob);
+  if (rc) { delete h; return rc; }
+  h->blob_bytes = (int)blob.size();
+  DeviceGuard guard(device);
+  const AnmConstHeader& H = h->H;
+  const size_t B = (size_t)num_envs;
+#define ALLOC(ptr, bytes)                                                                   \
+  do {                                                                                      \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes) ? (bytes) : 16);                    \
+    if (e_ != cudaSuccess) { anm_destroy(h); return fail(ANM_E_CUDA, "cudaMalloc(%s): %s", #ptr, cudaGetErrorString(e_)); } \
+  } while (0)
+  ALLOC(h->d_blob, blob.size());
+  ALLOC(h->d_soc, B * H.n_des * sizeof(double));
+  ALLOC(h->d_aux, B * H.K * sizeof(double));
+  ALLOC(h->d_term, B);
+  ALLOC(h->d_episode, B * sizeof(uint32_t));
+  ALLOC(h->s_action, B * H.n_action * sizeof(double));
+  ALLOC(h->s_nv, B * H.n_next_vars * sizeof(double));
+  ALLOC(h->s_obs, B * H.n_obs * sizeof(double));
+  ALLOC(h->s_reward, B * sizeof(double));
+  ALLOC(h->s_s0, B * H.n_state * sizeof(double));
+  ALLOC(h->s_state, B * H.n_state * sizeof(double));
+  ALLOC(h->s_term, B);
+  ALLOC(h->s_mask, B);
+#undef ALLOC
+  cudaError_t e = cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->d_soc, 0, B * H.n_des * sizeof(double) + (H.n_des ? 0 : 16));
+  if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, B * H.K * sizeof(double) + (H.K ? 0 : 16));
+  if (e == cudaSuccess) e = cudaMemset(h->d_term, 1, B); /* nothing is runnable before the first reset */
+  if (e == cudaSuccess) e = cudaMemset(h->d_episode, 0, B * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { anm_destroy(h); return fail(ANM_E_CUDA, "handle init: %s", cudaGetErrorString(e)); }
+  rc = choose_geometry(h);
+  if (rc) { anm_destroy(h); return rc; }
+  *out = h;
+  return ANM_OK;
+}
+
+int anm_destroy(anm_handle h) {
+  if (!h) return ANM_OK;
+  DeviceGuard guard(h->device);
+  cudaFree(h->d_blob); cudaFree(h->d_soc); cudaFree(h->d_aux); cudaFree(h->d_term); cudaFree(h->d_episode);
+  cudaFree(h->s_action); cudaFree(h->s_nv); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_s0);
+  cudaFree(h->s_state); cudaFree(h->s_term); cudaFree(h->s_mask);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return ANM_OK;
+}
+
+int anm_get_sizes(anm_handle h, anm_sizes* o) {
+  if (!h || !o) return fail(ANM_E_INVALID, "null argument");
+  const AnmConstHeader& H = h->H;
+  o->num_envs = h->B;
+  o->n_bus = H.n_bus; o->n_dev = H.n_dev; o->n_branch = H.n_branch;
+  o->n_load = H.n_load; o->n_gen = H.n_gen; o->n_des = H.n_des;
+  o->n_action = H.n_action; o->n_state = H.n_state; o->n_obs = H.n_obs;
+  o->n_next_vars = H.n_next_vars; o->n_full_state = H.n_full; o->K = H.K;
+  o->lanes_per_env = h->lpe; o->envs_per_block = h->gpb; o->smem_bytes = h->smem;
+  return ANM_OK;
+}
+
+int anm_reset(anm_handle h, const double* s0, const uint8_t* mask, double* obs, double* state, uint8_t* converged,
+              void* stream) {
+  if (!h || !s0 || !obs || !converged) return fail(ANM_E_INVALID, "anm_reset: null argument");
+  DeviceGuard guard(h->device);
+  AnmLaunch p;
+  memset(&p, 0, sizeof(p));
+  p.mode = ANM_MODE_RESET;
+  p.s0 = s0; p.mask = mask; p.obs = obs; p.state = state; p.converged = converged;
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int anm_step(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
+             uint8_t* terminated, const anm_step_extras* ex, void* stream) {
+  if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step: null argument");
+  if (!next_vars && h->H.table_len == 0)
+    return fail(ANM_E_INVALID, "anm_step: next_vars is NULL but the environment has no built-in table");
+  DeviceGuard guard(h->device);
+  AnmLaunch p;
+  memset(&p, 0, sizeof(p));
+  p.mode = ANM_MODE_STEP;
+  p.action = action; p.next_vars = next_vars; p.obs = obs; p.reward = reward; p.term_out = terminated;
+  if (ex) { p.state = ex->state; p.e_loss = ex->e_loss; p.penalty = ex->penalty; p.n_iter = ex->n_iter; p.full_state = ex->full_state; }
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int anm_set_autoreset_pool(anm_handle h, const double* pool, int64_t pool_size) {
+  if (!h || pool_size < 0 || (pool_size > 0 && !pool)) return fail(ANM_E_INVALID, "anm_set_autoreset_pool: bad argument");
+  h->pool = pool_size ? pool : nullptr;
+  h->pool_size = pool_size;
+  return ANM_OK;
+}
+
+int anm_transition(anm_handle h, const double* p_load, const double* p_pot, const double* p_set, const double* q_set,
+                   double* full_state, double* reward, double* e_loss, double* penalty, uint8_t* converged,
+                   void* stream) {
+  if (!h) return fail(ANM_E_INVALID, "anm_transition: null handle");
+  const AnmConstHeader& H = h->H;
+  if ((H.n_load && !p_load) || (H.n_gen && !p_pot) || (H.n_ctrl && (!p_set || !q_set)))
+    return fail(ANM_E_INVALID, "anm_transition: missing input");
+  DeviceGuard guard(h->device);
+  AnmLaunch p;
+  memset(&p, 0, sizeof(p));
+  p.mode = ANM_MODE_TRANSITION;
+  p.p_load = p_load; p.p_pot = p_pot; p.p_set = p_set; p.q_set = q_set;
+  p.full_state = full_state; p.reward = reward; p.e_loss = e_loss; p.penalty = penalty; p.converged = converged;
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int anm_get_state(anm_handle h, double* soc, double* aux, uint8_t* term, void* stream) {
+  if (!h) return fail(ANM_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = (size_t)h->B;
+  if (soc && h->H.n_des) CUDA_TRY(cudaMemcpyAsync(soc, h->d_soc, B * h->H.n_des * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (aux && h->H.K) CUDA_TRY(cudaMemcpyAsync(aux, h->d_aux, B * h->H.K * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (term) CUDA_TRY(cudaMemcpyAsync(term, h->d_term, B, cudaMemcpyDeviceToDevice, st));
+  return ANM_OK;
+}
+
+int anm_set_state(anm_handle h, const double* soc, const double* aux, const uint8_t* term, void* stream) {
+  if (!h) return fail(ANM_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = (size_t)h->B;
+  if (soc && h->H.n_des) CUDA_TRY(cudaMemcpyAsync(h->d_soc, soc, B * h->H.n_des * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (aux && h->H.K) CUDA_TRY(cudaMemcpyAsync(h->d_aux, aux, B * h->H.K * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (term) CUDA_TRY(cudaMemcpyAsync(h->d_term, term, B, cudaMemcpyDeviceToDevice, st));
+  return ANM_OK;
+}
+
+int anm_step_host(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
+                  uint8_t* terminated) {
+  if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_host: null argument");
+  DeviceGuard guard(h->device);
+  const AnmConstHeader& H = h->H;
+  const size_t B = (size_t)h->B;
+  cudaStream_t st = h->stream;
+  CUDA_TRY(cudaMemcpyAsync(h->s_action, action, B * H.n_action * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (next_vars) CUDA_TRY(cudaMemcpyAsync(h->s_nv, next_vars, B * H.n_next_vars * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = anm_step(h, h->s_action, next_vars ? h->s_nv : nullptr, h->s_obs, h->s_reward, h->s_term, nullptr, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(obs, h->s_obs, B * H.n_obs * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(reward, h->s_reward, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(terminated, h->s_term, B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return ANM_OK;
+}
+
+int anm_reset_host(anm_handle h, const double* s0, const uint8_t* mask, double* obs, double* state, uint8_t* converged) {
+  if (!h || !s0 || !obs || !converged) return fail(ANM_E_INVALID, "anm_reset_host: null argument");
+  DeviceGuard guard(h->device);
+  const AnmConstHeader& H = h->H;
+  const size_t B = (size_t)h->B;
+  cudaStream_t st = h->stream;
+  CUDA_TRY(cudaMemcpyAsync(h->s_s0, s0, B * H.n_state * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (mask) CUDA_TRY(cudaMemcpyAsync(h->s_mask, mask, B, cudaMemcpyHostToDevice, st));
+  /* rows of unselected envs are left untouched: pre-load the caller's buffers */
+  CUDA_TRY(cudaMemcpyAsync(h->s_obs, obs, B * H.n_obs * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (state) CUDA_TRY(cudaMemcpyAsync(h->s_state, state, B * H.n_state * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(h->s_term, 0, B, st));
+  int rc = anm_reset(h, h->s_s0, mask ? h->s_mask : nullptr, h->s_obs, state ? h->s_state : nullptr, h->s_term, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(obs, h->s_obs, B * H.n_obs * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (state) CUDA_TRY(cudaMemcpyAsync(state, h->s_state, B * H.n_state * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(converged, h->s_term, B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return ANM_OK;
+}
+
+int64_t anm_launch_count(anm_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

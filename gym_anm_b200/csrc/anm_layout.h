@@ -1,0 +1,50 @@
+/*
+ * anm_layout.h -- layout of the per-network constant blob and of the per-environment
+ * shared-memory workspace.  Shared by the host builder (anm_capi.cu) and the kernels
+ * (anm_kernels.cuh).
+ *
+ * The blob lives once in global memory; every CTA stages it into shared memory with one
+ * TMA bulk copy (cp.async.bulk.shared::cluster.global) at kernel entry, so all per-step
+ * constant reads (Y-bus, polygon rows, 96-slot tables, observation map) are shared-memory
+ * broadcasts.  All offsets are in BYTES from the start of the blob and 16-byte aligned.
+ */
+#pragma once
+#include <stdint.h>
+
+#define ANM_MAX_ROWS 10  /* half-planes per device polygon (devices.py:486-514) */
+#define ANM_NPAIRS 45    /* ANM_MAX_ROWS choose 2 */
+#define ANM_NCAND (1 + ANM_MAX_ROWS + ANM_NPAIRS)
+
+enum { ANM_MODE_STEP = 0, ANM_MODE_RESET = 1, ANM_MODE_TRANSITION = 2 };
+
+struct AnmConstHeader {
+  /* sizes */
+  int32_t n_bus, n_dev, n_branch, n_load, n_gen, n_des, n_ctrl, K;
+  int32_t n_unk;       /* 2 (n_bus - 1) Newton-Raphson unknowns */
+  int32_t n_action, n_state, n_obs, n_next_vars, n_full;
+  int32_t table_len, y_nnz, n_jac; /* n_jac: Y entries with row, col >= 1 */
+  int32_t need_angles;  /* some state/obs entry is an angle */
+  int32_t blob_bytes;
+  int32_t ws_doubles;   /* per-env workspace size (doubles) */
+  double base_mva, delta_t, lamb, gamma, clip_e, clip_pen, term_reward;
+  /* blob offsets (bytes) */
+  int32_t o_vmin, o_vmax;                    /* double[n_bus]                                  */
+  int32_t o_dev_bus, o_dev_type, o_dev_slot; /* int[n_dev]  (slot = index inside its category) */
+  int32_t o_dev_param;                       /* double[n_dev][16]                              */
+  int32_t o_bus_dev_ptr, o_bus_dev_idx;      /* int[n_bus+1], int[n_dev]  devices of each bus  */
+  int32_t o_br_from, o_br_to;                /* int[n_branch]                                  */
+  int32_t o_br_coef;                         /* double[n_branch][10]: a_ff a_ft a_tf a_tt (re,im) rate pad */
+  int32_t o_y_ptr, o_y_col, o_y_val;         /* CSR of Y: int[n_bus+1], int[nnz], double[nnz][2] */
+  int32_t o_jac_row, o_jac_col, o_jac_y;     /* int[n_jac] each: bus b>=1, bus j>=1, index into y_val */
+  int32_t o_ctrl_dev;                        /* int[n_ctrl] device position (gens then storage) */
+  int32_t o_ctrl_rows;                       /* double[n_ctrl][3][ANM_MAX_ROWS]: a[], b[], h[]  */
+  int32_t o_sv_off, o_sv_mul, o_sv_div;      /* state vars: int[], double[], double[]          */
+  int32_t o_ov_off, o_ov_mul, o_ov_div, o_ov_low, o_ov_high; /* obs vars                       */
+  int32_t o_table;                           /* double[table_len][n_load+n_gen]                */
+  int32_t o_pair_i, o_pair_j;                /* int[ANM_NPAIRS]                                */
+  /* per-env workspace offsets (in doubles) */
+  int32_t w_in_pl, w_in_pp, w_in_ps, w_in_qs, w_soc, w_aux, w_devp, w_devq, w_ppot, w_busp, w_busq;
+  int32_t w_x, w_vre, w_vim, w_ere, w_eim, w_ire, w_iim, w_J, w_rowh;
+  int32_t w_brp, w_brq, w_brs, w_brire, w_briim, w_full, w_s0;
+  int32_t pad_;
+};
