@@ -1,0 +1,142 @@
+"""`NativeBatch`: a thin, typed wrapper of one `anm_handle` over torch CUDA tensors.
+
+This is the only module that touches the C ABI at run time.  All tensors are float64 /
+uint8 / int32 CUDA tensors on the handle's device; calls are enqueued on the current torch
+CUDA stream and do not synchronise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from .errors import NativeLibraryError
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class NativeBatch:
+    def __init__(self, spec, num_envs, device=None):
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("a CUDA device is required (there is no CPU fallback)")
+        self.lib = _capi.load_library()
+        self.spec = spec
+        self.B = int(num_envs)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise NativeLibraryError("device must be a CUDA device, got %s" % self.device)
+        net, env, keep = spec.descs()
+        self._keep = keep
+        h = C.c_void_p()
+        _capi.check(self.lib.anm_create(C.byref(net), C.byref(env), C.c_int64(self.B), self.device.index or 0, C.byref(h)),
+                    self.lib)  # fmt: skip
+        self.h = h
+        sz = _capi.Sizes()
+        _capi.check(self.lib.anm_get_sizes(self.h, C.byref(sz)), self.lib)
+        self.sizes = {k: getattr(sz, k) for k, _ in sz._fields_}
+        self.A, self.S, self.O = sz.n_action, sz.n_state, sz.n_obs
+        self.NV, self.F, self.K = sz.n_next_vars, sz.n_full_state, sz.K
+        self.n_load, self.n_gen, self.n_des = sz.n_load, sz.n_gen, sz.n_des
+        self._pool = None
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                self.lib.anm_destroy(h)
+            except Exception:  # noqa: BLE001
+                pass
+
+    # -- helpers ---------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _f64(self, t, cols):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            t = torch.as_tensor(np.asarray(t, dtype=np.float64) if not isinstance(t, torch.Tensor) else t,
+                                dtype=torch.float64, device=self.device).contiguous()  # fmt: skip
+        if tuple(t.shape) != (self.B, cols):
+            raise ValueError("expected a tensor of shape (%d, %d), got %s" % (self.B, cols, tuple(t.shape)))
+        return t
+
+    # -- C-ABI calls -------------------------------------------------------------------
+    def reset(self, s0, mask=None, obs=None, state=None, converged=None):
+        s0 = self._f64(s0, self.S)
+        obs = self.empty(self.B, self.O) if obs is None else obs
+        state = self.empty(self.B, self.S) if state is None else state
+        converged = torch.zeros(self.B, dtype=torch.uint8, device=self.device) if converged is None else converged
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        _capi.check(self.lib.anm_reset(self.h, _ptr(s0), _ptr(mask), _ptr(obs), _ptr(state), _ptr(converged),
+                                       self._stream()), self.lib)  # fmt: skip
+        return obs, state, converged
+
+    def step(self, action, next_vars=None, out=None, extras=None):
+        """out = (obs, reward, terminated) preallocated tensors or None; extras = dict of
+        optional preallocated tensors among state / e_loss / penalty / n_iter / full_state."""
+        action = self._f64(action, self.A)
+        nv = None if next_vars is None else self._f64(next_vars, self.NV)
+        if out is None:
+            out = (self.empty(self.B, self.O), self.empty(self.B), self.empty(self.B, dtype=torch.uint8))
+        obs, reward, term = out
+        ex = None
+        if extras:
+            ex = _capi.StepExtras()
+            for k in ("state", "e_loss", "penalty", "n_iter", "full_state"):
+                t = extras.get(k)
+                setattr(ex, k, None if t is None else t.data_ptr())
+        _capi.check(self.lib.anm_step(self.h, _ptr(action), _ptr(nv), _ptr(obs), _ptr(reward), _ptr(term),
+                                      None if ex is None else C.byref(ex), self._stream()), self.lib)  # fmt: skip
+        return obs, reward, term
+
+    def transition(self, p_load, p_pot, p_set, q_set):
+        n_ctrl = self.n_gen + self.n_des
+        p_load, p_pot = self._f64(p_load, self.n_load), self._f64(p_pot, self.n_gen)
+        p_set, q_set = self._f64(p_set, n_ctrl), self._f64(q_set, n_ctrl)
+        full = self.empty(self.B, self.F - self.K)
+        r, e, pe = self.empty(self.B), self.empty(self.B), self.empty(self.B)
+        conv = self.empty(self.B, dtype=torch.uint8)
+        _capi.check(self.lib.anm_transition(self.h, _ptr(p_load), _ptr(p_pot), _ptr(p_set), _ptr(q_set), _ptr(full),
+                                            _ptr(r), _ptr(e), _ptr(pe), _ptr(conv), self._stream()), self.lib)  # fmt: skip
+        return full, r, e, pe, conv
+
+    def get_state(self):
+        soc, aux = self.empty(self.B, self.n_des), self.empty(self.B, self.K)
+        term = self.empty(self.B, dtype=torch.uint8)
+        _capi.check(self.lib.anm_get_state(self.h, _ptr(soc), _ptr(aux), _ptr(term), self._stream()), self.lib)
+        return soc, aux, term
+
+    def set_state(self, soc=None, aux=None, terminated=None):
+        f = lambda t, c: None if t is None else self._f64(t, c)  # noqa: E731
+        soc, aux = f(soc, self.n_des), f(aux, self.K)
+        if terminated is not None:
+            terminated = torch.as_tensor(terminated, device=self.device).to(torch.uint8).contiguous()
+        _capi.check(self.lib.anm_set_state(self.h, _ptr(soc), _ptr(aux), _ptr(terminated), self._stream()), self.lib)
+
+    def set_autoreset_pool(self, pool):
+        if pool is None:
+            self._pool = None
+            _capi.check(self.lib.anm_set_autoreset_pool(self.h, None, 0), self.lib)
+            return
+        pool = torch.as_tensor(pool, dtype=torch.float64, device=self.device).contiguous()
+        assert pool.ndim == 2 and pool.shape[1] == self.S
+        self._pool = pool  # keep alive: the library does not copy it
+        _capi.check(self.lib.anm_set_autoreset_pool(self.h, _ptr(pool), pool.shape[0]), self.lib)
+
+    def step_host(self, action, next_vars, obs, reward, terminated):
+        """NumPy / pinned-host path: H2D + step + D2H inside the library, synchronous."""
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())  # noqa: E731
+        _capi.check(self.lib.anm_step_host(self.h, p(action), p(next_vars), p(obs), p(reward), p(terminated)), self.lib)
+
+    def reset_host(self, s0, mask, obs, state, converged):
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())  # noqa: E731
+        _capi.check(self.lib.anm_reset_host(self.h, p(s0), p(mask), p(obs), p(state), p(converged)), self.lib)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.anm_launch_count(self.h))

@@ -26,5 +26,12 @@ def transition_spec(g):
 
 
 def rel_err(a, b, atol=1e-9):
+    """max relative error beyond an absolute floor: (|a-b| - atol)+ / |b|.  `atol` covers
+    quantities that are exactly 0 in the reference (SURVEY.md section 8c parity definition)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return float(np.max(np.abs(a - b) / (atol + np.abs(b)))) if a.size else 0.0
+    if a.size == 0:
+        return 0.0
+    if not np.array_equal(np.isnan(a), np.isnan(b)):
+        return float("inf")
+    d = np.nan_to_num(np.abs(a - b), nan=0.0, posinf=0.0) * ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    return float(np.max(np.maximum(d - atol, 0.0) / np.maximum(np.abs(np.nan_to_num(b, posinf=1.0, neginf=1.0)), 1e-300)))
