@@ -18,12 +18,13 @@ from .networks import anm6_network, anm6easy_tables
 
 
 class BatchedANM6Easy(BatchedANMEnv):
-    def __init__(self, num_envs=1, device=None, seed=None, validate_actions=True):
+    def __init__(self, num_envs=1, device=None, seed=None, validate_actions=True, env_offset=0):
         self.P_loads, self.P_maxs = anm6easy_tables()
         delta_t = 0.25
         table = np.ascontiguousarray(np.vstack((self.P_loads, self.P_maxs)).T)
         super().__init__(anm6_network(), "state", 1, delta_t, 0.995, 100, np.array([[0, 24 / delta_t - 1]]), (1, 100),
-                         seed, num_envs=num_envs, device=device, table=table, validate_actions=validate_actions)  # fmt: skip
+                         seed, num_envs=num_envs, device=device, table=table, validate_actions=validate_actions,
+                         env_offset=env_offset)  # fmt: skip
 
     def init_state(self):
         n_dev, n_gen, n_des = 7, 2, 1

@@ -31,9 +31,10 @@ class BatchedANMEnv:
     metadata = {"render_modes": []}
 
     def __init__(self, network, observation, K, delta_t, gamma, lamb, aux_bounds=None, costs_clipping=None, seed=None,
-                 *, num_envs=1, device=None, table=None, validate_actions=True):  # fmt: skip
+                 *, num_envs=1, device=None, table=None, validate_actions=True, env_offset=0):  # fmt: skip
         self.spec = HostEnvSpec(network, observation, K, delta_t, gamma, lamb, aux_bounds, costs_clipping, table=table)
         self.num_envs = int(num_envs)
+        self.env_offset = int(env_offset)  # global index of local env 0 (multi-GPU sharding)
         self.K, self.gamma, self.lamb, self.delta_t, self.aux_bounds = K, gamma, lamb, delta_t, aux_bounds
         self.costs_clipping = self.spec.costs_clipping
         self.native = NativeBatch(self.spec, self.num_envs, device)
@@ -108,12 +109,12 @@ class BatchedANMEnv:
         self._env_index = 0
         return out
 
-    # ---- RNG (one PCG64 stream per env, env i seeded with seed + i) ------------------------------
+    # ---- RNG (one PCG64 stream per env; global env g is seeded with seed + g, for any sharding) ----
     def _seed_rngs(self, seed):
         if seed is None:
             self._rngs = [_make_rng(None) for _ in range(self.num_envs)]
         else:
-            self._rngs = [_make_rng(int(seed) + i) for i in range(self.num_envs)]
+            self._rngs = [_make_rng(int(seed) + self.env_offset + i) for i in range(self.num_envs)]
 
     @property
     def np_random(self):

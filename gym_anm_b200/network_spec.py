@@ -346,7 +346,7 @@ def check_network_specs(network):
     slack_bus = bus[np.where(np.array(bus_types) == 0)[0], BUS_H["BUS_ID"]]
     slack_dev_bus = dev[np.where(np.array(dev_types) == 0)[0], DEV_H["BUS_ID"]]
     if slack_bus != slack_dev_bus:
-        raise DeviceSpecError("The slack device sits at bus %d but the slack bus is %d." % (slack_dev_bus, slack_bus))
+        raise DeviceSpecError("The slack device sits at bus {} but the slack bus is {}.".format(slack_dev_bus, slack_bus))
     bus_ids = list(bus[:, BUS_H["BUS_ID"]])
     if len(set(bus_ids)) != len(bus_ids):
         raise BusSpecError("The buses should all have unique IDs.")

@@ -1,0 +1,201 @@
+"""CPU tests of the host side: network compile / validation semantics, env spec, the C-ABI
+library's exported symbols, sharding + gloo all-gather (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gym_anm_b200 import _capi, errors
+from gym_anm_b200.env_spec import HostEnvSpec, anm6easy_spec
+from gym_anm_b200.network_spec import CompiledNetwork
+from gym_anm_b200.networks import anm6_network, synth_feeder_network
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_anm6_compile_known_values():
+    cn = CompiledNetwork(anm6_network(), 0.25, 100)
+    assert (cn.N_bus, cn.N_device, cn.N_branch, cn.N_load, cn.N_non_slack_gen, cn.N_des) == (6, 7, 5, 3, 2, 1)
+    d2, d6 = cn.devices[2], cn.devices[6]
+    assert (d2.tau_1, d2.tau_2, d2.rho_1, d2.rho_2) == pytest.approx((-1.5, 1.5, 0.6, -0.6))
+    assert (d6.tau_1, d6.tau_2, d6.tau_3, d6.tau_4) == pytest.approx((-1.25, 1.25, -1.25, 1.25))
+    Y = cn.Y_bus_dense
+    assert Y[0, 0] == pytest.approx(0.106988 - 5.450463j, rel=1e-5) and Y[0, 1] == -Y[0, 0]
+    assert np.count_nonzero(Y) == 16
+    spec = anm6easy_spec()
+    assert spec.state_N == 18 and len(spec.obs_specs) == 18
+    np.testing.assert_array_equal(spec.action_low, [0, 0, -30, -50, -50, -50])
+    np.testing.assert_array_equal(spec.action_high, [30, 50, 30, 50, 50, 50])
+    np.testing.assert_allclose(spec.obs_low, [-200, -10, 0, -30, 0, -30, -50, -200, -2, -30, -6, -50, -6, -50, 0, 0, 0, 0], rtol=1e-15)
+    np.testing.assert_allclose(spec.obs_high, [200, 0, 30, 0, 50, 0, 50, 200, 0, 30, 0, 50, 0, 50, 100, 30, 50, 95], rtol=1e-15)
+
+
+def test_admittance_with_tap_and_shift():
+    """Known answer of the reference's test_simulator_basics.py:48-67 (tap=2, 90 degree shift)."""
+    net = {
+        "baseMVA": 10,
+        "bus": np.array([[0, 1, 50, 1.1, 0.9], [2, 1, 50, 1.1, 0.9], [1, 0, 100, 1.0, 1.0]]),
+        "branch": np.array([[0, 1, 0.1, 0.2, 0.3, 20, 1, 90], [1, 2, 0.4, 0.5, 0.6, 20, 2, 0]]),
+        "device": np.array([
+            [1, 0, -1, 0.2, 0, -10, None, None, None, None, None, None, None, None, None],
+            [0, 1, 0, None, 200, -200, 200, -200, None, None, None, None, None, None, None],
+            [2, 2, 2, None, 30, 0, 30, -30, None, None, None, None, None, None, None],
+            [3, 2, 3, None, 50, -50, 50, -50, None, None, None, None, 100, 0, 0.9]]),
+    }  # fmt: skip
+    cn = CompiledNetwork(net, 1, 100)
+    y01, y01s, t01 = 1 / (0.1 + 0.2j), 0.3j / 2, np.exp(1j * np.pi / 2)
+    y12, y12s = 1 / (0.4 + 0.5j), 0.6j / 2
+    Y = np.array([[(y01 + y01s), -y01 / np.conj(t01), 0], [-y01 / t01, (y12 + y12s) / 4 + y01 + y01s, -y12 / 2],
+                  [0, -y12 / 2, y12 + y12s]])  # fmt: skip
+    np.testing.assert_allclose(cn.Y_bus_dense, Y, rtol=1e-12)
+    assert list(cn.devices) == [0, 1, 2, 3] and list(cn.branches) == [(0, 1), (1, 2)]
+    assert [cn.buses[i].p_min * 10 for i in (0, 1, 2)] == pytest.approx([-10, -200, -50])
+    with pytest.raises(errors.BusSpecError):  # the batched solver needs slack == bus 0 (solve_load_flow.py:171)
+        cn.flat()
+
+
+@pytest.mark.parametrize("mutate,exc", [
+    (lambda n: n.__setitem__("baseMVA", 0), errors.BaseMVAError),
+    (lambda n: n["bus"].__setitem__((1, 1), 0), errors.BusSpecError),                 # two slack buses
+    (lambda n: n["device"].__setitem__((1, 2), 0), errors.DeviceSpecError),           # two slack devices
+    (lambda n: n["device"].__setitem__((0, 1), 3), errors.DeviceSpecError),           # slack dev not at slack bus
+    (lambda n: n["branch"].__setitem__((1, slice(0, 2)), [1, 0]), errors.BranchSpecError),  # parallel branch
+    (lambda n: n["branch"].__setitem__((0, 2), -0.1), errors.BranchSpecError),        # r < 0
+    (lambda n: n["branch"].__setitem__((0, slice(2, 4)), [0, 0]), errors.BranchSpecError),  # r = x = 0
+    (lambda n: n["branch"].__setitem__((0, 6), 0), errors.BranchSpecError),           # tap <= 0
+    (lambda n: n["device"].__setitem__((1, 3), None), errors.LoadSpecError),          # load without Q/P
+    (lambda n: n["device"].__setitem__((1, 4), 5), errors.LoadSpecError),             # load with Pmax > 0
+    (lambda n: n["device"].__setitem__((2, 4), -1), errors.GenSpecError),             # gen Pmax < 0
+    (lambda n: n["device"].__setitem__((2, 8), 40), errors.GenSpecError),             # P+ > Pmax
+    (lambda n: n["device"].__setitem__((6, 12), None), errors.StorageSpecError),      # storage without SoC max
+    (lambda n: n["device"].__setitem__((6, 14), 1.5), errors.StorageSpecError),       # eff > 1
+    (lambda n: n["device"].__setitem__((6, 5), 10), errors.StorageSpecError),         # storage Pmin > 0
+    (lambda n: n["bus"].__setitem__((2, 3), 0.5), errors.BusSpecError),               # vmax < vmin
+])  # fmt: skip
+def test_network_validation_errors(mutate, exc):
+    net = anm6_network()
+    mutate(net)
+    with pytest.raises(exc):
+        CompiledNetwork(net, 0.25, 100)
+
+
+def test_env_arg_validation_and_obs_spec():
+    net = anm6_network()
+    with pytest.raises(errors.ArgsError):
+        HostEnvSpec(net, "state", -1, 0.25, 0.9, 100)
+    with pytest.raises(errors.ArgsError):
+        HostEnvSpec(net, "state", 1, 0.25, 1.5, 100, np.array([[0, 1]]))
+    with pytest.raises(errors.ArgsError):
+        HostEnvSpec(net, 3.0, 0, 0.25, 0.9, 100)
+    with pytest.raises(errors.ObsNotSupportedError):
+        HostEnvSpec(net, [("bogus", "all")], 0, 0.25, 0.9, 100)
+    with pytest.raises(errors.UnitsNotSupportedError):
+        HostEnvSpec(net, [("bus_p", "all", "kV")], 0, 0.25, 0.9, 100)
+    with pytest.raises(errors.ObsSpaceError):
+        HostEnvSpec(net, [("dev_p", [99], "MW")], 0, 0.25, 0.9, 100)
+    # list-style observation (reference tests/envs/custom_obs_space.py:33-52)
+    s = HostEnvSpec(net, [("bus_p", "all", "MW"), ("dev_q", [0, 2], "pu"), ("branch_s", "all", "pu"), ("bus_v_ang", [1])],
+                    0, 0.25, 0.9, 100)  # fmt: skip
+    assert s.obs_values[0] == ("bus_p", [0, 1, 2, 3, 4, 5], "MW") and s.obs_values[3] == ("bus_v_ang", [1], "degree")
+    assert len(s.obs_specs) == 6 + 2 + 5 + 1
+    np.testing.assert_allclose(s.obs_low[:8], [-200, 0, 0, -10, -30, -80, -2, -0.3])
+    assert np.all(np.isinf(s.obs_low[8:13])) and s.obs_low[13] == -180
+    assert s.obs_specs["mul"][13] == 180.0 and s.obs_specs["div"][13] == np.pi
+
+
+def test_synth30_passes_validators():
+    cn = CompiledNetwork(synth_feeder_network(), 0.25, 100)
+    assert (cn.N_bus, cn.N_load, cn.N_non_slack_gen, cn.N_des) == (30, 10, 6, 3)
+    cn.flat()
+
+
+def test_capi_library_exports_every_declared_symbol():
+    """The C-ABI library loads (no GPU needed) and exports each function of include/anm_b200.h."""
+    hdr = open(os.path.join(ROOT, "include", "anm_b200.h")).read()
+    declared = set(re.findall(r"\b(anm_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_capi.EXPORTED_SYMBOLS)
+    lib = _capi.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.anm_abi_version() == 1
+    # create must fail loudly (not fall back) without a usable device / with bad arguments
+    spec = anm6easy_spec()
+    net, env, keep = spec.descs()
+    h = ctypes.c_void_p()
+    rc = lib.anm_create(ctypes.byref(net), ctypes.byref(env), 0, 0, ctypes.byref(h))
+    assert rc != 0 and lib.anm_last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "gym_anm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "anm_oracle" not in src and "anm_numpy" not in src and "ref_loader" not in src, f
+
+
+def test_missing_extension_fails_loudly(tmp_path):
+    with pytest.raises(errors.NativeLibraryError):
+        _capi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_shard_slices():
+    from gym_anm_b200.distributed import shard_slice
+
+    for n, w in ((65536, 8), (10, 4), (7, 8), (4096, 1)):
+        parts = [shard_slice(n, r, w) for r in range(w)]
+        assert parts[0].start == 0 and parts[-1].stop == n
+        assert all(a.stop == b.start for a, b in zip(parts, parts[1:]))
+        sizes = [p.stop - p.start for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+import numpy as np, torch, torch.distributed as dist
+import anm_oracle, anm_numpy
+from gym_anm_b200.distributed import shard_slice, all_gather_rows
+from gym_anm_b200.env_spec import anm6easy_spec
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, B = dist.get_rank(), 11                    # uneven shards on purpose (6 + 5)
+spec = anm6easy_spec()
+def rollout(lo, hi):
+    env = anm_oracle.OracleEnv(spec, hi - lo)      # CPU stand-in for the per-rank CUDA batch
+    s0 = np.stack([anm_numpy.anm6easy_init_state(spec, np.random.Generator(np.random.PCG64(np.random.SeedSequence(2020 + g)))) for g in range(lo, hi)])
+    obs, _, _ = env.reset(s0)
+    for t in range(5):
+        a = np.stack([np.random.default_rng(10**6 + g * 100 + t).uniform(spec.action_low, spec.action_high) for g in range(lo, hi)])
+        obs, r, term, _ = env.step(a)
+    return obs
+sl = shard_slice(B, rank, 2)
+mine = torch.as_tensor(rollout(sl.start, sl.stop))
+full = all_gather_rows(mine)
+if rank == 0:
+    want = torch.as_tensor(rollout(0, B))
+    assert full.shape == want.shape and torch.equal(full, want), "shard-equivalence failed"
+    print("SHARD_OK")
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_gloo_world2_shard_equivalence(tmp_path):
+    """N>1 host logic on CPU: global-index seeding + all-gather == the single-process batch."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]  # fmt: skip
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_OK" in outs[0]
