@@ -116,6 +116,7 @@ _PROTOS = {
     "anm_set_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 3 + [C.c_void_p]),
     "anm_step_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "anm_reset_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
+    "anm_host_stream": (C.c_void_p, [C.c_void_p]),
     "anm_launch_count": (C.c_int64, [C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

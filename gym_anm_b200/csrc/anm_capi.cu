@@ -524,6 +524,8 @@ int anm_reset_host(anm_handle h, const double* s0, const uint8_t* mask, double* 
   return ANM_OK;
 }
 
+void* anm_host_stream(anm_handle h) { return h ? (void*)h->stream : nullptr; }
+
 int64_t anm_launch_count(anm_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"

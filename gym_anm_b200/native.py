@@ -138,5 +138,10 @@ class NativeBatch:
         _capi.check(self.lib.anm_reset_host(self.h, p(s0), p(mask), p(obs), p(state), p(converged)), self.lib)
 
     @property
+    def host_stream(self):
+        """torch view of the library's own stream (the one step_host / reset_host run on)."""
+        return torch.cuda.ExternalStream(int(self.lib.anm_host_stream(self.h)), device=self.device)
+
+    @property
     def launch_count(self):
         return int(self.lib.anm_launch_count(self.h))

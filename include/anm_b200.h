@@ -207,6 +207,9 @@ int anm_step_host(anm_handle h, const double* action_host, const double* next_va
 int anm_reset_host(anm_handle h, const double* s0_host, const uint8_t* mask_host_or_null,
                    double* obs_host, double* state_host_or_null, uint8_t* converged_host);
 
+/* The handle's own cudaStream_t (the one the *_host calls run on), e.g. to record events. */
+void* anm_host_stream(anm_handle h);
+
 /* Number of kernels this library has launched on behalf of `h` (for bench accounting). */
 int64_t anm_launch_count(anm_handle h);
 
