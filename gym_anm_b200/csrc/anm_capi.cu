@@ -12,6 +12,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -195,6 +196,7 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.o_y_ptr = bb.add(ptr);
     H.o_y_col = bb.add(col);
     H.o_y_val = bb.add(val);
+    H.o_y_dense = bb.add(std::vector<double>(net->ybus, net->ybus + (size_t)2 * N * N));
     H.o_jac_row = bb.add(jr);
     H.o_jac_col = bb.add(jc);
     H.o_jac_y = bb.add(jy);
@@ -281,11 +283,27 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
 }
 
 typedef void (*kernel_fn)(const AnmLaunch);
-kernel_fn kernel_for(int lpe) {
+/* Register-resident Newton solve for the bus counts instantiated below, generic shared-memory
+ * solve otherwise.  ANM_FORCE_GENERIC=1 (environment) selects the generic kernels (testing). */
+kernel_fn kernel_for(int lpe, int n_bus) {
+  static const bool force_generic = getenv("ANM_FORCE_GENERIC") && atoi(getenv("ANM_FORCE_GENERIC")) != 0;
+  if (!force_generic) {
+    switch (n_bus) {
+      case 2: return anm::anm_env_kernel<8, 2>;
+      case 3: return anm::anm_env_kernel<8, 3>;
+      case 4: return anm::anm_env_kernel<8, 4>;
+      case 5: return anm::anm_env_kernel<8, 5>;
+      case 6: return anm::anm_env_kernel<16, 6>;
+      case 7: return anm::anm_env_kernel<16, 7>;
+      case 8: return anm::anm_env_kernel<16, 8>;
+      case 9: return anm::anm_env_kernel<16, 9>;
+      default: break;
+    }
+  }
   switch (lpe) {
-    case 8: return anm::anm_env_kernel<8>;
-    case 16: return anm::anm_env_kernel<16>;
-    default: return anm::anm_env_kernel<32>;
+    case 8: return anm::anm_env_kernel<8, 0>;
+    case 16: return anm::anm_env_kernel<16, 0>;
+    default: return anm::anm_env_kernel<32, 0>;
   }
 }
 
@@ -305,7 +323,7 @@ int choose_geometry(anm_handle h) {
                 fixed + gpb * per_env, max_smem);
   h->gpb = gpb;
   h->smem = (int)(fixed + gpb * per_env);
-  kernel_fn fn = kernel_for(h->lpe);
+  kernel_fn fn = kernel_for(h->lpe, h->H.n_bus);
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, gpb * h->lpe, h->smem));
@@ -322,7 +340,7 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st) {
   p.B = h->B;
   p.soc = h->d_soc; p.aux = h->d_aux; p.terminated = h->d_term; p.episode = h->d_episode;
   p.pool = h->pool; p.pool_size = h->pool_size;
-  kernel_for(h->lpe)<<<h->grid, h->gpb * h->lpe, h->smem, st>>>(p);
+  kernel_for(h->lpe, h->H.n_bus)<<<h->grid, h->gpb * h->lpe, h->smem, st>>>(p);
   ++h->launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return fail(ANM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));

@@ -138,7 +138,7 @@ __device__ __forceinline__ double sign_nan(double x) { return (x != x) ? x : (x 
 struct Cst {  // resolved pointers into the staged blob
   const AnmConstHeader* H;
   const double *vmin, *vmax, *dev_param, *br_coef, *y_val, *ctrl_rows, *sv_mul, *sv_div, *ov_mul, *ov_div, *ov_low,
-      *ov_high, *table;
+      *ov_high, *table, *y_dense;
   const int *dev_bus, *dev_type, *dev_slot, *bus_dev_ptr, *bus_dev_idx, *br_from, *br_to, *y_ptr, *y_col, *jac_row,
       *jac_col, *jac_y, *ctrl_dev, *sv_off, *ov_off, *pair_i, *pair_j;
   __device__ explicit Cst(const unsigned char* b) {
@@ -148,6 +148,7 @@ struct Cst {  // resolved pointers into the staged blob
     DP(vmin, o_vmin); DP(vmax, o_vmax); DP(dev_param, o_dev_param); DP(br_coef, o_br_coef); DP(y_val, o_y_val);
     DP(ctrl_rows, o_ctrl_rows); DP(sv_mul, o_sv_mul); DP(sv_div, o_sv_div); DP(ov_mul, o_ov_mul);
     DP(ov_div, o_ov_div); DP(ov_low, o_ov_low); DP(ov_high, o_ov_high); DP(table, o_table);
+    DP(y_dense, o_y_dense);
     IP(dev_bus, o_dev_bus); IP(dev_type, o_dev_type); IP(dev_slot, o_dev_slot); IP(bus_dev_ptr, o_bus_dev_ptr);
     IP(bus_dev_idx, o_bus_dev_idx); IP(br_from, o_br_from); IP(br_to, o_br_to); IP(y_ptr, o_y_ptr); IP(y_col, o_y_col);
     IP(jac_row, o_jac_row); IP(jac_col, o_jac_col); IP(jac_y, o_jac_y); IP(ctrl_dev, o_ctrl_dev);
@@ -163,15 +164,16 @@ struct Cst {  // resolved pointers into the staged blob
 template <int LPE>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
                                                 const double* __restrict__ rh, const int* __restrict__ pair_i,
-                                                const int* __restrict__ pair_j, double p, double q, int lane,
+                                                const int* __restrict__ pair_j, int R, double p, double q, int lane,
                                                 unsigned gm, double& po, double& qo) {
   double best = CUDART_INF, bx = CUDART_NAN, by = CUDART_NAN;
   int bidx = 1 << 20;
-  for (int c = lane; c < ANM_NCAND; c += LPE) {
+  const int ncand = 1 + R + R * (R - 1) / 2; /* pairs are ordered (0,1),(0,2),(1,2),(0,3).. so the first R(R-1)/2 stay below R */
+  for (int c = lane; c < ncand; c += LPE) {
     double x = p, y = q;
     int s1 = -1, s2 = -1;
     bool valid = true;
-    if (c >= 1 && c <= ANM_MAX_ROWS) {
+    if (c >= 1 && c <= R) {
       s1 = c - 1;
       const double a = ra[s1], b = rb[s1], h = rh[s1];
       valid = isfinite(h);
@@ -184,9 +186,9 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
         x = p - t * a;
         y = q - t * b;
       }
-    } else if (c > ANM_MAX_ROWS) {
-      s1 = pair_i[c - 1 - ANM_MAX_ROWS];
-      s2 = pair_j[c - 1 - ANM_MAX_ROWS];
+    } else if (c > R) {
+      s1 = pair_i[c - 1 - R];
+      s2 = pair_j[c - 1 - R];
       const double a1 = ra[s1], b1 = rb[s1], h1 = rh[s1], a2 = ra[s2], b2 = rb[s2], h2 = rh[s2];
       const double det = a1 * b2 - a2 * b1;
       valid = isfinite(h1) && isfinite(h2) && det != 0.0;
@@ -194,8 +196,7 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
       y = (a1 * h2 - a2 * h1) / det;
     }
     if (valid) {
-#pragma unroll
-      for (int k = 0; k < ANM_MAX_ROWS; ++k) {
+      for (int k = 0; k < R; ++k) {
         const double h = rh[k];
         if (k != s1 && k != s2 && isfinite(h) && (ra[k] * x + rb[k] * y - h > ANM_FEAS_TOL)) valid = false;
       }
@@ -214,107 +215,22 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
   qo = __shfl_sync(gm, by, src, LPE);
 }
 
-/* ---- one Simulator.transition for one environment ----------------------------------------
- * Inputs in the workspace: in_pl, in_pp, in_ps, in_qs (MW / MVAr), soc (p.u.).
- * Leaves dev_p/q, ppot, bus_p/q, V, I, branch quantities in the workspace.  Returns `stable`
- * and the (unclipped) reward terms to every lane of the group. */
+/* ---- Newton-Raphson, generic sizes: Jacobian in shared memory, runtime loops ----------------
+ * (solve_load_flow.py:176-226).  Returns diff-state flags: converged (no NaN) and stable. */
 template <int LPE>
-__device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, double& e_loss,
-                                           double& penalty, int& n_iter_out) {
+__device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, int& it_out,
+                                           bool& converged_out, bool& stable_out) {
   const AnmConstHeader& H = *C.H;
-  const int N = H.n_bus, D = H.n_dev, L = H.n_branch, n = N - 1, M = H.n_unk, LD = M + 1;
-  const double m = H.base_mva, dt = H.delta_t;
-  double* in_pl = ws + H.w_in_pl; double* in_pp = ws + H.w_in_pp; double* in_ps = ws + H.w_in_ps;
-  double* in_qs = ws + H.w_in_qs; double* soc = ws + H.w_soc; double* devp = ws + H.w_devp;
-  double* devq = ws + H.w_devq; double* ppot = ws + H.w_ppot; double* busp = ws + H.w_busp;
-  double* busq = ws + H.w_busq; double* x = ws + H.w_x; double* vre = ws + H.w_vre; double* vim = ws + H.w_vim;
-  double* ere = ws + H.w_ere; double* eim = ws + H.w_eim; double* ire = ws + H.w_ire; double* iim = ws + H.w_iim;
-  double* J = ws + H.w_J; double* rowh = ws + H.w_rowh;
-
-  /* 1. loads, p_pot, slack (devices.py:156-167, simulator.py:511, 521-523) */
-  for (int d = lane; d < D; d += LPE) {
-    const int t = C.dev_type[d], slot = C.dev_slot[d];
-    const double* P = C.dev_param + d * ANM_DEV_NPARAM;
-    double pp = 0.0;
-    if (t == ANM_DEV_LOAD) {
-      const double pv = clipd(in_pl[slot] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]);
-      devp[d] = pv;
-      devq[d] = pv * P[ANM_DP_QP_RATIO];
-    } else if (t == ANM_DEV_GEN || t == ANM_DEV_RENEWABLE) {
-      pp = clipd(in_pp[slot] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]);
-    } else if (t == ANM_DEV_SLACK) {
-      devp[d] = 0.0;
-      devq[d] = 0.0;
-    }
-    ppot[d] = pp;
-  }
-  __syncwarp(gm);
-
-  /* 2. generators / storage units: exact projection on the feasible polygon, SoC update */
-  for (int c = 0; c < H.n_ctrl; ++c) {
-    const int d = C.ctrl_dev[c];
-    const double* P = C.dev_param + d * ANM_DEV_NPARAM;
-    const double* rows = C.ctrl_rows + c * 3 * ANM_MAX_ROWS;
-    const bool is_des = (c >= H.n_gen);
-    if (lane < ANM_MAX_ROWS) {
-      double h = rows[2 * ANM_MAX_ROWS + lane];
-      if (!is_des) {
-        if (lane == 2) h = ppot[d]; /* p <= p_pot, devices.py:296 */
-      } else {
-        const double s = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
-        if (lane == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
-        if (lane == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
-      }
-      rowh[lane] = h;
-    }
-    if (LPE < ANM_MAX_ROWS + 0 && lane + LPE < ANM_MAX_ROWS) { /* LPE == 8: lanes 0,1 also fill rows 8,9 */
-      const int r = lane + LPE;
-      double h = rows[2 * ANM_MAX_ROWS + r];
-      if (is_des) {
-        const double s = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
-        if (r == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff);
-        if (r == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;
-      }
-      rowh[r] = h;
-    }
-    __syncwarp(gm);
-    double po, qo;
-    project_polygon<LPE>(rows, rows + ANM_MAX_ROWS, rowh, C.pair_i, C.pair_j, in_ps[c] / m, in_qs[c] / m, lane, gm, po,
-                         qo);
-    if (lane == 0) {
-      devp[d] = po;
-      devq[d] = qo;
-      if (is_des) { /* update_soc, devices.py:524-545 */
-        double s = soc[c - H.n_gen];
-        if (po <= 0.0)
-          s -= dt * P[ANM_DP_EFF] * po;
-        else
-          s -= dt * po / P[ANM_DP_EFF];
-        soc[c - H.n_gen] = clipd(s, P[ANM_DP_SOCMIN], P[ANM_DP_SOCMAX]);
-      }
-    }
-    __syncwarp(gm);
-  }
-
-  /* 3. bus injections, device-id order (simulator.py:539-549) */
-  for (int b = lane; b < N; b += LPE) {
-    double sp = 0.0, sq = 0.0;
-    for (int k = C.bus_dev_ptr[b]; k < C.bus_dev_ptr[b + 1]; ++k) {
-      const int d = C.bus_dev_idx[k];
-      sp += devp[d];
-      sq += devq[d];
-    }
-    busp[b] = sp;
-    busq[b] = sq;
-  }
+  const int N = H.n_bus, n = N - 1, M = H.n_unk, LD = M + 1;
+  double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* x = ws + H.w_x;
+  double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* J = ws + H.w_J;
   /* flat start (solve_load_flow.py:42) */
   for (int j = lane; j < n; j += LPE) {
     x[j] = 0.0;
     x[n + j] = 1.0;
   }
   __syncwarp(gm);
-
-  /* 4. Newton-Raphson (solve_load_flow.py:176-226) */
   int it = 0;
   double diff;
   for (;;) {
@@ -433,9 +349,254 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     }
     __syncwarp(gm);
   }
+  it_out = it;
+  converged_out = (diff == diff);
+  stable_out = converged_out && diff <= ANM_NR_TOL; /* solve_load_flow.py:49 */
+}
+
+/* ---- Newton-Raphson, compile-time bus count NB: everything in registers -----------------------
+ * Lane r < M = 2(NB-1) owns unknown x[r] and row r of the Jacobian (r < n: theta of bus r+1 and the
+ * real mismatch row; r >= n: |V| of bus r-n+1 and the imaginary row).  The dense Y row of the lane's
+ * bus is held in registers for the whole solve.  Per iteration the lanes exchange V, E through
+ * shared memory (one __syncwarp), build their Jacobian row in registers, and eliminate by
+ * Gauss-Jordan with partial pivoting: pivot = REDUX max over the high words of |a[k]| + ballot,
+ * pivot row broadcast by shuffles, no row swaps, no back-substitution.  Fully unrolled. */
+template <int LPE, int NB>
+__device__ __forceinline__ void nr_small(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, int& it_out,
+                                         bool& converged_out, bool& stable_out) {
+  constexpr int n = NB - 1, M = 2 * n;
+  static_assert(M <= LPE, "one Jacobian row per lane");
+  const AnmConstHeader& H = *C.H;
+  double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* sdx = ws + H.w_x;
+  double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim;
+  const bool active = lane < M;
+  const int part = (lane >= n) ? 1 : 0;
+  const int b = active ? (lane - part * n + 1) : 1;         /* bus of my row / unknown */
+  const int partner = active ? (part ? lane - n : lane + n) : lane;
+  const int gbase = (threadIdx.x & 31) / LPE * LPE;         /* first warp lane of my group */
+  /* my bus's dense Y row and injection target */
+  double yre[NB], yim[NB];
+  const double* Yd = C.y_dense + (size_t)b * NB * 2;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    yre[j] = Yd[2 * j];
+    yim[j] = Yd[2 * j + 1];
+  }
+  const double target = part ? busq[b] : busp[b];
+  double xr = part ? 1.0 : 0.0; /* flat start (solve_load_flow.py:42) */
+  if (lane == 0) {
+    vre[0] = 1.0; vim[0] = 0.0; ere[0] = 1.0; eim[0] = 0.0; /* slack: V = 1+0j (:171) */
+  }
+  int it = 0;
+  bool bad = false, big = false;
+  double vbr = 1.0, vbi = 0.0, ibr = 0.0, ibi = 0.0;
+  for (;;) {
+    /* V_b = |V| e^{j theta} (both lanes of a bus compute it), E_b = V_b / |V_b| */
+    const double other = __shfl_sync(gm, xr, partner, LPE);
+    const double th = part ? other : xr, vm = part ? xr : other;
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    vbr = vm * cs;
+    vbi = vm * sn;
+    const double ab = hypot(vbr, vbi);
+    const double ebr = vbr / ab, ebi = vbi / ab;
+    if (active && !part) {
+      vre[b] = vbr; vim[b] = vbi; ere[b] = ebr; eim[b] = ebi;
+    }
+    __syncwarp(gm);
+    double vr[NB], vi[NB], er[NB], ei[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      vr[j] = vre[j]; vi[j] = vim[j]; er[j] = ere[j]; ei[j] = eim[j];
+    }
+    /* I_b = sum_j Y_bj V_j ; S_b = V_b conj(I_b) ; my mismatch entry (:84-120) */
+    ibr = 0.0; ibi = 0.0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      ibr += yre[j] * vr[j] - yim[j] * vi[j];
+      ibi += yre[j] * vi[j] + yim[j] * vr[j];
+    }
+    const double F = (part ? (vbi * ibr - vbr * ibi) : (vbr * ibr + vbi * ibi)) - target;
+    bad = __any_sync(gm, active && (F != F));
+    big = __any_sync(gm, active && (fabs(F) > ANM_NR_TOL));
+    if (bad || !big || it >= ANM_NR_MAXIT) break; /* numpy: `nan > tol` is False (:218) */
+    ++it;
+
+    /* my Jacobian row (:123-164), augmented with the right-hand side F */
+    double a[M + 1];
+    a[M] = F;
+#pragma unroll
+    for (int j = 1; j < NB; ++j) {
+      const bool dg = (b == j);
+      const double tr = yre[j] * vr[j] - yim[j] * vi[j], ti = yre[j] * vi[j] + yim[j] * vr[j];
+      const double inr = (dg ? ibr : 0.0) - tr, ini = (dg ? ibi : 0.0) - ti;
+      const double jr = -vbi, ji = vbr; /* j V_b */
+      const double wr = jr * inr + ji * ini, wi = ji * inr - jr * ini;
+      const double gr = yre[j] * er[j] - yim[j] * ei[j], gi = yre[j] * ei[j] + yim[j] * er[j];
+      double ur = vbr * gr + vbi * gi, ui = vbi * gr - vbr * gi;
+      if (dg) {
+        ur += ebr * ibr + ebi * ibi;
+        ui += ebi * ibr - ebr * ibi;
+      }
+      a[j - 1] = part ? wi : wr;
+      a[n + j - 1] = part ? ui : ur;
+    }
+    /* Gauss-Jordan, partial pivoting, rows stay in their lanes */
+    bool used = !active;
+    int mycol = 0;
+    double myinv = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double av = fabs(a[k]);
+      const double rinv = 1.0 / a[k]; /* speculative: only the pivot lane's value is used */
+      unsigned key = used ? 0u : ((av != av) ? 1u : (unsigned)__double2hiint(av) + 2u);
+      const unsigned kmax = __reduce_max_sync(gm, key);
+      const unsigned cand = __ballot_sync(gm, key == kmax);
+      const int p = __ffs(cand) - 1 - gbase; /* first maximum wins */
+      const double pinv = __shfl_sync(gm, rinv, p, LPE);
+      double prow[M + 1];
+#pragma unroll
+      for (int c = k + 1; c <= M; ++c) prow[c] = __shfl_sync(gm, a[c], p, LPE);
+      if (lane == p) {
+        used = true;
+        mycol = k;
+        myinv = rinv;
+      } else {
+        const double f = a[k] * pinv;
+#pragma unroll
+        for (int c = k + 1; c <= M; ++c) a[c] = fma(-f, prow[c], a[c]);
+      }
+    }
+    /* dx[col] = rhs / pivot sits in the lane that pivoted col; route it to lane col */
+    if (active) sdx[mycol] = a[M] * myinv;
+    __syncwarp(gm);
+    if (active) xr -= sdx[lane];
+    __syncwarp(gm);
+  }
+  /* publish I (V is already there); bus 0's current by lane 0 */
+  if (active && !part) {
+    ire[b] = ibr; iim[b] = ibi;
+  }
+  if (lane == 0) {
+    double sr = 0.0, si = 0.0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const double yr = C.y_dense[2 * j], yi = C.y_dense[2 * j + 1];
+      sr += yr * vre[j] - yi * vim[j];
+      si += yr * vim[j] + yi * vre[j];
+    }
+    ire[0] = sr; iim[0] = si;
+  }
+  __syncwarp(gm);
+  it_out = it;
+  converged_out = !bad;
+  stable_out = !bad && !big; /* solve_load_flow.py:49 */
+}
+
+/* ---- one Simulator.transition for one environment ----------------------------------------
+ * Inputs in the workspace: in_pl, in_pp, in_ps, in_qs (MW / MVAr), soc (p.u.).
+ * Leaves dev_p/q, ppot, bus_p/q, V, I, branch quantities in the workspace.  Returns `stable`
+ * and the (unclipped) reward terms to every lane of the group. */
+template <int LPE, int NB>
+__device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, double& e_loss,
+                                           double& penalty, int& n_iter_out) {
+  const AnmConstHeader& H = *C.H;
+  const int N = H.n_bus, D = H.n_dev, L = H.n_branch;
+  const double m = H.base_mva, dt = H.delta_t;
+  double* in_pl = ws + H.w_in_pl; double* in_pp = ws + H.w_in_pp; double* in_ps = ws + H.w_in_ps;
+  double* in_qs = ws + H.w_in_qs; double* soc = ws + H.w_soc; double* devp = ws + H.w_devp;
+  double* devq = ws + H.w_devq; double* ppot = ws + H.w_ppot; double* busp = ws + H.w_busp;
+  double* busq = ws + H.w_busq; double* vre = ws + H.w_vre; double* vim = ws + H.w_vim;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* rowh = ws + H.w_rowh;
+
+  /* 1. loads, p_pot, slack (devices.py:156-167, simulator.py:511, 521-523) */
+  for (int d = lane; d < D; d += LPE) {
+    const int t = C.dev_type[d], slot = C.dev_slot[d];
+    const double* P = C.dev_param + d * ANM_DEV_NPARAM;
+    double pp = 0.0;
+    if (t == ANM_DEV_LOAD) {
+      const double pv = clipd(in_pl[slot] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]);
+      devp[d] = pv;
+      devq[d] = pv * P[ANM_DP_QP_RATIO];
+    } else if (t == ANM_DEV_GEN || t == ANM_DEV_RENEWABLE) {
+      pp = clipd(in_pp[slot] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]);
+    } else if (t == ANM_DEV_SLACK) {
+      devp[d] = 0.0;
+      devq[d] = 0.0;
+    }
+    ppot[d] = pp;
+  }
+  __syncwarp(gm);
+
+  /* 2. generators / storage units: exact projection on the feasible polygon, SoC update */
+  for (int c = 0; c < H.n_ctrl; ++c) {
+    const int d = C.ctrl_dev[c];
+    const double* P = C.dev_param + d * ANM_DEV_NPARAM;
+    const double* rows = C.ctrl_rows + c * 3 * ANM_MAX_ROWS;
+    const bool is_des = (c >= H.n_gen);
+    if (lane < ANM_MAX_ROWS) {
+      double h = rows[2 * ANM_MAX_ROWS + lane];
+      if (!is_des) {
+        if (lane == 2) h = ppot[d]; /* p <= p_pot, devices.py:296 */
+      } else {
+        const double s = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
+        if (lane == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
+        if (lane == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
+      }
+      rowh[lane] = h;
+    }
+    if (LPE < ANM_MAX_ROWS + 0 && lane + LPE < ANM_MAX_ROWS) { /* LPE == 8: lanes 0,1 also fill rows 8,9 */
+      const int r = lane + LPE;
+      double h = rows[2 * ANM_MAX_ROWS + r];
+      if (is_des) {
+        const double s = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
+        if (r == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff);
+        if (r == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;
+      }
+      rowh[r] = h;
+    }
+    __syncwarp(gm);
+    double po, qo;
+    project_polygon<LPE>(rows, rows + ANM_MAX_ROWS, rowh, C.pair_i, C.pair_j, is_des ? 10 : 7, in_ps[c] / m, in_qs[c] / m,
+                         lane, gm, po, qo);
+    if (lane == 0) {
+      devp[d] = po;
+      devq[d] = qo;
+      if (is_des) { /* update_soc, devices.py:524-545 */
+        double s = soc[c - H.n_gen];
+        if (po <= 0.0)
+          s -= dt * P[ANM_DP_EFF] * po;
+        else
+          s -= dt * po / P[ANM_DP_EFF];
+        soc[c - H.n_gen] = clipd(s, P[ANM_DP_SOCMIN], P[ANM_DP_SOCMAX]);
+      }
+    }
+    __syncwarp(gm);
+  }
+
+  /* 3. bus injections, device-id order (simulator.py:539-549) */
+  for (int b = lane; b < N; b += LPE) {
+    double sp = 0.0, sq = 0.0;
+    for (int k = C.bus_dev_ptr[b]; k < C.bus_dev_ptr[b + 1]; ++k) {
+      const int d = C.bus_dev_idx[k];
+      sp += devp[d];
+      sq += devq[d];
+    }
+    busp[b] = sp;
+    busq[b] = sq;
+  }
+  __syncwarp(gm);
+
+  /* 4. Newton-Raphson (solve_load_flow.py:176-226) */
+  int it = 0;
+  bool converged = false, stable = false;
+  if constexpr (NB > 0)
+    nr_small<LPE, NB>(C, ws, lane, gm, it, converged, stable);
+  else
+    nr_generic<LPE>(C, ws, lane, gm, it, converged, stable);
+  (void)converged;
   n_iter_out = it;
-  const bool converged = (diff == diff);
-  const bool stable = converged && diff <= ANM_NR_TOL; /* solve_load_flow.py:49 */
 
   /* 5. slack injection (:63-72) and branch flows (branch.py:153-198) */
   if (lane == 0) {
@@ -530,8 +691,8 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
   __syncwarp(gm);
 }
 
-template <int LPE>
-__global__ void __launch_bounds__(ANM_THREADS) anm_env_kernel(const AnmLaunch P) {
+template <int LPE, int NB>
+__global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) anm_env_kernel(const AnmLaunch P) {
   extern __shared__ __align__(128) unsigned char smem[];
   stage_constants(smem, P.blob, P.blob_bytes);
   const Cst C(smem + ANM_BLOB_SMEM_OFF);
@@ -628,7 +789,7 @@ __global__ void __launch_bounds__(ANM_THREADS) anm_env_kernel(const AnmLaunch P)
 
     double el, pe;
     int nit;
-    const bool stable = transition<LPE>(C, ws, lane, gm, el, pe, nit);
+    const bool stable = transition<LPE, NB>(C, ws, lane, gm, el, pe, nit);
 
     if (mode == ANM_MODE_TRANSITION) {
       if (P.full_state) {

@@ -35,6 +35,7 @@ struct AnmConstHeader {
   int32_t o_br_from, o_br_to;                /* int[n_branch]                                  */
   int32_t o_br_coef;                         /* double[n_branch][10]: a_ff a_ft a_tf a_tt (re,im) rate pad */
   int32_t o_y_ptr, o_y_col, o_y_val;         /* CSR of Y: int[n_bus+1], int[nnz], double[nnz][2] */
+  int32_t o_y_dense;                         /* double[n_bus][n_bus][2] dense Y (register-resident NR) */
   int32_t o_jac_row, o_jac_col, o_jac_y;     /* int[n_jac] each: bus b>=1, bus j>=1, index into y_val */
   int32_t o_ctrl_dev;                        /* int[n_ctrl] device position (gens then storage) */
   int32_t o_ctrl_rows;                       /* double[n_ctrl][3][ANM_MAX_ROWS]: a[], b[], h[]  */

@@ -290,3 +290,18 @@ def test_state_dict_roundtrip_and_simulator_view():
                                           {2: 1.0, 4: 2.0, 6: 0.0})  # fmt: skip
     d = sim.state_dict(0)
     assert set(d) >= {"bus_v_magn", "dev_p", "branch_s", "des_soc", "gen_p_max"} and abs(d["bus_v_magn"]["pu"][0] - 1.0) < 1e-12
+
+
+def test_generic_kernels_same_results_subprocess():
+    """The shared-memory (generic) kernels are used for N >= 10 buses; force them for the small
+    networks too (ANM_FORCE_GENERIC=1) and re-run the golden/oracle parity tests in a subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, ANM_FORCE_GENERIC="1")
+    here = os.path.abspath(__file__)
+    sel = "test_anm6easy_golden_trajectory or test_transition_goldens or test_batch_vs_oracle"
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900)  # fmt: skip
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
