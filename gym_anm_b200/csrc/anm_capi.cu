@@ -273,6 +273,7 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_J = take(M * (M + 1)); H.w_rowh = take(ANM_MAX_ROWS);
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
+    H.w_vx = take(4 * N);
     H.ws_doubles = (w + 15) / 16 * 16;
   }
   bb.buf.resize((bb.buf.size() + 127) / 128 * 128, 0);

@@ -18,8 +18,14 @@
  *   state / observation   _gather_state, observation    simulator.py:551-636, anm_env.py:313-331,562-592
  *
  * Constants are staged once per CTA into shared memory by a TMA bulk copy; the per-env
- * working set (voltages, Jacobian, flows) lives in shared memory; cross-lane traffic is
- * warp shuffles inside the lane group.  All arithmetic is IEEE fp64.
+ * working set lives in shared memory / registers; cross-lane traffic is warp shuffles inside
+ * the lane group.  All arithmetic is IEEE fp64.
+ *
+ * Two Newton-Raphson back-ends:
+ *   nr_small<LPE, NB>  compile-time bus count NB <= 9: one Jacobian row per lane, held in registers,
+ *                      fully unrolled Gauss-Jordan; the warp runs its environments in lock-step
+ *                      so every warp intrinsic uses the full mask (single SASS instruction).
+ *   nr_generic<LPE>    any size: Jacobian in shared memory, runtime loops (30-bus network, ...).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -33,7 +39,9 @@
 #define ANM_NR_TOL 1e-5   /* simulator.py:529 */
 #define ANM_NR_MAXIT 100  /* solve_load_flow.py:176 */
 #define ANM_FEAS_TOL 1e-12
+#define ANM_PIVOT_TAU 1e-2 /* natural pivot accepted if >= TAU * largest remaining entry of its column */
 #define ANM_BLOB_SMEM_OFF 128 /* blob starts here in dynamic smem; [0,8) holds the mbarrier */
+#define ANM_FULL 0xffffffffu
 
 struct AnmLaunch {
   const unsigned char* blob;
@@ -106,34 +114,64 @@ __device__ __forceinline__ void stage_constants(unsigned char* smem, const unsig
   }
 }
 
-/* ---- lane-group collectives (LPE lanes, mask gm) ------------------------------------- */
-template <int LPE>
+/* ---- lane-group collectives -----------------------------------------------------------
+ * FULL = the whole warp executes this code convergently (lock-step environments): use the
+ * constant full mask so each intrinsic is one SASS instruction.  Otherwise the group's own
+ * mask gm (groups of a warp may then diverge from each other). */
+template <bool FULL>
+__device__ __forceinline__ unsigned mk(unsigned gm) { return FULL ? ANM_FULL : gm; }
+template <bool FULL>
+__device__ __forceinline__ void gsync(unsigned gm) { __syncwarp(mk<FULL>(gm)); }
+template <bool FULL>
+__device__ __forceinline__ bool g_any(bool pred, unsigned gm) {
+  return FULL ? ((__ballot_sync(ANM_FULL, pred) & gm) != 0u) : (__any_sync(gm, pred) != 0);
+}
+template <int LPE, bool FULL>
 __device__ __forceinline__ double g_sum(double v, unsigned gm) {
 #pragma unroll
-  for (int o = LPE / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o);
+  for (int o = LPE / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mk<FULL>(gm), v, o);
   return v;
 }
-template <int LPE>
+template <int LPE, bool FULL>
 __device__ __forceinline__ double g_max(double v, unsigned gm) {
 #pragma unroll
-  for (int o = LPE / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(gm, v, o));
+  for (int o = LPE / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mk<FULL>(gm), v, o));
   return v;
 }
-/* arg-min / arg-max of (key, idx); ties -> lower idx; returns idx of the winner in all lanes */
-template <int LPE, bool MAX>
+/* arg-min / arg-max of (key, idx); ties -> lower idx; result in all lanes of the group */
+template <int LPE, bool FULL, bool MAX>
 __device__ __forceinline__ void g_argopt(double& key, int& idx, unsigned gm) {
 #pragma unroll
   for (int o = LPE / 2; o > 0; o >>= 1) {
-    double k2 = __shfl_xor_sync(gm, key, o);
-    int i2 = __shfl_xor_sync(gm, idx, o);
+    double k2 = __shfl_xor_sync(mk<FULL>(gm), key, o);
+    int i2 = __shfl_xor_sync(mk<FULL>(gm), idx, o);
     bool take = MAX ? (k2 > key || (k2 == key && i2 < idx)) : (k2 < key || (k2 == key && i2 < idx));
     if (take) key = k2, idx = i2;
   }
+}
+/* max of an unsigned key over each lane group (REDUX); FULL: one REDUX per group of the warp */
+template <int LPE, bool FULL>
+__device__ __forceinline__ unsigned g_umax(unsigned key, unsigned gm, int grp_in_warp) {
+  if (!FULL || LPE == 32) return __reduce_max_sync(mk<FULL>(gm), key);
+  unsigned res = 0;
+#pragma unroll
+  for (int g = 0; g < 32 / LPE; ++g) {
+    const unsigned m = __reduce_max_sync(ANM_FULL, (grp_in_warp == g) ? key : 0u);
+    if (grp_in_warp == g) res = m;
+  }
+  return res;
 }
 
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ double relu_nan(double x) { return (x != x) ? x : (x > 0.0 ? x : 0.0); }
 __device__ __forceinline__ double sign_nan(double x) { return (x != x) ? x : (x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0)); }
+
+/* 2^-floor(log2|v|): an exact power-of-two scale with |v| * s in [1, 2) (exponent clamped) */
+__device__ __forceinline__ double pow2_inv_scale(double v) {
+  int e = (__double2hiint(v) >> 20) & 0x7ff;
+  e = min(max(e, 1), 2045);
+  return __hiloint2double((2046 - e) << 20, 0);
+}
 
 struct Cst {  // resolved pointers into the staged blob
   const AnmConstHeader* H;
@@ -158,17 +196,18 @@ struct Cst {  // resolved pointers into the staged blob
   }
 };
 
-/* ---- exact projection of (p,q) on the polygon rows a[],b[],h[] (10 rows, h=inf unused) -------
+/* ---- exact projection of (p,q) on the polygon rows a[],b[],h[] (R rows, h=inf unused) ---------
  * Candidates: the point itself, its projection on each boundary line, every pairwise line
  * intersection; closest feasible one wins (oracle/shims/cvxpy/_projection.py is the definition). */
-template <int LPE>
+template <int LPE, bool FULL>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
                                                 const double* __restrict__ rh, const int* __restrict__ pair_i,
                                                 const int* __restrict__ pair_j, int R, double p, double q, int lane,
                                                 unsigned gm, double& po, double& qo) {
   double best = CUDART_INF, bx = CUDART_NAN, by = CUDART_NAN;
   int bidx = 1 << 20;
-  const int ncand = 1 + R + R * (R - 1) / 2; /* pairs are ordered (0,1),(0,2),(1,2),(0,3).. so the first R(R-1)/2 stay below R */
+  /* pairs are ordered (0,1),(0,2),(1,2),(0,3).. so the first R(R-1)/2 of them stay below R */
+  const int ncand = 1 + R + R * (R - 1) / 2;
   for (int c = lane; c < ncand; c += LPE) {
     double x = p, y = q;
     int s1 = -1, s2 = -1;
@@ -209,28 +248,32 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
   /* arg-min over the group (ties -> lowest candidate index, like a serial scan) */
   double key = best;
   int who = (bidx << 5) | (lane & 31);
-  g_argopt<LPE, false>(key, who, gm);
+  g_argopt<LPE, FULL, false>(key, who, gm);
   const int src = who & 31; /* lane index inside the group */
-  po = __shfl_sync(gm, bx, src, LPE);
-  qo = __shfl_sync(gm, by, src, LPE);
+  po = __shfl_sync(mk<FULL>(gm), bx, src, LPE);
+  qo = __shfl_sync(mk<FULL>(gm), by, src, LPE);
 }
 
 /* ---- Newton-Raphson, generic sizes: Jacobian in shared memory, runtime loops ----------------
- * (solve_load_flow.py:176-226).  Returns diff-state flags: converged (no NaN) and stable. */
-template <int LPE>
-__device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, int& it_out,
-                                           bool& converged_out, bool& stable_out) {
+ * (solve_load_flow.py:176-226).  Only instantiated with group-private control flow
+ * (FULL is true only for LPE == 32, where the group is the warp). */
+template <int LPE, bool FULL>
+__device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
+                                           int& it_out, bool& converged_out, bool& stable_out) {
   const AnmConstHeader& H = *C.H;
   const int N = H.n_bus, n = N - 1, M = H.n_unk, LD = M + 1;
   double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* x = ws + H.w_x;
   double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
   double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* J = ws + H.w_J;
+  it_out = 0;
+  converged_out = stable_out = true;
+  if (!live) return; /* group-uniform */
   /* flat start (solve_load_flow.py:42) */
   for (int j = lane; j < n; j += LPE) {
     x[j] = 0.0;
     x[n + j] = 1.0;
   }
-  __syncwarp(gm);
+  gsync<FULL>(gm);
   int it = 0;
   double diff;
   for (;;) {
@@ -248,7 +291,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
       vre[b] = re; vim[b] = im;
       ere[b] = re / a; eim[b] = im / a;
     }
-    __syncwarp(gm);
+    gsync<FULL>(gm);
     /* I = Y V (sparse rows) and mismatch F (:84-120) -> column M of J */
     double lmax = 0.0;
     bool bad = false;
@@ -262,8 +305,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
       }
       ire[b] = sr; iim[b] = si;
       if (b > 0) {
-        /* S = V conj(I) */
-        const double fr = (vre[b] * sr + vim[b] * si) - busp[b];
+        const double fr = (vre[b] * sr + vim[b] * si) - busp[b]; /* S = V conj(I) */
         const double fi = (vim[b] * sr - vre[b] * si) - busq[b];
         J[(b - 1) * LD + M] = fr;
         J[(n + b - 1) * LD + M] = fi;
@@ -271,32 +313,27 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
         lmax = fmax(lmax, fmax(fabs(fr), fabs(fi)));
       }
     }
-    lmax = g_max<LPE>(lmax, gm);
-    bad = __any_sync(gm, bad);
+    lmax = g_max<LPE, FULL>(lmax, gm);
+    bad = g_any<FULL>(bad, gm);
     diff = bad ? CUDART_NAN : lmax; /* numpy.linalg.norm(F, inf) propagates NaN */
     if (!(diff > ANM_NR_TOL) || it >= ANM_NR_MAXIT) break;
     ++it;
-    __syncwarp(gm);
+    gsync<FULL>(gm);
 
     /* Jacobian (:123-164): zero fill, then the structurally non-zero 2x2 blocks */
-    for (int k = lane; k < M * M; k += LPE) {
-      const int r = k / M, c = k - r * M;
-      J[r * LD + c] = 0.0;
-    }
-    __syncwarp(gm);
+    for (int r = 0; r < M; ++r)
+      for (int c = lane; c < M; c += LPE) J[r * LD + c] = 0.0;
+    gsync<FULL>(gm);
     for (int e = lane; e < H.n_jac; e += LPE) {
       const int b = C.jac_row[e], j = C.jac_col[e], yk = C.jac_y[e];
       const double yr = C.y_val[2 * yk], yi = C.y_val[2 * yk + 1];
       const bool dg = (b == j);
-      /* t = Y_bj V_j ; inner = delta I_b - t */
-      const double tr = yr * vre[j] - yi * vim[j], ti = yr * vim[j] + yi * vre[j];
-      const double inr = (dg ? ire[b] : 0.0) - tr, ini = (dg ? iim[b] : 0.0) - ti;
-      /* w = (j V_b) conj(inner) */
-      const double jr = -vim[b], ji = vre[b];
-      const double wr = jr * inr + ji * ini, wi = ji * inr - jr * ini;
-      /* u = V_b conj(Y_bj E_j) (+ E_b conj(I_b) on the diagonal) */
+      const double tr = yr * vre[j] - yi * vim[j], ti = yr * vim[j] + yi * vre[j]; /* Y_bj V_j */
+      const double inr = (dg ? ire[b] : 0.0) - tr, ini = (dg ? iim[b] : 0.0) - ti;   /* delta I_b - Y_bj V_j */
+      const double jr = -vim[b], ji = vre[b];                                        /* j V_b */
+      const double wr = jr * inr + ji * ini, wi = ji * inr - jr * ini;               /* dS/dtheta */
       const double gr = yr * ere[j] - yi * eim[j], gi = yr * eim[j] + yi * ere[j];
-      double ur = vre[b] * gr + vim[b] * gi, ui = vim[b] * gr - vre[b] * gi;
+      double ur = vre[b] * gr + vim[b] * gi, ui = vim[b] * gr - vre[b] * gi;         /* dS/d|V| */
       if (dg) {
         ur += ere[b] * ire[b] + eim[b] * iim[b];
         ui += eim[b] * ire[b] - ere[b] * iim[b];
@@ -306,7 +343,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
       J[(n + b - 1) * LD + (j - 1)] = wi;
       J[(n + b - 1) * LD + (n + j - 1)] = ui;
     }
-    __syncwarp(gm);
+    gsync<FULL>(gm);
 
     /* Solve J dx = F by Gauss-Jordan elimination with partial pivoting; rows are owned by
      * lanes (row r -> lane r % LPE), pivot rows are never swapped, only remembered.
@@ -314,17 +351,16 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
     uint32_t used = 0;    /* bit i: my i-th row (lane + i*LPE) already served as a pivot */
     uint32_t colpack = 0; /* byte i: the column my i-th row is the pivot of              */
     for (int k = 0; k < M; ++k) {
-      /* pivot = first maximum of |J[r][k]| over unused rows (NaN only if nothing else is left) */
       double bestv = -1.0;
       int bestr = 1 << 20;
       int i = 0;
       for (int r = lane; r < M; r += LPE, ++i) {
         if ((used >> i) & 1u) continue;
         double v = fabs(J[r * LD + k]);
-        if (v != v) v = -0.5;
+        if (v != v) v = -0.5; /* NaN only if nothing else is left */
         if (v > bestv) bestv = v, bestr = r;
       }
-      g_argopt<LPE, true>(bestv, bestr, gm);
+      g_argopt<LPE, FULL, true>(bestv, bestr, gm);
       const int pr = bestr;
       const double pv = J[pr * LD + k];
       i = 0;
@@ -337,9 +373,8 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
           for (int c = k + 1; c <= M; ++c) J[r * LD + c] -= f * J[pr * LD + c];
         }
       }
-      __syncwarp(gm);
+      gsync<FULL>(gm);
     }
-    /* x <- x - dx, dx_col = rhs / pivot for the row that pivoted column col (:220) */
     {
       int i = 0;
       for (int r = lane; r < M; r += LPE, ++i) {
@@ -347,7 +382,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
         x[col] -= J[r * LD + M] / J[r * LD + col];
       }
     }
-    __syncwarp(gm);
+    gsync<FULL>(gm);
   }
   it_out = it;
   converged_out = (diff == diff);
@@ -357,84 +392,32 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
 /* ---- Newton-Raphson, compile-time bus count NB: everything in registers -----------------------
  * Lane r < M = 2(NB-1) owns unknown x[r] and row r of the Jacobian (r < n: theta of bus r+1 and the
  * real mismatch row; r >= n: |V| of bus r-n+1 and the imaginary row).  The dense Y row of the lane's
- * bus is held in registers for the whole solve.  Per iteration the lanes exchange V, E through
- * shared memory (one __syncwarp), build their Jacobian row in registers, and eliminate by
- * Gauss-Jordan with partial pivoting: pivot = REDUX max over the high words of |a[k]| + ballot,
- * pivot row broadcast by shuffles, no row swaps, no back-substitution.  Fully unrolled. */
+ * bus stays in registers for the whole solve.  Per iteration the lanes exchange (V, E) through one
+ * shared-memory round trip, build their Jacobian row in registers and eliminate it by a fully
+ * unrolled, division-free Gauss-Jordan in natural pivot order (row k pivots column k, so the
+ * solution needs no routing); every lane watches its column for an entry that would have been a
+ * much better pivot, and only then the iteration is redone with REDUX-based partial pivoting.
+ * All lane groups of the warp run in lock-step (a finished group idles) => full-mask intrinsics. */
 template <int LPE, int NB>
-__device__ __forceinline__ void nr_small(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, int& it_out,
-                                         bool& converged_out, bool& stable_out) {
-  constexpr int n = NB - 1, M = 2 * n;
-  static_assert(M <= LPE, "one Jacobian row per lane");
-  const AnmConstHeader& H = *C.H;
-  double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* sdx = ws + H.w_x;
-  double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
-  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim;
-  const bool active = lane < M;
-  const int part = (lane >= n) ? 1 : 0;
-  const int b = active ? (lane - part * n + 1) : 1;         /* bus of my row / unknown */
-  const int partner = active ? (part ? lane - n : lane + n) : lane;
-  const int gbase = (threadIdx.x & 31) / LPE * LPE;         /* first warp lane of my group */
-  /* my bus's dense Y row and injection target */
-  double yre[NB], yim[NB];
-  const double* Yd = C.y_dense + (size_t)b * NB * 2;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    yre[j] = Yd[2 * j];
-    yim[j] = Yd[2 * j + 1];
-  }
-  const double target = part ? busq[b] : busp[b];
-  double xr = part ? 1.0 : 0.0; /* flat start (solve_load_flow.py:42) */
-  if (lane == 0) {
-    vre[0] = 1.0; vim[0] = 0.0; ere[0] = 1.0; eim[0] = 0.0; /* slack: V = 1+0j (:171) */
-  }
-  int it = 0;
-  bool bad = false, big = false;
-  double vbr = 1.0, vbi = 0.0, ibr = 0.0, ibi = 0.0;
-  for (;;) {
-    /* V_b = |V| e^{j theta} (both lanes of a bus compute it), E_b = V_b / |V_b| */
-    const double other = __shfl_sync(gm, xr, partner, LPE);
-    const double th = part ? other : xr, vm = part ? xr : other;
-    double sn, cs;
-    sincos(th, &sn, &cs);
-    vbr = vm * cs;
-    vbi = vm * sn;
-    const double ab = hypot(vbr, vbi);
-    const double ebr = vbr / ab, ebi = vbi / ab;
-    if (active && !part) {
-      vre[b] = vbr; vim[b] = vbi; ere[b] = ebr; eim[b] = ebi;
-    }
-    __syncwarp(gm);
-    double vr[NB], vi[NB], er[NB], ei[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      vr[j] = vre[j]; vi[j] = vim[j]; er[j] = ere[j]; ei[j] = eim[j];
-    }
-    /* I_b = sum_j Y_bj V_j ; S_b = V_b conj(I_b) ; my mismatch entry (:84-120) */
-    ibr = 0.0; ibi = 0.0;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      ibr += yre[j] * vr[j] - yim[j] * vi[j];
-      ibi += yre[j] * vi[j] + yim[j] * vr[j];
-    }
-    const double F = (part ? (vbi * ibr - vbr * ibi) : (vbr * ibr + vbi * ibi)) - target;
-    bad = __any_sync(gm, active && (F != F));
-    big = __any_sync(gm, active && (fabs(F) > ANM_NR_TOL));
-    if (bad || !big || it >= ANM_NR_MAXIT) break; /* numpy: `nan > tol` is False (:218) */
-    ++it;
+struct SmallNR {
+  static constexpr int n = NB - 1, M = 2 * (NB - 1);
 
-    /* my Jacobian row (:123-164), augmented with the right-hand side F */
-    double a[M + 1];
+  /* my Jacobian row (solve_load_flow.py:123-164), augmented with the right-hand side */
+  static __device__ __forceinline__ void build_row(double (&a)[M + 1], const double (&yre)[NB], const double (&yim)[NB],
+                                                   const double4* __restrict__ xch, int b, int part, double vbr,
+                                                   double vbi, double ebr, double ebi, double ibr, double ibi, double F) {
     a[M] = F;
 #pragma unroll
     for (int j = 1; j < NB; ++j) {
       const bool dg = (b == j);
-      const double tr = yre[j] * vr[j] - yim[j] * vi[j], ti = yre[j] * vi[j] + yim[j] * vr[j];
-      const double inr = (dg ? ibr : 0.0) - tr, ini = (dg ? ibi : 0.0) - ti;
-      const double jr = -vbi, ji = vbr; /* j V_b */
-      const double wr = jr * inr + ji * ini, wi = ji * inr - jr * ini;
-      const double gr = yre[j] * er[j] - yim[j] * ei[j], gi = yre[j] * ei[j] + yim[j] * er[j];
-      double ur = vbr * gr + vbi * gi, ui = vbi * gr - vbr * gi;
+      const double4 t4 = xch[j];
+      const double vr = t4.x, vi = t4.y, er = t4.z, ei = t4.w;
+      const double tr = yre[j] * vr - yim[j] * vi, ti = yre[j] * vi + yim[j] * vr; /* Y_bj V_j */
+      const double inr = (dg ? ibr : 0.0) - tr, ini = (dg ? ibi : 0.0) - ti;        /* delta I_b - Y_bj V_j */
+      const double jr = -vbi, ji = vbr;                                             /* j V_b */
+      const double wr = jr * inr + ji * ini, wi = ji * inr - jr * ini;              /* dS/dtheta */
+      const double gr = yre[j] * er - yim[j] * ei, gi = yre[j] * ei + yim[j] * er;
+      double ur = vbr * gr + vbi * gi, ui = vbi * gr - vbr * gi;                    /* dS/d|V| */
       if (dg) {
         ur += ebr * ibr + ebi * ibi;
         ui += ebi * ibr - ebr * ibi;
@@ -442,65 +425,155 @@ __device__ __forceinline__ void nr_small(const Cst& C, double* __restrict__ ws, 
       a[j - 1] = part ? wi : wr;
       a[n + j - 1] = part ? ui : ur;
     }
-    /* Gauss-Jordan, partial pivoting, rows stay in their lanes */
-    bool used = !active;
-    int mycol = 0;
-    double myinv = 0.0;
+  }
+
+  static __device__ __forceinline__ void run(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
+                                             int& it_out, bool& converged_out, bool& stable_out) {
+    static_assert(M <= LPE, "one Jacobian row per lane");
+    const AnmConstHeader& H = *C.H;
+    const double* busp = ws + H.w_busp; const double* busq = ws + H.w_busq; double* sdx = ws + H.w_x;
+    double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ire = ws + H.w_ire; double* iim = ws + H.w_iim;
+    double4* xch = reinterpret_cast<double4*>(ws + H.w_vx); /* (Vre, Vim, Ere, Eim) per bus */
+    const bool active = lane < M;
+    const int part = (lane >= n) ? 1 : 0;
+    const int b = active ? (lane - part * n + 1) : 1; /* bus of my row / unknown */
+    const int partner = active ? (part ? lane - n : lane + n) : lane;
+    const int giw = (threadIdx.x & 31) / LPE; /* my group's index inside the warp */
+    double yre[NB], yim[NB];
+    {
+      const double* Yd = C.y_dense + (size_t)b * NB * 2;
 #pragma unroll
-    for (int k = 0; k < M; ++k) {
-      const double av = fabs(a[k]);
-      const double rinv = 1.0 / a[k]; /* speculative: only the pivot lane's value is used */
-      unsigned key = used ? 0u : ((av != av) ? 1u : (unsigned)__double2hiint(av) + 2u);
-      const unsigned kmax = __reduce_max_sync(gm, key);
-      const unsigned cand = __ballot_sync(gm, key == kmax);
-      const int p = __ffs(cand) - 1 - gbase; /* first maximum wins */
-      const double pinv = __shfl_sync(gm, rinv, p, LPE);
-      double prow[M + 1];
-#pragma unroll
-      for (int c = k + 1; c <= M; ++c) prow[c] = __shfl_sync(gm, a[c], p, LPE);
-      if (lane == p) {
-        used = true;
-        mycol = k;
-        myinv = rinv;
-      } else {
-        const double f = a[k] * pinv;
-#pragma unroll
-        for (int c = k + 1; c <= M; ++c) a[c] = fma(-f, prow[c], a[c]);
+      for (int j = 0; j < NB; ++j) {
+        yre[j] = Yd[2 * j];
+        yim[j] = Yd[2 * j + 1];
       }
     }
-    /* dx[col] = rhs / pivot sits in the lane that pivoted col; route it to lane col */
-    if (active) sdx[mycol] = a[M] * myinv;
-    __syncwarp(gm);
-    if (active) xr -= sdx[lane];
-    __syncwarp(gm);
-  }
-  /* publish I (V is already there); bus 0's current by lane 0 */
-  if (active && !part) {
-    ire[b] = ibr; iim[b] = ibi;
-  }
-  if (lane == 0) {
-    double sr = 0.0, si = 0.0;
+    const double target = part ? busq[b] : busp[b];
+    double xr = part ? 1.0 : 0.0; /* flat start (solve_load_flow.py:42) */
+    if (lane == 0) xch[0] = make_double4(1.0, 0.0, 1.0, 0.0); /* slack: V = 1+0j (:171) */
+    int it = 0;
+    bool done = !live, bad = false, big = false;
+    double vbr = 1.0, vbi = 0.0, ibr = 0.0, ibi = 0.0;
+    for (;;) {
+      /* V_b = |V| e^{j theta} (both lanes of a bus compute it); E_b = V_b/|V_b| = sign(|V|) e^{j theta} */
+      const double other = __shfl_sync(ANM_FULL, xr, partner, LPE);
+      const double th = part ? other : xr, vm = part ? xr : other;
+      double sn, cs;
+      sincos(th, &sn, &cs);
+      vbr = vm * cs;
+      vbi = vm * sn;
+      const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN); /* v/abs(v): 0/0 -> NaN */
+      const double ebr = sg * cs, ebi = sg * sn;
+      if (active && !part) xch[b] = make_double4(vbr, vbi, ebr, ebi);
+      __syncwarp();
+      /* I_b = sum_j Y_bj V_j ; S_b = V_b conj(I_b) ; my mismatch entry (:84-120) */
+      ibr = 0.0; ibi = 0.0;
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const double yr = C.y_dense[2 * j], yi = C.y_dense[2 * j + 1];
-      sr += yr * vre[j] - yi * vim[j];
-      si += yr * vim[j] + yi * vre[j];
+      for (int j = 0; j < NB; ++j) {
+        const double4 t = xch[j];
+        ibr += yre[j] * t.x - yim[j] * t.y;
+        ibi += yre[j] * t.y + yim[j] * t.x;
+      }
+      const double F = (part ? (vbi * ibr - vbr * ibi) : (vbr * ibr + vbi * ibi)) - target;
+      const unsigned nanb = __ballot_sync(ANM_FULL, active && (F != F));
+      const unsigned bigb = __ballot_sync(ANM_FULL, active && (fabs(F) > ANM_NR_TOL));
+      if (!done) {
+        bad = (nanb & gm) != 0u; /* numpy: norm(F, inf) is NaN, and `nan > tol` is False (:218) */
+        big = (bigb & gm) != 0u;
+        if (bad || !big || it >= ANM_NR_MAXIT) done = true; else ++it;
+      }
+      if (__all_sync(ANM_FULL, done)) break;
+
+      double a[M + 1];
+      build_row(a, yre, yim, xch, b, part, vbr, vbi, ebr, ebi, ibr, ibi, F);
+      /* division-free Gauss-Jordan, natural pivot order: row r != k becomes
+       * s (pv * row_r - a_rk * row_k) with s = 2^-floor(log2|pv|), an exact scale that keeps the
+       * entries bounded (the pivot lane computes s while the previous step is still updating) */
+      bool susp = false;
+      double diag = 1.0;
+      double sc = pow2_inv_scale(a[0]);
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        const double pv = __shfl_sync(ANM_FULL, a[k], k, LPE);
+        const double s2 = __shfl_sync(ANM_FULL, sc, k, LPE);
+        const double mine = a[k];
+        const double pvs = pv * s2, ms = mine * s2;
+        if (lane == k) diag = mine;
+        susp = susp || (lane > k && active && (fabs(mine) * ANM_PIVOT_TAU > fabs(pv))) || !(fabs(pv) > 0.0);
+        if (lane < k) diag *= pvs;
+#pragma unroll
+        for (int c = k + 1; c <= M; ++c) {
+          const double pr = __shfl_sync(ANM_FULL, a[c], k, LPE);
+          if (lane != k) a[c] = fma(a[c], pvs, -(ms * pr));
+        }
+        if (k + 1 < M) sc = pow2_inv_scale(a[k + 1]);
+      }
+      double dx = a[M] / diag;
+      /* rare: some lane saw a far better pivot in its column -> redo this iteration with partial pivoting */
+      const unsigned suspb = __ballot_sync(ANM_FULL, susp);
+      if (suspb != 0u) {
+        build_row(a, yre, yim, xch, b, part, vbr, vbi, ebr, ebi, ibr, ibi, F);
+        bool used = !active;
+        int mycol = 0;
+        double myinv = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+          const double av = fabs(a[k]);
+          const double rinv = 1.0 / a[k]; /* speculative: only the pivot lane's value is used */
+          const unsigned key = used ? 0u : ((av != av) ? 1u : (unsigned)__double2hiint(av) + 2u);
+          const unsigned kmax = g_umax<LPE, true>(key, gm, giw);
+          const unsigned cand = __ballot_sync(ANM_FULL, key == kmax) & gm;
+          const int p = __ffs(cand) - 1 - giw * LPE; /* first maximum wins */
+          const double pinv = __shfl_sync(ANM_FULL, rinv, p, LPE);
+          const double f = a[k] * pinv;
+          if (lane == p) {
+            used = true;
+            mycol = k;
+            myinv = rinv;
+          }
+#pragma unroll
+          for (int c = k + 1; c <= M; ++c) {
+            const double pr = __shfl_sync(ANM_FULL, a[c], p, LPE);
+            if (lane != p) a[c] = fma(-f, pr, a[c]);
+          }
+        }
+        if (active) sdx[mycol] = a[M] * myinv;
+        __syncwarp();
+        if ((suspb & gm) != 0u && active) dx = sdx[lane]; /* only the group that needed it */
+        __syncwarp();
+      }
+      if (active && !done) xr -= dx; /* x <- x - J^{-1} F (:220) */
     }
-    ire[0] = sr; iim[0] = si;
+    /* publish V, I for the post-processing phases (bus 0's current by lane 0) */
+    if (active && !part) {
+      vre[b] = vbr; vim[b] = vbi; ire[b] = ibr; iim[b] = ibi;
+    }
+    if (lane == 0) {
+      double sr = 0.0, si = 0.0;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const double yr = C.y_dense[2 * j], yi = C.y_dense[2 * j + 1];
+        const double4 t = xch[j];
+        sr += yr * t.x - yi * t.y;
+        si += yr * t.y + yi * t.x;
+      }
+      vre[0] = 1.0; vim[0] = 0.0; ire[0] = sr; iim[0] = si;
+    }
+    __syncwarp();
+    it_out = it;
+    converged_out = !bad;
+    stable_out = !bad && !big; /* solve_load_flow.py:49 */
   }
-  __syncwarp(gm);
-  it_out = it;
-  converged_out = !bad;
-  stable_out = !bad && !big; /* solve_load_flow.py:49 */
-}
+};
 
 /* ---- one Simulator.transition for one environment ----------------------------------------
  * Inputs in the workspace: in_pl, in_pp, in_ps, in_qs (MW / MVAr), soc (p.u.).
  * Leaves dev_p/q, ppot, bus_p/q, V, I, branch quantities in the workspace.  Returns `stable`
- * and the (unclipped) reward terms to every lane of the group. */
-template <int LPE, int NB>
-__device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, double& e_loss,
-                                           double& penalty, int& n_iter_out) {
+ * and the (unclipped) reward terms to every lane of the group.  `live` = this group has a real
+ * environment (a dead group runs along for lock-step but skips the Newton iterations). */
+template <int LPE, int NB, bool FULL>
+__device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
+                                           double& e_loss, double& penalty, int& n_iter_out) {
   const AnmConstHeader& H = *C.H;
   const int N = H.n_bus, D = H.n_dev, L = H.n_branch;
   const double m = H.base_mva, dt = H.delta_t;
@@ -527,7 +600,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     }
     ppot[d] = pp;
   }
-  __syncwarp(gm);
+  gsync<FULL>(gm);
 
   /* 2. generators / storage units: exact projection on the feasible polygon, SoC update */
   for (int c = 0; c < H.n_ctrl; ++c) {
@@ -535,31 +608,21 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const double* P = C.dev_param + d * ANM_DEV_NPARAM;
     const double* rows = C.ctrl_rows + c * 3 * ANM_MAX_ROWS;
     const bool is_des = (c >= H.n_gen);
-    if (lane < ANM_MAX_ROWS) {
-      double h = rows[2 * ANM_MAX_ROWS + lane];
+    for (int r = lane; r < ANM_MAX_ROWS; r += LPE) {
+      double h = rows[2 * ANM_MAX_ROWS + r];
       if (!is_des) {
-        if (lane == 2) h = ppot[d]; /* p <= p_pot, devices.py:296 */
+        if (r == 2) h = ppot[d]; /* p <= p_pot, devices.py:296 */
       } else {
         const double s = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
-        if (lane == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
-        if (lane == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
-      }
-      rowh[lane] = h;
-    }
-    if (LPE < ANM_MAX_ROWS + 0 && lane + LPE < ANM_MAX_ROWS) { /* LPE == 8: lanes 0,1 also fill rows 8,9 */
-      const int r = lane + LPE;
-      double h = rows[2 * ANM_MAX_ROWS + r];
-      if (is_des) {
-        const double s = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
-        if (r == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff);
-        if (r == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;
+        if (r == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
+        if (r == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
       }
       rowh[r] = h;
     }
-    __syncwarp(gm);
+    gsync<FULL>(gm);
     double po, qo;
-    project_polygon<LPE>(rows, rows + ANM_MAX_ROWS, rowh, C.pair_i, C.pair_j, is_des ? 10 : 7, in_ps[c] / m, in_qs[c] / m,
-                         lane, gm, po, qo);
+    project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rowh, C.pair_i, C.pair_j, is_des ? 10 : 7, in_ps[c] / m,
+                               in_qs[c] / m, lane, gm, po, qo);
     if (lane == 0) {
       devp[d] = po;
       devq[d] = qo;
@@ -572,7 +635,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
         soc[c - H.n_gen] = clipd(s, P[ANM_DP_SOCMIN], P[ANM_DP_SOCMAX]);
       }
     }
-    __syncwarp(gm);
+    gsync<FULL>(gm);
   }
 
   /* 3. bus injections, device-id order (simulator.py:539-549) */
@@ -586,15 +649,15 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     busp[b] = sp;
     busq[b] = sq;
   }
-  __syncwarp(gm);
+  gsync<FULL>(gm);
 
   /* 4. Newton-Raphson (solve_load_flow.py:176-226) */
   int it = 0;
   bool converged = false, stable = false;
   if constexpr (NB > 0)
-    nr_small<LPE, NB>(C, ws, lane, gm, it, converged, stable);
+    SmallNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable);
   else
-    nr_generic<LPE>(C, ws, lane, gm, it, converged, stable);
+    nr_generic<LPE, FULL>(C, ws, lane, gm, live, it, converged, stable);
   (void)converged;
   n_iter_out = it;
 
@@ -630,7 +693,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     brp[l] = pf; brq[l] = qf; brs[l] = s; brire[l] = ifr; briim[l] = ifi;
     pen += relu_nan(fabs(s) - A[8]);
   }
-  __syncwarp(gm);
+  gsync<FULL>(gm);
 
   /* 6. reward terms (simulator.py:638-683) */
   double el = 0.0;
@@ -643,15 +706,15 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const double vm = hypot(vre[b], vim[b]);
     pen += relu_nan(vm - C.vmax[b]) + relu_nan(C.vmin[b] - vm);
   }
-  el = g_sum<LPE>(el, gm) * dt;
-  pen = g_sum<LPE>(pen, gm) * (dt * H.lamb);
+  el = g_sum<LPE, FULL>(el, gm) * dt;
+  pen = g_sum<LPE, FULL>(pen, gm) * (dt * H.lamb);
   e_loss = el;
   penalty = pen;
   return stable;
 }
 
 /* Simulator._gather_state (simulator.py:551-636), p.u. / rad, layout of anm_b200.h */
-template <int LPE>
+template <int LPE, bool FULL>
 __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restrict__ ws, int lane, unsigned gm,
                                                   bool angles) {
   const AnmConstHeader& H = *C.H;
@@ -688,11 +751,15 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
   }
   double* fa = fb + 5 * L;
   for (int k = lane; k < H.K; k += LPE) fa[k] = aux[k];
-  __syncwarp(gm);
+  gsync<FULL>(gm);
 }
+
+/* what a lane group does with its environment in this pass */
+enum { ACT_NONE = 0, ACT_ZERO = 1, ACT_STEP = 2, ACT_RESET = 3, ACT_TRANSITION = 4 };
 
 template <int LPE, int NB>
 __global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) anm_env_kernel(const AnmLaunch P) {
+  constexpr bool FULL = (NB > 0) || (LPE == 32);
   extern __shared__ __align__(128) unsigned char smem[];
   stage_constants(smem, P.blob, P.blob_bytes);
   const Cst C(smem + ANM_BLOB_SMEM_OFF);
@@ -701,7 +768,7 @@ __global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) an
   const int GPB = blockDim.x / LPE; /* env groups per block */
   const int lane = threadIdx.x % LPE;
   const int grp = threadIdx.x / LPE;
-  const unsigned gm = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << ((threadIdx.x & 31) / LPE * LPE));
+  const unsigned gm = (LPE == 32) ? ANM_FULL : (((1u << LPE) - 1u) << ((threadIdx.x & 31) / LPE * LPE));
   double* ws = reinterpret_cast<double*>(smem + ANM_BLOB_SMEM_OFF + ((P.blob_bytes + 127) / 128) * 128) +
                (size_t)grp * H.ws_doubles;
 
@@ -711,64 +778,72 @@ __global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) an
   double* in_qs = ws + H.w_in_qs; double* soc = ws + H.w_soc; double* aux = ws + H.w_aux;
   double* s0w = ws + H.w_s0; double* full = ws + H.w_full;
 
-  for (int64_t e = (int64_t)blockIdx.x * GPB + grp; e < P.B; e += (int64_t)gridDim.x * GPB) {
-    int mode = P.mode;
+  /* every group of the block makes the same number of passes (lock-step warps) */
+  for (int64_t base = (int64_t)blockIdx.x * GPB; base < P.B; base += (int64_t)gridDim.x * GPB) {
+    const int64_t e = base + grp;
+    int act = ACT_NONE;
     const double* s0row = nullptr;
-    if (mode == ANM_MODE_RESET) {
-      if (P.mask && !P.mask[e]) continue;
-      s0row = P.s0 + e * S;
-    } else if (mode == ANM_MODE_STEP && P.terminated[e]) {
-      if (P.pool_size > 0) { /* optional next-step auto-reset (not in the reference) */
+    if (e < P.B) {
+      if (P.mode == ANM_MODE_TRANSITION) {
+        act = ACT_TRANSITION;
+      } else if (P.mode == ANM_MODE_RESET) {
+        if (!P.mask || P.mask[e]) act = ACT_RESET, s0row = P.s0 + e * S;
+      } else if (!P.terminated[e]) {
+        act = ACT_STEP;
+      } else if (P.pool_size > 0) { /* optional next-step auto-reset (not in the reference) */
         const uint32_t ep = P.episode[e];
         const uint64_t h = ((uint64_t)e * 0x9E3779B97F4A7C15ull + (uint64_t)ep * 0xD1B54A32D192ED03ull) >> 17;
         s0row = P.pool + (int64_t)(h % (uint64_t)P.pool_size) * S;
-        mode = ANM_MODE_RESET;
-        __syncwarp(gm);
-        if (lane == 0) P.episode[e] = ep + 1;
-      } else { /* anm_env.py:365-367 */
-        for (int k = lane; k < O; k += LPE) P.obs[e * O + k] = 0.0;
-        if (P.state) for (int k = lane; k < S; k += LPE) P.state[e * S + k] = 0.0;
-        if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = 0.0;
-        if (lane == 0) {
-          P.reward[e] = 0.0;
-          P.term_out[e] = 1;
-          if (P.e_loss) P.e_loss[e] = H.clip_e;
-          if (P.penalty) P.penalty[e] = H.clip_pen;
-          if (P.n_iter) P.n_iter[e] = 0;
-        }
-        continue;
+        act = ACT_RESET;
+      } else {
+        act = ACT_ZERO;
       }
     }
 
-    /* ---- stage this env's inputs into the workspace ------------------------------------- */
-    for (int k = lane; k < ns; k += LPE) soc[k] = P.soc[e * ns + k];
-    for (int k = lane; k < K; k += LPE) aux[k] = P.aux[e * K + k];
-    if (mode == ANM_MODE_STEP) {
-      /* next_vars (anm6_easy.py:54-65) or caller-supplied vars (anm_env.py:370-380) */
-      if (P.next_vars) {
-        const double* nv = P.next_vars + e * NV;
-        for (int k = lane; k < nl; k += LPE) in_pl[k] = nv[k];
-        for (int k = lane; k < ng; k += LPE) in_pp[k] = nv[nl + k];
-        __syncwarp(gm);
-        for (int k = lane; k < K; k += LPE) s0w[k] = nv[nl + ng + k]; /* new aux, applied if not terminal */
-      } else {
-        const int a = (int)fmod(P.aux[e * K + K - 1] + 1.0, (double)H.table_len);
-        const double* row = C.table + a * (nl + ng);
-        for (int k = lane; k < nl; k += LPE) in_pl[k] = row[k];
-        for (int k = lane; k < ng; k += LPE) in_pp[k] = row[nl + k];
-        for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : P.aux[e * K + k];
+    /* ---- per-group prologue (no group collectives inside) ------------------------------------ */
+    if (act == ACT_ZERO) { /* anm_env.py:365-367 */
+      for (int k = lane; k < O; k += LPE) P.obs[e * O + k] = 0.0;
+      if (P.state) for (int k = lane; k < S; k += LPE) P.state[e * S + k] = 0.0;
+      if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = 0.0;
+      if (lane == 0) {
+        P.reward[e] = 0.0;
+        P.term_out[e] = 1;
+        if (P.e_loss) P.e_loss[e] = H.clip_e;
+        if (P.penalty) P.penalty[e] = H.clip_pen;
+        if (P.n_iter) P.n_iter[e] = 0;
       }
-      /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410) */
-      const double* act = P.action + e * A;
-      for (int k = lane; k < ng; k += LPE) { in_ps[k] = act[k]; in_qs[k] = act[ng + k]; }
-      for (int k = lane; k < ns; k += LPE) { in_ps[ng + k] = act[2 * ng + k]; in_qs[ng + k] = act[2 * ng + ns + k]; }
-    } else if (mode == ANM_MODE_TRANSITION) {
-      for (int k = lane; k < nl; k += LPE) in_pl[k] = P.p_load[e * nl + k];
-      for (int k = lane; k < ng; k += LPE) in_pp[k] = P.p_pot[e * ng + k];
-      for (int k = lane; k < nc; k += LPE) { in_ps[k] = P.p_set[e * nc + k]; in_qs[k] = P.q_set[e * nc + k]; }
-    } else { /* reset: Simulator.reset (simulator.py:225-293) */
-      for (int k = lane; k < S; k += LPE) s0w[k] = s0row[k];
-      __syncwarp(gm);
+    } else if (act != ACT_NONE) {
+      for (int k = lane; k < ns; k += LPE) soc[k] = P.soc[e * ns + k];
+      for (int k = lane; k < K; k += LPE) aux[k] = P.aux[e * K + k];
+      if (act == ACT_STEP) {
+        /* next_vars (anm6_easy.py:54-65) or caller-supplied vars (anm_env.py:370-380);
+         * the new aux values wait in s0w until the step is known to be non-terminal */
+        if (P.next_vars) {
+          const double* nv = P.next_vars + e * NV;
+          for (int k = lane; k < nl; k += LPE) in_pl[k] = nv[k];
+          for (int k = lane; k < ng; k += LPE) in_pp[k] = nv[nl + k];
+          for (int k = lane; k < K; k += LPE) s0w[k] = nv[nl + ng + k];
+        } else {
+          const int a = (int)fmod(P.aux[e * K + K - 1] + 1.0, (double)H.table_len);
+          const double* row = C.table + a * (nl + ng);
+          for (int k = lane; k < nl; k += LPE) in_pl[k] = row[k];
+          for (int k = lane; k < ng; k += LPE) in_pp[k] = row[nl + k];
+          for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : P.aux[e * K + k];
+        }
+        /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410) */
+        const double* av = P.action + e * A;
+        for (int k = lane; k < ng; k += LPE) { in_ps[k] = av[k]; in_qs[k] = av[ng + k]; }
+        for (int k = lane; k < ns; k += LPE) { in_ps[ng + k] = av[2 * ng + k]; in_qs[ng + k] = av[2 * ng + ns + k]; }
+      } else if (act == ACT_TRANSITION) {
+        for (int k = lane; k < nl; k += LPE) in_pl[k] = P.p_load[e * nl + k];
+        for (int k = lane; k < ng; k += LPE) in_pp[k] = P.p_pot[e * ng + k];
+        for (int k = lane; k < nc; k += LPE) { in_ps[k] = P.p_set[e * nc + k]; in_qs[k] = P.q_set[e * nc + k]; }
+      } else { /* ACT_RESET: Simulator.reset (simulator.py:225-293); s0 row kept in s0w */
+        for (int k = lane; k < S; k += LPE) s0w[k] = s0row[k];
+      }
+    }
+    gsync<FULL>(gm);
+    if (act == ACT_RESET) {
       for (int d = lane; d < D; d += LPE) {
         const int t = C.dev_type[d], slot = C.dev_slot[d];
         if (t == ANM_DEV_LOAD) {
@@ -785,17 +860,30 @@ __global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) an
         }
       }
     }
-    __syncwarp(gm);
+    gsync<FULL>(gm);
 
+    /* ---- the transition itself: all groups of the warp together ---------------------------------- */
+    const bool run = (act >= ACT_STEP);
     double el, pe;
     int nit;
-    const bool stable = transition<LPE, NB>(C, ws, lane, gm, el, pe, nit);
+    const bool stable = transition<LPE, NB, FULL>(C, ws, lane, gm, run, el, pe, nit);
 
-    if (mode == ANM_MODE_TRANSITION) {
-      if (P.full_state) {
-        gather_full_state<LPE>(C, ws, lane, gm, true);
-        for (int k = lane; k < F - K; k += LPE) P.full_state[e * (F - K) + k] = full[k];
-      }
+    /* ---- carried-state updates that feed the state vector ----------------------------------------- */
+    const bool term = !stable;
+    if (act == ACT_RESET) {
+      /* SoC <- s0 (simulator.py:284-288); aux <- s0 tail (anm_env.py:587) */
+      for (int k = lane; k < ns; k += LPE) soc[k] = s0w[2 * D + k] / H.base_mva;
+      for (int k = lane; k < K; k += LPE) aux[k] = s0w[S - K + k];
+    } else if (act == ACT_STEP && !term) {
+      for (int k = lane; k < K; k += LPE) aux[k] = s0w[k];
+    }
+    gsync<FULL>(gm);
+    gather_full_state<LPE, FULL>(C, ws, lane, gm,
+                                 P.mode == ANM_MODE_TRANSITION || H.need_angles || P.full_state != nullptr);
+
+    /* ---- per-group epilogue (no group collectives inside) ------------------------------------------- */
+    if (act == ACT_TRANSITION) {
+      if (P.full_state) for (int k = lane; k < F - K; k += LPE) P.full_state[e * (F - K) + k] = full[k];
       for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
       if (lane == 0) {
         if (P.reward) P.reward[e] = -(el + pe);
@@ -804,18 +892,7 @@ __global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) an
         if (P.converged) P.converged[e] = stable ? 1 : 0;
         if (P.n_iter) P.n_iter[e] = nit;
       }
-      __syncwarp(gm);
-      continue;
-    }
-
-    if (mode == ANM_MODE_RESET) {
-      /* SoC <- s0 (simulator.py:284-288); aux <- s0 tail (anm_env.py:587) */
-      for (int k = lane; k < ns; k += LPE) soc[k] = s0w[2 * D + k] / H.base_mva;
-      for (int k = lane; k < K; k += LPE) aux[k] = s0w[S - K + k];
-      __syncwarp(gm);
-      gather_full_state<LPE>(C, ws, lane, gm, H.need_angles || P.full_state != nullptr);
-      for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
-      for (int k = lane; k < K; k += LPE) P.aux[e * K + k] = aux[k];
+    } else if (act == ACT_RESET || (act == ACT_STEP && !term)) {
       for (int k = lane; k < O; k += LPE) {
         double v = full[C.ov_off[k]] * C.ov_mul[k];
         if (C.ov_div[k] != 1.0) v /= C.ov_div[k];
@@ -828,62 +905,45 @@ __global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) an
           P.state[e * S + k] = v;
         }
       if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = full[k];
+      for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
+      for (int k = lane; k < K; k += LPE) P.aux[e * K + k] = aux[k];
       if (lane == 0) {
-        P.terminated[e] = stable ? 0 : 1;
-        if (P.converged) P.converged[e] = stable ? 1 : 0;
-        if (P.mode == ANM_MODE_STEP) { /* auto-reset inside a step call */
-          P.reward[e] = 0.0;
-          P.term_out[e] = stable ? 0 : 1;
-          if (P.e_loss) P.e_loss[e] = 0.0;
-          if (P.penalty) P.penalty[e] = 0.0;
+        if (act == ACT_RESET) {
+          P.terminated[e] = stable ? 0 : 1;
+          if (P.converged) P.converged[e] = stable ? 1 : 0;
+          if (P.mode == ANM_MODE_STEP) { /* auto-reset inside a step call */
+            P.episode[e] = P.episode[e] + 1;
+            P.reward[e] = 0.0;
+            P.term_out[e] = stable ? 0 : 1;
+            if (P.e_loss) P.e_loss[e] = 0.0;
+            if (P.penalty) P.penalty[e] = 0.0;
+          }
+        } else { /* anm_env.py:424-427 */
+          const double elc = sign_nan(el) * clipd(fabs(el), 0.0, H.clip_e);
+          const double pec = clipd(pe, 0.0, H.clip_pen);
+          P.terminated[e] = 0;
+          P.term_out[e] = 0;
+          P.reward[e] = -(elc + pec);
+          if (P.e_loss) P.e_loss[e] = elc;
+          if (P.penalty) P.penalty[e] = pec;
         }
         if (P.n_iter) P.n_iter[e] = nit;
       }
-      __syncwarp(gm);
-      continue;
-    }
-
-    /* ---- step epilogue (anm_env.py:419-453) ------------------------------------------------ */
-    const bool term = !stable;
-    double r;
-    if (!term) {
-      el = sign_nan(el) * clipd(fabs(el), 0.0, H.clip_e);
-      pe = clipd(pe, 0.0, H.clip_pen);
-      r = -(el + pe);
-      for (int k = lane; k < K; k += LPE) aux[k] = s0w[k];
-      __syncwarp(gm);
-      gather_full_state<LPE>(C, ws, lane, gm, H.need_angles || P.full_state != nullptr);
-      for (int k = lane; k < O; k += LPE) {
-        double v = full[C.ov_off[k]] * C.ov_mul[k];
-        if (C.ov_div[k] != 1.0) v /= C.ov_div[k];
-        P.obs[e * O + k] = clipd(v, C.ov_low[k], C.ov_high[k]);
-      }
-      if (P.state)
-        for (int k = lane; k < S; k += LPE) {
-          double v = full[C.sv_off[k]] * C.sv_mul[k];
-          if (C.sv_div[k] != 1.0) v /= C.sv_div[k];
-          P.state[e * S + k] = v;
-        }
-      if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = full[k];
-      for (int k = lane; k < K; k += LPE) P.aux[e * K + k] = aux[k];
-    } else {
-      r = H.term_reward; /* -clip_pen / (1 - gamma), anm_env.py:430 */
-      el = H.clip_e;
-      pe = H.clip_pen;
+    } else if (act == ACT_STEP) { /* terminal step: anm_env.py:428-432, 446-448 */
       for (int k = lane; k < O; k += LPE) P.obs[e * O + k] = 0.0;
       if (P.state) for (int k = lane; k < S; k += LPE) P.state[e * S + k] = 0.0;
       if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = 0.0;
+      for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
+      if (lane == 0) {
+        P.terminated[e] = 1;
+        P.term_out[e] = 1;
+        P.reward[e] = H.term_reward; /* -clip_pen / (1 - gamma), anm_env.py:430 */
+        if (P.e_loss) P.e_loss[e] = H.clip_e;
+        if (P.penalty) P.penalty[e] = H.clip_pen;
+        if (P.n_iter) P.n_iter[e] = nit;
+      }
     }
-    for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
-    if (lane == 0) {
-      P.terminated[e] = term ? 1 : 0;
-      P.term_out[e] = term ? 1 : 0;
-      P.reward[e] = r;
-      if (P.e_loss) P.e_loss[e] = el;
-      if (P.penalty) P.penalty[e] = pe;
-      if (P.n_iter) P.n_iter[e] = nit;
-    }
-    __syncwarp(gm);
+    gsync<FULL>(gm);
   }
 }
 

@@ -47,5 +47,5 @@ struct AnmConstHeader {
   int32_t w_in_pl, w_in_pp, w_in_ps, w_in_qs, w_soc, w_aux, w_devp, w_devq, w_ppot, w_busp, w_busq;
   int32_t w_x, w_vre, w_vim, w_ere, w_eim, w_ire, w_iim, w_J, w_rowh;
   int32_t w_brp, w_brq, w_brs, w_brire, w_briim, w_full, w_s0;
-  int32_t pad_;
+  int32_t w_vx; /* (Vre, Vim, Ere, Eim) x n_bus exchange buffer of the register-resident solver */
 };
