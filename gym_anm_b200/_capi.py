@@ -12,7 +12,7 @@ import numpy as np
 from .errors import NativeLibraryError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libanm_b200.so")
+LIB_PATH = os.environ.get("ANM_B200_LIB") or os.path.join(_HERE, "lib", "libanm_b200.so")  # override: A/B builds
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -42,6 +42,16 @@
 #define ANM_PIVOT_TAU 1e-2 /* natural pivot accepted if >= TAU * largest remaining entry of its column */
 #define ANM_BLOB_SMEM_OFF 128 /* blob starts here in dynamic smem; [0,8) holds the mbarrier */
 #define ANM_FULL 0xffffffffu
+/* tuning switches of the register-resident solver (A/B-tested on B200, see profiles/) */
+#ifndef ANM_VAR_FSEL
+#define ANM_VAR_FSEL 1 /* 1: per-element select in the elimination update (measured 11% faster than (1, 0) multipliers) */
+#endif
+#ifndef ANM_VAR_MINB
+#define ANM_VAR_MINB 3 /* CTAs per SM the small-network kernels are register-limited to (168 regs, fewer spills: +4%) */
+#endif
+#ifndef ANM_VAR_YREG
+#define ANM_VAR_YREG 1 /* 1: the lane's dense Y row lives in registers; 0: re-read from shared memory */
+#endif
 
 struct AnmLaunch {
   const unsigned char* blob;
@@ -403,7 +413,11 @@ struct SmallNR {
   static constexpr int n = NB - 1, M = 2 * (NB - 1);
 
   /* my Jacobian row (solve_load_flow.py:123-164), augmented with the right-hand side */
+#if ANM_VAR_YREG
   static __device__ __forceinline__ void build_row(double (&a)[M + 1], const double (&yre)[NB], const double (&yim)[NB],
+#else
+  static __device__ __forceinline__ void build_row(double (&a)[M + 1], const double2* __restrict__ Yd,
+#endif
                                                    const double4* __restrict__ xch, int b, int part, double vbr,
                                                    double vbi, double ebr, double ebi, double ibr, double ibi, double F) {
     a[M] = F;
@@ -412,11 +426,17 @@ struct SmallNR {
       const bool dg = (b == j);
       const double4 t4 = xch[j];
       const double vr = t4.x, vi = t4.y, er = t4.z, ei = t4.w;
-      const double tr = yre[j] * vr - yim[j] * vi, ti = yre[j] * vi + yim[j] * vr; /* Y_bj V_j */
+#if ANM_VAR_YREG
+      const double yr_ = yre[j], yi_ = yim[j];
+#else
+      const double2 y_ = Yd[j];
+      const double yr_ = y_.x, yi_ = y_.y;
+#endif
+      const double tr = yr_ * vr - yi_ * vi, ti = yr_ * vi + yi_ * vr; /* Y_bj V_j */
       const double inr = (dg ? ibr : 0.0) - tr, ini = (dg ? ibi : 0.0) - ti;        /* delta I_b - Y_bj V_j */
       const double jr = -vbi, ji = vbr;                                             /* j V_b */
       const double wr = jr * inr + ji * ini, wi = ji * inr - jr * ini;              /* dS/dtheta */
-      const double gr = yre[j] * er - yim[j] * ei, gi = yre[j] * ei + yim[j] * er;
+      const double gr = yr_ * er - yi_ * ei, gi = yr_ * ei + yi_ * er;
       double ur = vbr * gr + vbi * gi, ui = vbi * gr - vbr * gi;                    /* dS/d|V| */
       if (dg) {
         ur += ebr * ibr + ebi * ibi;
@@ -439,15 +459,21 @@ struct SmallNR {
     const int b = active ? (lane - part * n + 1) : 1; /* bus of my row / unknown */
     const int partner = active ? (part ? lane - n : lane + n) : lane;
     const int giw = (threadIdx.x & 31) / LPE; /* my group's index inside the warp */
+    const double2* Yd = reinterpret_cast<const double2*>(C.y_dense) + (size_t)b * NB;
+#if ANM_VAR_YREG
     double yre[NB], yim[NB];
-    {
-      const double* Yd = C.y_dense + (size_t)b * NB * 2;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        yre[j] = Yd[2 * j];
-        yim[j] = Yd[2 * j + 1];
-      }
+    for (int j = 0; j < NB; ++j) {
+      const double2 y = Yd[j];
+      yre[j] = y.x;
+      yim[j] = y.y;
     }
+#define ANM_YRE(j) yre[j]
+#define ANM_YIM(j) yim[j]
+#define ANM_YARGS yre, yim
+#else
+#define ANM_YARGS Yd
+#endif
     const double target = part ? busq[b] : busp[b];
     double xr = part ? 1.0 : 0.0; /* flat start (solve_load_flow.py:42) */
     if (lane == 0) xch[0] = make_double4(1.0, 0.0, 1.0, 0.0); /* slack: V = 1+0j (:171) */
@@ -471,8 +497,14 @@ struct SmallNR {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const double4 t = xch[j];
-        ibr += yre[j] * t.x - yim[j] * t.y;
-        ibi += yre[j] * t.y + yim[j] * t.x;
+#if ANM_VAR_YREG
+        const double yr_ = yre[j], yi_ = yim[j];
+#else
+        const double2 y_ = Yd[j];
+        const double yr_ = y_.x, yi_ = y_.y;
+#endif
+        ibr += yr_ * t.x - yi_ * t.y;
+        ibi += yr_ * t.y + yi_ * t.x;
       }
       const double F = (part ? (vbi * ibr - vbr * ibi) : (vbr * ibr + vbi * ibi)) - target;
       const unsigned nanb = __ballot_sync(ANM_FULL, active && (F != F));
@@ -485,7 +517,7 @@ struct SmallNR {
       if (__all_sync(ANM_FULL, done)) break;
 
       double a[M + 1];
-      build_row(a, yre, yim, xch, b, part, vbr, vbi, ebr, ebi, ibr, ibi, F);
+      build_row(a, ANM_YARGS, xch, b, part, vbr, vbi, ebr, ebi, ibr, ibi, F);
       /* division-free Gauss-Jordan, natural pivot order: row r != k becomes
        * s (pv * row_r - a_rk * row_k) with s = 2^-floor(log2|pv|), an exact scale that keeps the
        * entries bounded (the pivot lane computes s while the previous step is still updating) */
@@ -497,14 +529,25 @@ struct SmallNR {
         const double pv = __shfl_sync(ANM_FULL, a[k], k, LPE);
         const double s2 = __shfl_sync(ANM_FULL, sc, k, LPE);
         const double mine = a[k];
-        const double pvs = pv * s2, ms = mine * s2;
-        if (lane == k) diag = mine;
+        const bool piv = (lane == k);
+        const double pvs = pv * s2;
+        /* the pivot row multiplies by 1 and subtracts 0: no per-element select needed */
+#if ANM_VAR_FSEL
+        const double pm = pvs, ms = mine * s2;
+#else
+        const double pm = piv ? 1.0 : pvs, ms = piv ? 0.0 : mine * s2;
+#endif
+        if (piv) diag = mine;
         susp = susp || (lane > k && active && (fabs(mine) * ANM_PIVOT_TAU > fabs(pv))) || !(fabs(pv) > 0.0);
         if (lane < k) diag *= pvs;
 #pragma unroll
         for (int c = k + 1; c <= M; ++c) {
           const double pr = __shfl_sync(ANM_FULL, a[c], k, LPE);
-          if (lane != k) a[c] = fma(a[c], pvs, -(ms * pr));
+#if ANM_VAR_FSEL
+          if (!piv) a[c] = fma(a[c], pm, -(ms * pr));
+#else
+          a[c] = fma(a[c], pm, -(ms * pr));
+#endif
         }
         if (k + 1 < M) sc = pow2_inv_scale(a[k + 1]);
       }
@@ -512,7 +555,7 @@ struct SmallNR {
       /* rare: some lane saw a far better pivot in its column -> redo this iteration with partial pivoting */
       const unsigned suspb = __ballot_sync(ANM_FULL, susp);
       if (suspb != 0u) {
-        build_row(a, yre, yim, xch, b, part, vbr, vbi, ebr, ebi, ibr, ibi, F);
+        build_row(a, ANM_YARGS, xch, b, part, vbr, vbi, ebr, ebi, ibr, ibi, F);
         bool used = !active;
         int mycol = 0;
         double myinv = 0.0;
@@ -758,7 +801,7 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
 enum { ACT_NONE = 0, ACT_ZERO = 1, ACT_STEP = 2, ACT_RESET = 3, ACT_TRANSITION = 4 };
 
 template <int LPE, int NB>
-__global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? 4 : 1) anm_env_kernel(const AnmLaunch P) {
+__global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? ANM_VAR_MINB : 1) anm_env_kernel(const AnmLaunch P) {
   constexpr bool FULL = (NB > 0) || (LPE == 32);
   extern __shared__ __align__(128) unsigned char smem[];
   stage_constants(smem, P.blob, P.blob_bytes);
