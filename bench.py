@@ -47,6 +47,27 @@ RING = 1000        # action ring slots (x B x 6 x 8 B = 197 MB at B = 4096)
 SEED0 = 2020
 
 
+def usable_cores():
+    """Host cores this process may really use: min(affinity mask, cgroup CPU quota)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:  # cgroup v2: "max 100000" or "<quota> <period>"
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:  # noqa: BLE001
+        try:  # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, n)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -103,7 +124,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     n = max(50, min(args.cpu_steps, args.steps))
     t0 = time.perf_counter()
     total, per_proc, resets = numpy_port_rate(cores, n, n_warm=min(10, max(1, args.warmup)))
@@ -130,7 +151,8 @@ def run_reference(args):
             "envs_per_gpu": args.envs,
         },
         "cpu_baseline": {"value": total, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
-                         "per_core_median": per_proc, "wall_s": wall, "resets": resets},  # fmt: skip
+                         "per_core_median": per_proc, "wall_s": wall, "resets": resets,
+                         "os_cpu_count": os.cpu_count()},  # fmt: skip
         "e2e": {"value": total, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -351,7 +373,7 @@ def run_ours(args):
     }  # fmt: skip
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         n = 800
         total, per_core, resets = numpy_port_rate(cores, n)
         cpu_baseline = {
@@ -403,6 +425,10 @@ def run_ours(args):
 
 
 if __name__ == "__main__":
+    # exactly ONE line on stdout: libraries that print to fd 1 (e.g. NCCL's version banner) go to stderr
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w")
     a = parse()
     if a.impl == "reference":
         run_reference(a)
