@@ -60,7 +60,7 @@ class Sizes(C.Structure):
 
 class StepExtras(C.Structure):
     _fields_ = [("state", C.c_void_p), ("e_loss", C.c_void_p), ("penalty", C.c_void_p), ("n_iter", C.c_void_p),
-                ("full_state", C.c_void_p)]  # fmt: skip
+                ("full_state", C.c_void_p), ("solver_stats", C.c_void_p)]  # fmt: skip
 
 
 def _dp(a):

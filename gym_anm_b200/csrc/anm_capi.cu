@@ -284,11 +284,18 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
 }
 
 typedef void (*kernel_fn)(const AnmLaunch);
+static bool force_generic() {
+  static const bool f = getenv("ANM_FORCE_GENERIC") && atoi(getenv("ANM_FORCE_GENERIC")) != 0;
+  return f;
+}
+/* CTA size: the register-resident small-network kernels use smaller CTAs (see anm_kernels.cuh) */
+static int threads_for(int lpe, int n_bus) {
+  return (!force_generic() && n_bus >= 2 && n_bus <= 9) ? ANM_VAR_THREADS : ANM_THREADS;
+}
 /* Register-resident Newton solve for the bus counts instantiated below, generic shared-memory
  * solve otherwise.  ANM_FORCE_GENERIC=1 (environment) selects the generic kernels (testing). */
 kernel_fn kernel_for(int lpe, int n_bus) {
-  static const bool force_generic = getenv("ANM_FORCE_GENERIC") && atoi(getenv("ANM_FORCE_GENERIC")) != 0;
-  if (!force_generic) {
+  if (!force_generic()) {
     switch (n_bus) {
       case 2: return anm::anm_env_kernel<8, 2>;
       case 3: return anm::anm_env_kernel<8, 3>;
@@ -317,7 +324,7 @@ int choose_geometry(anm_handle h) {
   const size_t max_smem = prop.sharedMemPerBlockOptin;
   const size_t fixed = ANM_BLOB_SMEM_OFF + (size_t)h->blob_bytes;
   const size_t per_env = (size_t)h->H.ws_doubles * sizeof(double);
-  int gpb = ANM_THREADS / h->lpe;
+  int gpb = threads_for(h->lpe, h->H.n_bus) / h->lpe;
   while (gpb > 1 && fixed + gpb * per_env > max_smem) gpb /= 2;
   if (fixed + gpb * per_env > max_smem)
     return fail(ANM_E_UNSUPPORTED, "network too large: %zu B of shared memory per CTA needed, %zu available",
@@ -455,7 +462,7 @@ int anm_step(anm_handle h, const double* action, const double* next_vars, double
   memset(&p, 0, sizeof(p));
   p.mode = ANM_MODE_STEP;
   p.action = action; p.next_vars = next_vars; p.obs = obs; p.reward = reward; p.term_out = terminated;
-  if (ex) { p.state = ex->state; p.e_loss = ex->e_loss; p.penalty = ex->penalty; p.n_iter = ex->n_iter; p.full_state = ex->full_state; }
+  if (ex) { p.state = ex->state; p.e_loss = ex->e_loss; p.penalty = ex->penalty; p.n_iter = ex->n_iter; p.full_state = ex->full_state; p.solver_stats = ex->solver_stats; }
   return launch(h, p, (cudaStream_t)stream);
 }
 

@@ -39,15 +39,23 @@
 #define ANM_NR_TOL 1e-5   /* simulator.py:529 */
 #define ANM_NR_MAXIT 100  /* solve_load_flow.py:176 */
 #define ANM_FEAS_TOL 1e-12
-#define ANM_PIVOT_TAU 1e-2 /* natural pivot accepted if >= TAU * largest remaining entry of its column */
+#ifndef ANM_PIVOT_TAU
+#define ANM_PIVOT_TAU 1e-4 /* natural pivot accepted if >= TAU * largest remaining entry of its column (A/B: profiles/) */
+#endif
 #define ANM_BLOB_SMEM_OFF 128 /* blob starts here in dynamic smem; [0,8) holds the mbarrier */
 #define ANM_FULL 0xffffffffu
 /* tuning switches of the register-resident solver (A/B-tested on B200, see profiles/) */
 #ifndef ANM_VAR_FSEL
 #define ANM_VAR_FSEL 1 /* 1: per-element select in the elimination update (measured 11% faster than (1, 0) multipliers) */
 #endif
+#ifndef ANM_DIAG
+#define ANM_DIAG 0 /* 1: fill anm_step_extras.solver_stats (costs ~10 %: clock64 + votes); tools/ build only */
+#endif
+#ifndef ANM_VAR_THREADS
+#define ANM_VAR_THREADS 64 /* CTA size of the small-network kernels */
+#endif
 #ifndef ANM_VAR_MINB
-#define ANM_VAR_MINB 3 /* CTAs per SM the small-network kernels are register-limited to (168 regs, fewer spills: +4%) */
+#define ANM_VAR_MINB 7 /* CTAs per SM they are register-limited to: 7 x 64 threads x 144 regs -> 28 envs/SM, one wave at B=4096 */
 #endif
 #ifndef ANM_VAR_YREG
 #define ANM_VAR_YREG 1 /* 1: the lane's dense Y row lives in registers; 0: re-read from shared memory */
@@ -84,6 +92,8 @@ struct AnmLaunch {
   int32_t* n_iter;
   double* full_state;
   uint8_t* converged;
+  int32_t* solver_stats; /* [B, 4] diagnostics: fallback iterations, large-angle iterations, SM cycles in the
+                            Newton loop, SM cycles of the whole pass -- or NULL */
 };
 
 namespace anm {
@@ -181,6 +191,41 @@ __device__ __forceinline__ double pow2_inv_scale(double v) {
   int e = (__double2hiint(v) >> 20) & 0x7ff;
   e = min(max(e, 1), 2045);
   return __hiloint2double((2046 - e) << 20, 0);
+}
+
+/* sin and cos of a double in one pass, branch-free up to |x| < 2^50.
+ * Range reduction: k = rint(x * 2/pi), r = x - k*pi/2 with pi/2 split into three doubles and FMAs
+ * (the same scheme as libdevice's fast path, which however leaves to a Payne-Hanek slow path above
+ * |x| > 105615 to guarantee <= 2 ulp *relative* error; here the absolute error of r stays ~2e-16, which
+ * is what V = |V| e^{j theta} needs -- divergent Newton trajectories routinely reach |theta| > 1e5 and the
+ * slow path dominated their latency).  Kernels: fdlibm's __kernel_sin/__kernel_cos minimax polynomials on
+ * [-pi/4, pi/4].  |x| >= 2^50, inf and NaN fall back to libdevice. */
+__device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
+  if (!(fabs(x) < 1.125899906842624e15)) { /* 2^50; also catches NaN / inf */
+    sincos(x, sn, cs);
+    return;
+  }
+  const double k = rint(x * 0.6366197723675814);
+  double r = fma(-k, 1.5707963267948966, x);
+  r = fma(-k, 6.123233995736766e-17, r);
+  r = fma(-k, -1.4973849048591698e-33, r);
+  const int q = (int)(__double2ll_rn(k) & 3ll);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double s = fma(z * r, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const double s1 = (q & 1) ? c : s, c1 = (q & 1) ? s : c;
+  *sn = (q & 2) ? -s1 : s1;
+  *cs = ((q + 1) & 2) ? -c1 : c1;
 }
 
 struct Cst {  // resolved pointers into the staged blob
@@ -448,7 +493,7 @@ struct SmallNR {
   }
 
   static __device__ __forceinline__ void run(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
-                                             int& it_out, bool& converged_out, bool& stable_out) {
+                                             int& it_out, bool& converged_out, bool& stable_out, int& n_fb, int& n_big) {
     static_assert(M <= LPE, "one Jacobian row per lane");
     const AnmConstHeader& H = *C.H;
     const double* busp = ws + H.w_busp; const double* busq = ws + H.w_busq; double* sdx = ws + H.w_x;
@@ -478,6 +523,12 @@ struct SmallNR {
     double xr = part ? 1.0 : 0.0; /* flat start (solve_load_flow.py:42) */
     if (lane == 0) xch[0] = make_double4(1.0, 0.0, 1.0, 0.0); /* slack: V = 1+0j (:171) */
     int it = 0;
+    n_fb = 0;
+    n_big = 0;
+#if ANM_DIAG
+    const long long t_loop0 = clock64();
+    long long t_done = 0;
+#endif
     bool done = !live, bad = false, big = false;
     double vbr = 1.0, vbi = 0.0, ibr = 0.0, ibi = 0.0;
     for (;;) {
@@ -485,7 +536,11 @@ struct SmallNR {
       const double other = __shfl_sync(ANM_FULL, xr, partner, LPE);
       const double th = part ? other : xr, vm = part ? xr : other;
       double sn, cs;
-      sincos(th, &sn, &cs);
+      sincos_fast(th, &sn, &cs);
+#if ANM_DIAG
+      const bool big_angle = g_any<true>(active && fabs(th) > 1e5, gm);
+      if (!done && big_angle) ++n_big;
+#endif
       vbr = vm * cs;
       vbi = vm * sn;
       const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN); /* v/abs(v): 0/0 -> NaN */
@@ -512,7 +567,11 @@ struct SmallNR {
       if (!done) {
         bad = (nanb & gm) != 0u; /* numpy: norm(F, inf) is NaN, and `nan > tol` is False (:218) */
         big = (bigb & gm) != 0u;
+#if ANM_DIAG
+        if (bad || !big || it >= ANM_NR_MAXIT) done = true, t_done = clock64(); else ++it;
+#else
         if (bad || !big || it >= ANM_NR_MAXIT) done = true; else ++it;
+#endif
       }
       if (__all_sync(ANM_FULL, done)) break;
 
@@ -554,6 +613,9 @@ struct SmallNR {
       double dx = a[M] / diag;
       /* rare: some lane saw a far better pivot in its column -> redo this iteration with partial pivoting */
       const unsigned suspb = __ballot_sync(ANM_FULL, susp);
+#if ANM_DIAG
+      if (!done && (suspb & gm) != 0u) ++n_fb;
+#endif
       if (suspb != 0u) {
         build_row(a, ANM_YARGS, xch, b, part, vbr, vbi, ebr, ebi, ibr, ibi, F);
         bool used = !active;
@@ -606,6 +668,9 @@ struct SmallNR {
     it_out = it;
     converged_out = !bad;
     stable_out = !bad && !big; /* solve_load_flow.py:49 */
+#if ANM_DIAG
+    n_fb = (n_fb & 0xffff) | ((int)((t_done - t_loop0) >> 4) << 16);
+#endif
   }
 };
 
@@ -616,7 +681,7 @@ struct SmallNR {
  * environment (a dead group runs along for lock-step but skips the Newton iterations). */
 template <int LPE, int NB, bool FULL>
 __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
-                                           double& e_loss, double& penalty, int& n_iter_out) {
+                                           double& e_loss, double& penalty, int& n_iter_out, int& n_fb, int& n_big) {
   const AnmConstHeader& H = *C.H;
   const int N = H.n_bus, D = H.n_dev, L = H.n_branch;
   const double m = H.base_mva, dt = H.delta_t;
@@ -697,8 +762,9 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   /* 4. Newton-Raphson (solve_load_flow.py:176-226) */
   int it = 0;
   bool converged = false, stable = false;
+  n_fb = n_big = 0;
   if constexpr (NB > 0)
-    SmallNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable);
+    SmallNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable, n_fb, n_big);
   else
     nr_generic<LPE, FULL>(C, ws, lane, gm, live, it, converged, stable);
   (void)converged;
@@ -801,7 +867,8 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
 enum { ACT_NONE = 0, ACT_ZERO = 1, ACT_STEP = 2, ACT_RESET = 3, ACT_TRANSITION = 4 };
 
 template <int LPE, int NB>
-__global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? ANM_VAR_MINB : 1) anm_env_kernel(const AnmLaunch P) {
+__global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_THREADS, (NB > 0 && LPE <= 16) ? ANM_VAR_MINB : 1)
+    anm_env_kernel(const AnmLaunch P) {
   constexpr bool FULL = (NB > 0) || (LPE == 32);
   extern __shared__ __align__(128) unsigned char smem[];
   stage_constants(smem, P.blob, P.blob_bytes);
@@ -908,8 +975,19 @@ __global__ void __launch_bounds__(ANM_THREADS, (NB > 0 && LPE <= 16) ? ANM_VAR_M
     /* ---- the transition itself: all groups of the warp together ---------------------------------- */
     const bool run = (act >= ACT_STEP);
     double el, pe;
-    int nit;
-    const bool stable = transition<LPE, NB, FULL>(C, ws, lane, gm, run, el, pe, nit);
+    int nit, nfb, nbig;
+#if ANM_DIAG
+    const long long t_pass0 = P.solver_stats ? clock64() : 0;
+#endif
+    const bool stable = transition<LPE, NB, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig);
+#if ANM_DIAG
+    if (P.solver_stats && run && lane == 0) {
+      P.solver_stats[4 * e] = nfb & 0xffff;
+      P.solver_stats[4 * e + 1] = nbig;
+      P.solver_stats[4 * e + 2] = nfb >> 16; /* Newton-loop cycles / 16 (see SmallNR::run) */
+      P.solver_stats[4 * e + 3] = (int)(clock64() - t_pass0);
+    }
+#endif
 
     /* ---- carried-state updates that feed the state vector ----------------------------------------- */
     const bool term = !stable;

@@ -87,7 +87,7 @@ class NativeBatch:
         ex = None
         if extras:
             ex = _capi.StepExtras()
-            for k in ("state", "e_loss", "penalty", "n_iter", "full_state"):
+            for k in ("state", "e_loss", "penalty", "n_iter", "full_state", "solver_stats"):
                 t = extras.get(k)
                 setattr(ex, k, None if t is None else t.data_ptr())
         _capi.check(self.lib.anm_step(self.h, _ptr(action), _ptr(nv), _ptr(obs), _ptr(reward), _ptr(term),

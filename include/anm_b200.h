@@ -147,6 +147,10 @@ typedef struct anm_step_extras {
   double* penalty;                /* dev [B]           ANMEnv.penalty (clipped)       */
   int32_t* n_iter;                /* dev [B]           Newton-Raphson iterations      */
   double* full_state;             /* dev [B, n_full_state] Simulator.state, p.u.      */
+  int32_t* solver_stats;          /* dev [B, 4] diagnostics: Newton iterations that needed the
+                                     partial-pivoting fallback, iterations with |theta| > 1e5,
+                                     SM cycles/16 spent in the Newton loop, SM cycles of the pass.
+                                     Only written by diagnostic builds (-DANM_DIAG=1, tools/).   */
 } anm_step_extras;
 
 typedef struct anm_handle_s* anm_handle;
