@@ -305,3 +305,69 @@ def test_generic_kernels_same_results_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=900)  # fmt: skip
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_power_flow_identities_at_full_size():
+    """BASELINE config 3 size (65536 instances): the reference's own physics identities
+    (tests/simulator/test_simulator_transitions.py:189-265) on every converged instance:
+    slack V = 1+0j, bus P/Q = sum of device P/Q, S = V conj(I), I = Y V, branch S/I formulas,
+    sign and magnitude of the apparent power."""
+    from gym_anm_b200.anm6 import BatchedANM6Easy
+
+    B = 65536
+    env = BatchedANM6Easy(B, validate_actions=False)
+    spec, cn = env.spec, env.spec.cn
+    rng = np.random.default_rng(65536)
+    # valid initial states without 65536 Python RNG objects: table slot + uniform Q / SoC, like init_state
+    t0 = rng.integers(0, 96, B)
+    s0 = np.zeros((B, 18))
+    tab = spec.table
+    for col, d in enumerate([1, 3, 5]):
+        s0[:, d] = tab[t0, col]
+        s0[:, 7 + d] = tab[t0, col] * 0.2
+    for k, d in enumerate([2, 4]):
+        s0[:, 15 + k] = tab[t0, 3 + k]
+        s0[:, d] = tab[t0, 3 + k]
+        s0[:, 7 + d] = rng.uniform(cn.devices[d].q_min, cn.devices[d].q_max, B)
+    s0[:, 14] = rng.uniform(0, 1, B)
+    s0[:, 17] = t0
+    obs, state, conv = env.native.reset(s0, obs=env._obs, state=env.state)
+    env._term_u8.copy_(1 - conv)
+    full = torch.zeros(B, env.native.F, dtype=torch.float64, device=env.device)
+    env._extras["full_state"] = full
+    for t in range(3):
+        a = torch.as_tensor(rng.uniform(spec.action_low, spec.action_high, size=(B, 6)), device=env.device)
+        obs, r, term, _, _ = env.step(a)
+    ok = (~term).cpu().numpy()
+    assert ok.sum() > 0.9 * B and (~ok).sum() > 0
+    f = full.cpu().numpy()[ok]
+    sl = spec.full_state_slices()
+    g = lambda k: f[:, sl[k]]  # noqa: E731
+    V = g("bus_v_magn") * np.exp(1j * g("bus_v_ang"))
+    I = g("bus_i_magn") * np.exp(1j * g("bus_i_ang"))  # noqa: E741
+    assert np.allclose(V[:, 0], 1.0, atol=1e-12)
+    # bus injections = sum of device injections
+    dev_bus = np.array([cn.devices[d].bus_id for d in cn.devices])
+    for b in range(6):
+        assert np.allclose(g("bus_p")[:, b], g("dev_p")[:, dev_bus == b].sum(1), atol=1e-12)
+        assert np.allclose(g("bus_q")[:, b], g("dev_q")[:, dev_bus == b].sum(1), atol=1e-12)
+    # S = V conj(I) within the NR tolerance, I = Y V
+    S = V * np.conj(I)
+    assert np.abs(S.real - g("bus_p")).max() < 2e-5 and np.abs(S.imag - g("bus_q")).max() < 2e-5
+    assert np.abs(I - V @ cn.Y_bus_dense.T).max() < 1e-9
+    # branch flows
+    for k, ((fb, tb), br) in enumerate(cn.branches.items()):
+        i_from = (br.series + br.shunt) / br.tap_magn**2 * V[:, fb] - br.series / np.conj(br.tap) * V[:, tb]
+        i_to = -br.series / br.tap * V[:, fb] + (br.series + br.shunt) * V[:, tb]
+        s_from, s_to = V[:, fb] * np.conj(i_from), V[:, tb] * np.conj(i_to)
+        assert np.allclose(g("branch_p")[:, k], s_from.real, atol=1e-10) and np.allclose(g("branch_q")[:, k], s_from.imag, atol=1e-10)
+        s_app = np.sign(s_from.real) * np.maximum(np.abs(s_from), np.abs(s_to))
+        assert np.allclose(g("branch_s")[:, k], s_app, atol=1e-10)
+    # reward = -(clipped e_loss + clipped penalty), obs = clip(state)
+    el, pe = env.e_loss.cpu().numpy()[ok], env.penalty.cpu().numpy()[ok]
+    assert np.allclose(r.cpu().numpy()[ok], -(el + pe), atol=1e-12) and np.all(pe >= 0) and np.all(pe <= 100) and np.all(np.abs(el) <= 1)
+    st, ob = env.state.cpu().numpy()[ok], obs.cpu().numpy()[ok]
+    assert np.array_equal(ob, np.clip(st, spec.obs_low, spec.obs_high))
+    # terminal rows: zeros and the terminal reward
+    bad = ~ok
+    assert np.all(obs.cpu().numpy()[bad] == 0) and np.all(np.isin(r.cpu().numpy()[bad], [0.0, -100 / (1 - 0.995)]))
