@@ -260,6 +260,65 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.o_pair_i = bb.add(pi);
     H.o_pair_j = bb.add(pj);
   }
+  {
+    /* Radial network?  The bus graph (branches) must be a tree rooted at the slack bus and no bus may have
+     * more than ANM_RAD_MAXC children; then the Jacobian has the tree's block sparsity and the kernel can
+     * eliminate it leaf-to-root (RadialNR in anm_kernels.cuh). */
+    const int n = N - 1;
+    std::vector<int> parent(N, -2), depth(N, 0), order;
+    std::vector<std::vector<int>> adj(N);
+    bool ok = (L == N - 1);
+    for (int l = 0; l < L && ok; ++l) {
+      const int f = net->br_from[l], t = net->br_to[l];
+      if (f == t) ok = false;
+      adj[f].push_back(t);
+      adj[t].push_back(f);
+    }
+    if (ok) {
+      parent[0] = -1;
+      order.push_back(0);
+      for (size_t q = 0; q < order.size(); ++q) {
+        const int u = order[q];
+        for (int v : adj[u])
+          if (parent[v] == -2) { parent[v] = u; depth[v] = depth[u] + 1; order.push_back(v); }
+      }
+      ok = ((int)order.size() == N);
+    }
+    std::vector<int> rp(n > 0 ? n : 1, -1), rd(n > 0 ? n : 1, 0), rc((size_t)(n > 0 ? n : 1) * ANM_RAD_MAXC, -1);
+    std::vector<double> ry((size_t)(n > 0 ? n : 1) * 6, 0.0);
+    int maxc = 0, maxd = 0;
+    if (ok) {
+      std::vector<int> nchild(N, 0);
+      for (int b = 1; b < N && ok; ++b) {
+        const int p = parent[b];
+        rp[b - 1] = (p == 0) ? -1 : p - 1;
+        rd[b - 1] = depth[b];
+        if (depth[b] > maxd) maxd = depth[b];
+        if (p > 0) {
+          if (nchild[p] >= ANM_RAD_MAXC) { ok = false; break; }
+          rc[(size_t)(p - 1) * ANM_RAD_MAXC + nchild[p]++] = b - 1;
+          if (nchild[p] > maxc) maxc = nchild[p];
+        }
+        const double* Y = net->ybus;
+        auto y = [&](int i, int j, int c) { return Y[2 * ((size_t)i * N + j) + c]; };
+        double* o = &ry[(size_t)(b - 1) * 6];
+        o[0] = y(b, b, 0); o[1] = y(b, b, 1); o[2] = y(b, p, 0); o[3] = y(b, p, 1); o[4] = y(p, b, 0); o[5] = y(p, b, 1);
+      }
+      /* the Y-bus must not couple buses that are not tree neighbours */
+      for (int i = 0; i < N && ok; ++i)
+        for (int j = 0; j < N && ok; ++j) {
+          if (i == j || parent[i] == j || parent[j] == i) continue;
+          if (net->ybus[2 * ((size_t)i * N + j)] != 0.0 || net->ybus[2 * ((size_t)i * N + j) + 1] != 0.0) ok = false;
+        }
+    }
+    H.is_radial = ok ? 1 : 0;
+    H.rad_maxc = maxc;
+    H.rad_maxdepth = maxd;
+    H.o_rad_parent = bb.add(rp);
+    H.o_rad_depth = bb.add(rd);
+    H.o_rad_child = bb.add(rc);
+    H.o_rad_y = bb.add(ry);
+  }
   /* per-env shared-memory workspace (doubles) */
   {
     int w = 0;
@@ -274,6 +333,7 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
     H.w_vx = take(4 * N);
+    H.w_dx = take(M);
     H.ws_doubles = (w + 15) / 16 * 16;
   }
   bb.buf.resize((bb.buf.size() + 127) / 128 * 128, 0);
@@ -284,54 +344,91 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
 }
 
 typedef void (*kernel_fn)(const AnmLaunch);
-static bool force_generic() {
-  static const bool f = getenv("ANM_FORCE_GENERIC") && atoi(getenv("ANM_FORCE_GENERIC")) != 0;
-  return f;
+/* Solver selection (anm_kernels.cuh), overridable with the environment variable ANM_SOLVER:
+ *   dense   (default for <= 9 buses)  Jacobian rows in registers, natural-order Gauss-Jordan     SmallNR
+ *   radial  (opt-in, tree networks)   2x2-block elimination along the tree, one bus per lane    RadialNR
+ *   generic (default for > 9 buses)   Jacobian in shared memory, partial pivoting                nr_generic
+ * On B200 `radial` has a ~13 % shorter Newton iteration for a lone warp and packs 4 environments per warp, but its
+ * dense fallback is slow and fires in ~0.5 % of the divergent solves; measured 0.29 vs 0.20 ms/step on the ANM6Easy
+ * bench (profiles/r01_v3_register_kernel.md), so it stays opt-in until that is fixed.
+ * ANM_FORCE_GENERIC=1 / ANM_FORCE_DENSE=1 are kept as aliases (tests). */
+static int solver_env() { /* -1: no override */
+  static const int v = [] {
+    const char* e = getenv("ANM_SOLVER");
+    if (e && !strcmp(e, "generic")) return 0;
+    if (e && !strcmp(e, "dense")) return 1;
+    if (e && !strcmp(e, "radial")) return 2;
+    if (getenv("ANM_FORCE_GENERIC") && atoi(getenv("ANM_FORCE_GENERIC")) != 0) return 0;
+    if (getenv("ANM_FORCE_DENSE") && atoi(getenv("ANM_FORCE_DENSE")) != 0) return 1;
+    return -1;
+  }();
+  return v;
 }
-/* CTA size: the register-resident small-network kernels use smaller CTAs (see anm_kernels.cuh) */
-static int threads_for(int lpe, int n_bus) {
-  return (!force_generic() && n_bus >= 2 && n_bus <= 9) ? ANM_VAR_THREADS : ANM_THREADS;
+static int solver_for(const AnmConstHeader& H) {
+  const int want = solver_env();
+  if (want == 0 || H.n_bus < 2 || H.n_bus > 9) return 0;
+  if (want == 2 && H.is_radial) return 2;
+  return 1;
 }
-/* Register-resident Newton solve for the bus counts instantiated below, generic shared-memory
- * solve otherwise.  ANM_FORCE_GENERIC=1 (environment) selects the generic kernels (testing). */
-kernel_fn kernel_for(int lpe, int n_bus) {
-  if (!force_generic()) {
-    switch (n_bus) {
-      case 2: return anm::anm_env_kernel<8, 2>;
-      case 3: return anm::anm_env_kernel<8, 3>;
-      case 4: return anm::anm_env_kernel<8, 4>;
-      case 5: return anm::anm_env_kernel<8, 5>;
-      case 6: return anm::anm_env_kernel<16, 6>;
-      case 7: return anm::anm_env_kernel<16, 7>;
-      case 8: return anm::anm_env_kernel<16, 8>;
-      case 9: return anm::anm_env_kernel<16, 9>;
-      default: break;
+static int lanes_for(const AnmConstHeader& H) {
+  const int M = H.n_unk;
+  switch (solver_for(H)) {
+    case 2: return 8;
+    case 1: return (H.n_bus <= 5) ? 8 : 16;
+    default: return (M <= 8) ? 8 : (M <= 16 ? 16 : 32);
+  }
+}
+static int threads_for(const AnmConstHeader& H) { return solver_for(H) ? ANM_VAR_THREADS : ANM_THREADS; }
+
+kernel_fn kernel_for(const AnmConstHeader& H) {
+  const int solver = solver_for(H);
+  if (solver == 2) {
+    switch (H.n_bus) {
+      case 2: return anm::anm_env_kernel<8, 2, 2>;
+      case 3: return anm::anm_env_kernel<8, 3, 2>;
+      case 4: return anm::anm_env_kernel<8, 4, 2>;
+      case 5: return anm::anm_env_kernel<8, 5, 2>;
+      case 6: return anm::anm_env_kernel<8, 6, 2>;
+      case 7: return anm::anm_env_kernel<8, 7, 2>;
+      case 8: return anm::anm_env_kernel<8, 8, 2>;
+      default: return anm::anm_env_kernel<8, 9, 2>;
     }
   }
-  switch (lpe) {
-    case 8: return anm::anm_env_kernel<8, 0>;
-    case 16: return anm::anm_env_kernel<16, 0>;
-    default: return anm::anm_env_kernel<32, 0>;
+  if (solver == 1) {
+    switch (H.n_bus) {
+      case 2: return anm::anm_env_kernel<8, 2, 1>;
+      case 3: return anm::anm_env_kernel<8, 3, 1>;
+      case 4: return anm::anm_env_kernel<8, 4, 1>;
+      case 5: return anm::anm_env_kernel<8, 5, 1>;
+      case 6: return anm::anm_env_kernel<16, 6, 1>;
+      case 7: return anm::anm_env_kernel<16, 7, 1>;
+      case 8: return anm::anm_env_kernel<16, 8, 1>;
+      default: return anm::anm_env_kernel<16, 9, 1>;
+    }
+  }
+  switch (lanes_for(H)) {
+    case 8: return anm::anm_env_kernel<8, 0, 0>;
+    case 16: return anm::anm_env_kernel<16, 0, 0>;
+    default: return anm::anm_env_kernel<32, 0, 0>;
   }
 }
 
 int choose_geometry(anm_handle h) {
-  const int M = h->H.n_unk;
-  h->lpe = (M <= 8) ? 8 : (M <= 16 ? 16 : 32);
+  h->lpe = lanes_for(h->H);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
   h->num_sms = prop.multiProcessorCount;
   const size_t max_smem = prop.sharedMemPerBlockOptin;
   const size_t fixed = ANM_BLOB_SMEM_OFF + (size_t)h->blob_bytes;
   const size_t per_env = (size_t)h->H.ws_doubles * sizeof(double);
-  int gpb = threads_for(h->lpe, h->H.n_bus) / h->lpe;
+  int gpb = threads_for(h->H) / h->lpe;
   while (gpb > 1 && fixed + gpb * per_env > max_smem) gpb /= 2;
   if (fixed + gpb * per_env > max_smem)
     return fail(ANM_E_UNSUPPORTED, "network too large: %zu B of shared memory per CTA needed, %zu available",
                 fixed + gpb * per_env, max_smem);
   h->gpb = gpb;
   h->smem = (int)(fixed + gpb * per_env);
-  kernel_fn fn = kernel_for(h->lpe, h->H.n_bus);
+  kernel_fn fn = kernel_for(h->H);
   CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, gpb * h->lpe, h->smem));
@@ -348,7 +445,7 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st) {
   p.B = h->B;
   p.soc = h->d_soc; p.aux = h->d_aux; p.terminated = h->d_term; p.episode = h->d_episode;
   p.pool = h->pool; p.pool_size = h->pool_size;
-  kernel_for(h->lpe, h->H.n_bus)<<<h->grid, h->gpb * h->lpe, h->smem, st>>>(p);
+  kernel_for(h->H)<<<h->grid, h->gpb * h->lpe, h->smem, st>>>(p);
   ++h->launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return fail(ANM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));

@@ -122,16 +122,20 @@ __device__ __forceinline__ void stage_constants(unsigned char* smem, const unsig
       done += chunk;
     }
   }
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar_a)
-        : "memory");
+  /* one warp polls the mbarrier (try_wait), the others park on the CTA barrier instead of spinning */
+  if (threadIdx.x < 32) {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_a)
+          : "memory");
+    }
   }
+  __syncthreads();
 }
 
 /* ---- lane-group collectives -----------------------------------------------------------
@@ -233,7 +237,8 @@ struct Cst {  // resolved pointers into the staged blob
   const double *vmin, *vmax, *dev_param, *br_coef, *y_val, *ctrl_rows, *sv_mul, *sv_div, *ov_mul, *ov_div, *ov_low,
       *ov_high, *table, *y_dense;
   const int *dev_bus, *dev_type, *dev_slot, *bus_dev_ptr, *bus_dev_idx, *br_from, *br_to, *y_ptr, *y_col, *jac_row,
-      *jac_col, *jac_y, *ctrl_dev, *sv_off, *ov_off, *pair_i, *pair_j;
+      *jac_col, *jac_y, *ctrl_dev, *sv_off, *ov_off, *pair_i, *pair_j, *rad_parent, *rad_depth, *rad_child;
+  const double* rad_y;
   __device__ explicit Cst(const unsigned char* b) {
     H = reinterpret_cast<const AnmConstHeader*>(b);
 #define DP(name, off) name = reinterpret_cast<const double*>(b + H->off)
@@ -241,11 +246,12 @@ struct Cst {  // resolved pointers into the staged blob
     DP(vmin, o_vmin); DP(vmax, o_vmax); DP(dev_param, o_dev_param); DP(br_coef, o_br_coef); DP(y_val, o_y_val);
     DP(ctrl_rows, o_ctrl_rows); DP(sv_mul, o_sv_mul); DP(sv_div, o_sv_div); DP(ov_mul, o_ov_mul);
     DP(ov_div, o_ov_div); DP(ov_low, o_ov_low); DP(ov_high, o_ov_high); DP(table, o_table);
-    DP(y_dense, o_y_dense);
+    DP(y_dense, o_y_dense); DP(rad_y, o_rad_y);
     IP(dev_bus, o_dev_bus); IP(dev_type, o_dev_type); IP(dev_slot, o_dev_slot); IP(bus_dev_ptr, o_bus_dev_ptr);
     IP(bus_dev_idx, o_bus_dev_idx); IP(br_from, o_br_from); IP(br_to, o_br_to); IP(y_ptr, o_y_ptr); IP(y_col, o_y_col);
     IP(jac_row, o_jac_row); IP(jac_col, o_jac_col); IP(jac_y, o_jac_y); IP(ctrl_dev, o_ctrl_dev);
     IP(sv_off, o_sv_off); IP(ov_off, o_ov_off); IP(pair_i, o_pair_i); IP(pair_j, o_pair_j);
+    IP(rad_parent, o_rad_parent); IP(rad_depth, o_rad_depth); IP(rad_child, o_rad_child);
 #undef DP
 #undef IP
   }
@@ -309,6 +315,49 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
   qo = __shfl_sync(mk<FULL>(gm), by, src, LPE);
 }
 
+/* ---- Solve J dx = F (F in column M of the M x (M+1) shared-memory array J) by Gauss-Jordan
+ * elimination with partial pivoting; rows are owned by lanes (row r -> lane r % LPE), pivot rows
+ * are never swapped, only remembered.  Writes dx to dxs[0..M).  Stands in for
+ * scipy.sparse.linalg.spsolve at solve_load_flow.py:220. */
+template <int LPE, bool FULL>
+__device__ __forceinline__ void gj_pivot_smem(double* __restrict__ J, int M, double* __restrict__ dxs, int lane,
+                                              unsigned gm) {
+  const int LD = M + 1;
+  uint32_t used = 0;    /* bit i: my i-th row (lane + i*LPE) already served as a pivot */
+  uint32_t colpack = 0; /* byte i: the column my i-th row is the pivot of              */
+  for (int k = 0; k < M; ++k) {
+    double bestv = -1.0;
+    int bestr = 1 << 20;
+    int i = 0;
+    for (int r = lane; r < M; r += LPE, ++i) {
+      if ((used >> i) & 1u) continue;
+      double v = fabs(J[r * LD + k]);
+      if (v != v) v = -0.5; /* NaN only if nothing else is left */
+      if (v > bestv) bestv = v, bestr = r;
+    }
+    g_argopt<LPE, FULL, true>(bestv, bestr, gm);
+    const int pr = bestr;
+    const double pv = J[pr * LD + k];
+    i = 0;
+    for (int r = lane; r < M; r += LPE, ++i) {
+      if (r == pr) {
+        used |= (1u << i);
+        colpack |= ((uint32_t)k << (8 * i));
+      } else {
+        const double f = J[r * LD + k] / pv;
+        for (int c = k + 1; c <= M; ++c) J[r * LD + c] -= f * J[pr * LD + c];
+      }
+    }
+    gsync<FULL>(gm);
+  }
+  int i = 0;
+  for (int r = lane; r < M; r += LPE, ++i) {
+    const int col = (colpack >> (8 * i)) & 0xff;
+    dxs[col] = J[r * LD + M] / J[r * LD + col];
+  }
+  gsync<FULL>(gm);
+}
+
 /* ---- Newton-Raphson, generic sizes: Jacobian in shared memory, runtime loops ----------------
  * (solve_load_flow.py:176-226).  Only instantiated with group-private control flow
  * (FULL is true only for LPE == 32, where the group is the warp). */
@@ -319,7 +368,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
   const int N = H.n_bus, n = N - 1, M = H.n_unk, LD = M + 1;
   double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* x = ws + H.w_x;
   double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
-  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* J = ws + H.w_J;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* J = ws + H.w_J; double* dxs = ws + H.w_dx;
   it_out = 0;
   converged_out = stable_out = true;
   if (!live) return; /* group-uniform */
@@ -400,43 +449,8 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
     }
     gsync<FULL>(gm);
 
-    /* Solve J dx = F by Gauss-Jordan elimination with partial pivoting; rows are owned by
-     * lanes (row r -> lane r % LPE), pivot rows are never swapped, only remembered.
-     * (stands in for scipy.sparse.linalg.spsolve at solve_load_flow.py:220) */
-    uint32_t used = 0;    /* bit i: my i-th row (lane + i*LPE) already served as a pivot */
-    uint32_t colpack = 0; /* byte i: the column my i-th row is the pivot of              */
-    for (int k = 0; k < M; ++k) {
-      double bestv = -1.0;
-      int bestr = 1 << 20;
-      int i = 0;
-      for (int r = lane; r < M; r += LPE, ++i) {
-        if ((used >> i) & 1u) continue;
-        double v = fabs(J[r * LD + k]);
-        if (v != v) v = -0.5; /* NaN only if nothing else is left */
-        if (v > bestv) bestv = v, bestr = r;
-      }
-      g_argopt<LPE, FULL, true>(bestv, bestr, gm);
-      const int pr = bestr;
-      const double pv = J[pr * LD + k];
-      i = 0;
-      for (int r = lane; r < M; r += LPE, ++i) {
-        if (r == pr) {
-          used |= (1u << i);
-          colpack |= ((uint32_t)k << (8 * i));
-        } else {
-          const double f = J[r * LD + k] / pv;
-          for (int c = k + 1; c <= M; ++c) J[r * LD + c] -= f * J[pr * LD + c];
-        }
-      }
-      gsync<FULL>(gm);
-    }
-    {
-      int i = 0;
-      for (int r = lane; r < M; r += LPE, ++i) {
-        const int col = (colpack >> (8 * i)) & 0xff;
-        x[col] -= J[r * LD + M] / J[r * LD + col];
-      }
-    }
+    gj_pivot_smem<LPE, FULL>(J, M, dxs, lane, gm);
+    for (int c = lane; c < M; c += LPE) x[c] -= dxs[c]; /* x <- x - J^{-1} F (:220) */
     gsync<FULL>(gm);
   }
   it_out = it;
@@ -674,12 +688,237 @@ struct SmallNR {
   }
 };
 
+/* ---- Newton-Raphson for RADIAL networks (the bus graph is a tree rooted at the slack bus) --------
+ * Lane b-1 owns non-slack bus b: its two unknowns (theta_b, |V|_b), its two mismatch rows and the three
+ * non-zero 2x2 Jacobian blocks of a tree: D = J[b][b], L = J[b][parent], U = J[parent][b]
+ * (solve_load_flow.py:123-164 restricted to the Y-bus sparsity).  The Newton step is a block elimination
+ * along the tree: leaves first, every bus folds  U D^-1 [L | f]  into its parent's (D, f) (one shuffle
+ * round per tree level), then the step is back-substituted from the root down -- the critical path is the
+ * tree depth instead of 2(N-1) pivots, and an environment needs only N-1 lanes.  2x2 diagonal blocks are
+ * inverted by the adjugate; a numerically singular block (|det| << |d00 d11| + |d01 d10|) sends that
+ * iteration to the dense partial-pivoting solver in shared memory.  Lock-step lane groups, full-mask
+ * intrinsics, like SmallNR. */
+#define ANM_RAD_MAXC 4
+template <int LPE, int NB>
+struct RadialNR {
+  static constexpr int n = NB - 1, M = 2 * (NB - 1);
+
+  static __device__ __forceinline__ void run(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
+                                             int& it_out, bool& converged_out, bool& stable_out, int& n_fb, int& n_big) {
+    static_assert(n <= LPE, "one bus per lane");
+    const AnmConstHeader& H = *C.H;
+    const double* busp = ws + H.w_busp; const double* busq = ws + H.w_busq;
+    double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ire = ws + H.w_ire; double* iim = ws + H.w_iim;
+    double* J = ws + H.w_J; double* dxs = ws + H.w_dx;
+    const bool active = lane < n;
+    const int bl = active ? lane : 0;  /* clamp for the table reads of idle lanes */
+    const int b = bl + 1;
+    const int pl = active ? C.rad_parent[bl] : -1; /* parent's lane, -1: the slack bus */
+    const int depth = active ? C.rad_depth[bl] : 0;
+    const int maxc = H.rad_maxc, maxd = H.rad_maxdepth;
+    int cl[ANM_RAD_MAXC];
+#pragma unroll
+    for (int s = 0; s < ANM_RAD_MAXC; ++s) cl[s] = active ? C.rad_child[bl * ANM_RAD_MAXC + s] : -1;
+    const double* yv = C.rad_y + 6 * bl;
+    const double ybbr = yv[0], ybbi = yv[1], ybpr = yv[2], ybpi = yv[3], ypbr = yv[4], ypbi = yv[5];
+    const double pb = busp[b], qb = busq[b];
+    const int psrc = (pl < 0) ? lane : pl;
+    double th = 0.0, vm = 1.0; /* flat start (solve_load_flow.py:42) */
+    int it = 0;
+    n_fb = 0;
+    n_big = 0;
+#if ANM_DIAG
+    const long long t_loop0 = clock64();
+    long long t_done = 0;
+#endif
+    bool done = !live, bad = false, big = false;
+    double vr = 1.0, vi = 0.0, ir = 0.0, ii = 0.0;
+    for (;;) {
+      /* V_b = |V| e^{j theta}, E_b = V_b / |V_b| (:167-173, :150) */
+      double sn, cs;
+      sincos_fast(th, &sn, &cs);
+      vr = vm * cs;
+      vi = vm * sn;
+      const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN);
+      const double er = sg * cs, ei = sg * sn;
+      /* the parent's V, E (slack: 1+0j) */
+      double pvr = __shfl_sync(ANM_FULL, vr, psrc, LPE), pvi = __shfl_sync(ANM_FULL, vi, psrc, LPE);
+      double per = __shfl_sync(ANM_FULL, er, psrc, LPE), pei = __shfl_sync(ANM_FULL, ei, psrc, LPE);
+      if (pl < 0) { pvr = 1.0; pvi = 0.0; per = 1.0; pei = 0.0; }
+      /* I_b = Y_bb V_b + Y_bp V_p + sum_children Y_bc V_c ; the child computes its own term Y_pc V_c */
+      const double tbr = ybbr * vr - ybbi * vi, tbi = ybbr * vi + ybbi * vr; /* Y_bb V_b */
+      const double tpr = ybpr * pvr - ybpi * pvi, tpi = ybpr * pvi + ybpi * pvr; /* Y_bp V_p */
+      const double cr = ypbr * vr - ypbi * vi, ci = ypbr * vi + ypbi * vr;     /* Y_pb V_b, for the parent */
+      ir = tbr + tpr;
+      ii = tbi + tpi;
+      for (int s = 0; s < maxc; ++s) {
+        const int c = cl[s], src = (c < 0) ? lane : c;
+        const double gr = __shfl_sync(ANM_FULL, cr, src, LPE), gi = __shfl_sync(ANM_FULL, ci, src, LPE);
+        if (c >= 0) { ir += gr; ii += gi; }
+      }
+      /* mismatch rows (:84-120): S_b = V_b conj(I_b) */
+      const double f0 = (vr * ir + vi * ii) - pb, f1 = (vi * ir - vr * ii) - qb;
+      const unsigned nanb = __ballot_sync(ANM_FULL, active && ((f0 != f0) || (f1 != f1)));
+      const unsigned bigb = __ballot_sync(ANM_FULL, active && (fabs(f0) > ANM_NR_TOL || fabs(f1) > ANM_NR_TOL));
+      if (!done) {
+        bad = (nanb & gm) != 0u; /* numpy: norm(F, inf) is NaN, and `nan > tol` is False (:218) */
+        big = (bigb & gm) != 0u;
+#if ANM_DIAG
+        if (bad || !big || it >= ANM_NR_MAXIT) done = true, t_done = clock64(); else ++it;
+#else
+        if (bad || !big || it >= ANM_NR_MAXIT) done = true; else ++it;
+#endif
+      }
+      if (__all_sync(ANM_FULL, done)) break;
+
+      /* Jacobian blocks, rows (dP, dQ) x columns (dtheta, d|V|) */
+      const double jr = -vi, ji = vr; /* j V_b */
+      /* D = J[b][b]: w = (jV_b) conj(I_b - Y_bb V_b), u = V_b conj(Y_bb E_b) + E_b conj(I_b) */
+      double d00, d01, d10, d11;
+      {
+        const double inr = ir - tbr, ini = ii - tbi;
+        const double gr = ybbr * er - ybbi * ei, gi = ybbr * ei + ybbi * er;
+        d00 = jr * inr + ji * ini;
+        d10 = ji * inr - jr * ini;
+        d01 = (vr * gr + vi * gi) + (er * ir + ei * ii);
+        d11 = (vi * gr - vr * gi) + (ei * ir - er * ii);
+      }
+      /* L = J[b][p]: w = (jV_b) conj(-Y_bp V_p), u = V_b conj(Y_bp E_p) */
+      double l00, l01, l10, l11;
+      {
+        const double gr = ybpr * per - ybpi * pei, gi = ybpr * pei + ybpi * per;
+        l00 = -(jr * tpr + ji * tpi);
+        l10 = -(ji * tpr - jr * tpi);
+        l01 = vr * gr + vi * gi;
+        l11 = vi * gr - vr * gi;
+      }
+      /* U = J[p][b]: w = (jV_p) conj(-Y_pb V_b), u = V_p conj(Y_pb E_b) */
+      double u00, u01, u10, u11;
+      {
+        const double qr = -pvi, qi = pvr; /* j V_p */
+        const double gr = ypbr * er - ypbi * ei, gi = ypbr * ei + ypbi * er;
+        u00 = -(qr * cr + qi * ci);
+        u10 = -(qi * cr - qr * ci);
+        u01 = pvr * gr + pvi * gi;
+        u11 = pvi * gr - pvr * gi;
+      }
+      const double o00 = d00, o01 = d01, o10 = d10, o11 = d11; /* untouched copies for the dense fallback */
+      double r0 = f0, r1 = f1;
+      double rdet = 0.0;
+      bool susp = false;
+      /* leaves -> root: bus b (depth lev) folds U D^-1 [L | f] into its parent */
+      for (int lev = maxd; lev >= 2; --lev) {
+        const double det = d00 * d11 - d01 * d10;
+        const double rd = 1.0 / det;
+        const bool mine = (depth == lev);
+        if (mine) {
+          rdet = rd;
+          susp = susp || !(fabs(det) > 1e-10 * (fabs(d00 * d11) + fabs(d01 * d10)));
+        }
+        /* T = adj(D) [L | f],  C = U T / det */
+        const double t00 = d11 * l00 - d01 * l10, t01 = d11 * l01 - d01 * l11;
+        const double t10 = d00 * l10 - d10 * l00, t11 = d00 * l11 - d10 * l01;
+        const double tf0 = d11 * r0 - d01 * r1, tf1 = d00 * r1 - d10 * r0;
+        const double c00 = (u00 * t00 + u01 * t10) * rd, c01 = (u00 * t01 + u01 * t11) * rd;
+        const double c10 = (u10 * t00 + u11 * t10) * rd, c11 = (u10 * t01 + u11 * t11) * rd;
+        const double cf0 = (u00 * tf0 + u01 * tf1) * rd, cf1 = (u10 * tf0 + u11 * tf1) * rd;
+        const bool gather = active && (depth + 1 == lev);
+        for (int s = 0; s < maxc; ++s) {
+          const int c = cl[s], src = (c < 0) ? lane : c;
+          const double g00 = __shfl_sync(ANM_FULL, c00, src, LPE), g01 = __shfl_sync(ANM_FULL, c01, src, LPE);
+          const double g10 = __shfl_sync(ANM_FULL, c10, src, LPE), g11 = __shfl_sync(ANM_FULL, c11, src, LPE);
+          const double gf0 = __shfl_sync(ANM_FULL, cf0, src, LPE), gf1 = __shfl_sync(ANM_FULL, cf1, src, LPE);
+          if (gather && c >= 0) {
+            d00 -= g00; d01 -= g01; d10 -= g10; d11 -= g11;
+            r0 -= gf0; r1 -= gf1;
+          }
+        }
+      }
+      /* root level (children of the slack): plain 2x2 solves */
+      double x0 = 0.0, x1 = 0.0;
+      {
+        const double det = d00 * d11 - d01 * d10;
+        if (depth == 1) {
+          rdet = 1.0 / det;
+          susp = susp || !(fabs(det) > 1e-10 * (fabs(d00 * d11) + fabs(d01 * d10)));
+          x0 = (d11 * r0 - d01 * r1) * rdet;
+          x1 = (d00 * r1 - d10 * r0) * rdet;
+        }
+      }
+      /* root -> leaves: x_b = D^-1 (f - L x_p) */
+      for (int lev = 2; lev <= maxd; ++lev) {
+        const double xp0 = __shfl_sync(ANM_FULL, x0, psrc, LPE), xp1 = __shfl_sync(ANM_FULL, x1, psrc, LPE);
+        if (depth == lev) {
+          const double q0 = r0 - (l00 * xp0 + l01 * xp1), q1 = r1 - (l10 * xp0 + l11 * xp1);
+          x0 = (d11 * q0 - d01 * q1) * rdet;
+          x1 = (d00 * q1 - d10 * q0) * rdet;
+        }
+      }
+      /* rare: a numerically singular diagonal block -> dense partial-pivoting solve of this iteration */
+      const unsigned suspb = __ballot_sync(ANM_FULL, active && susp);
+#if ANM_DIAG
+      if (!done && (suspb & gm) != 0u) ++n_fb;
+#endif
+      if (suspb != 0u) {
+        for (int k = lane; k < M * (M + 1); k += LPE) J[k] = 0.0;
+        __syncwarp();
+        if (active) {
+          const int LD = M + 1, rp = b - 1, rq = n + b - 1;
+          J[rp * LD + rp] = o00; J[rp * LD + rq] = o01; J[rq * LD + rp] = o10; J[rq * LD + rq] = o11;
+          J[rp * LD + M] = f0; J[rq * LD + M] = f1;
+          if (pl >= 0) {
+            const int cp = pl, cq = n + pl;
+            J[rp * LD + cp] = l00; J[rp * LD + cq] = l01; J[rq * LD + cp] = l10; J[rq * LD + cq] = l11;
+            J[cp * LD + rp] = u00; J[cp * LD + rq] = u01; J[cq * LD + rp] = u10; J[cq * LD + rq] = u11;
+          }
+        }
+        __syncwarp();
+        gj_pivot_smem<LPE, true>(J, M, dxs, lane, gm);
+        if ((suspb & gm) != 0u && active) {
+          x0 = dxs[b - 1];
+          x1 = dxs[n + b - 1];
+        }
+        __syncwarp();
+      }
+      if (active && !done) { /* x <- x - J^{-1} F (:220) */
+        th -= x0;
+        vm -= x1;
+      }
+    }
+    /* publish V, I for the post-processing phases (bus 0: V = 1+0j, I_0 = Y_00 + sum_children Y_0c V_c) */
+    if (active) {
+      vre[b] = vr; vim[b] = vi; ire[b] = ir; iim[b] = ii;
+    }
+    {
+      const double cr = ypbr * vr - ypbi * vi, ci = ypbr * vi + ypbi * vr;
+      double sr = (active && pl < 0) ? cr : 0.0, si = (active && pl < 0) ? ci : 0.0;
+#pragma unroll
+      for (int o = LPE / 2; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(ANM_FULL, sr, o);
+        si += __shfl_xor_sync(ANM_FULL, si, o);
+      }
+      if (lane == 0) {
+        vre[0] = 1.0; vim[0] = 0.0;
+        ire[0] = C.y_dense[0] + sr;
+        iim[0] = C.y_dense[1] + si;
+      }
+    }
+    __syncwarp();
+    it_out = it;
+    converged_out = !bad;
+    stable_out = !bad && !big; /* solve_load_flow.py:49 */
+#if ANM_DIAG
+    n_fb = (n_fb & 0xffff) | ((int)((t_done - t_loop0) >> 4) << 16);
+#endif
+  }
+};
+
 /* ---- one Simulator.transition for one environment ----------------------------------------
  * Inputs in the workspace: in_pl, in_pp, in_ps, in_qs (MW / MVAr), soc (p.u.).
  * Leaves dev_p/q, ppot, bus_p/q, V, I, branch quantities in the workspace.  Returns `stable`
  * and the (unclipped) reward terms to every lane of the group.  `live` = this group has a real
  * environment (a dead group runs along for lock-step but skips the Newton iterations). */
-template <int LPE, int NB, bool FULL>
+template <int LPE, int NB, int SOLVER, bool FULL>
 __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
                                            double& e_loss, double& penalty, int& n_iter_out, int& n_fb, int& n_big) {
   const AnmConstHeader& H = *C.H;
@@ -763,7 +1002,9 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   int it = 0;
   bool converged = false, stable = false;
   n_fb = n_big = 0;
-  if constexpr (NB > 0)
+  if constexpr (SOLVER == 2)
+    RadialNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable, n_fb, n_big);
+  else if constexpr (SOLVER == 1)
     SmallNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable, n_fb, n_big);
   else
     nr_generic<LPE, FULL>(C, ws, lane, gm, live, it, converged, stable);
@@ -866,7 +1107,7 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
 /* what a lane group does with its environment in this pass */
 enum { ACT_NONE = 0, ACT_ZERO = 1, ACT_STEP = 2, ACT_RESET = 3, ACT_TRANSITION = 4 };
 
-template <int LPE, int NB>
+template <int LPE, int NB, int SOLVER>
 __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_THREADS, (NB > 0 && LPE <= 16) ? ANM_VAR_MINB : 1)
     anm_env_kernel(const AnmLaunch P) {
   constexpr bool FULL = (NB > 0) || (LPE == 32);
@@ -979,7 +1220,7 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 #if ANM_DIAG
     const long long t_pass0 = P.solver_stats ? clock64() : 0;
 #endif
-    const bool stable = transition<LPE, NB, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig);
+    const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig);
 #if ANM_DIAG
     if (P.solver_stats && run && lane == 0) {
       P.solver_stats[4 * e] = nfb & 0xffff;

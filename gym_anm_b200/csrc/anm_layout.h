@@ -43,9 +43,15 @@ struct AnmConstHeader {
   int32_t o_ov_off, o_ov_mul, o_ov_div, o_ov_low, o_ov_high; /* obs vars                       */
   int32_t o_table;                           /* double[table_len][n_load+n_gen]                */
   int32_t o_pair_i, o_pair_j;                /* int[ANM_NPAIRS]                                */
+  /* radial networks (bus graph = tree rooted at the slack): per non-slack bus b (lane b-1) */
+  int32_t is_radial, rad_maxc, rad_maxdepth;
+  int32_t o_rad_parent, o_rad_depth;         /* int[n_bus-1]: parent's lane (-1 = slack), depth >= 1 */
+  int32_t o_rad_child;                       /* int[n_bus-1][4]: children's lanes, -1 padded         */
+  int32_t o_rad_y;                           /* double[n_bus-1][6]: Y_bb, Y_b,parent, Y_parent,b     */
   /* per-env workspace offsets (in doubles) */
   int32_t w_in_pl, w_in_pp, w_in_ps, w_in_qs, w_soc, w_aux, w_devp, w_devq, w_ppot, w_busp, w_busq;
   int32_t w_x, w_vre, w_vim, w_ere, w_eim, w_ire, w_iim, w_J, w_rowh;
   int32_t w_brp, w_brq, w_brs, w_brire, w_briim, w_full, w_s0;
   int32_t w_vx; /* (Vre, Vim, Ere, Eim) x n_bus exchange buffer of the register-resident solver */
+  int32_t w_dx; /* Newton step written by the shared-memory solver */
 };

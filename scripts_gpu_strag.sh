@@ -1,2 +1,4 @@
 #!/bin/bash
-python tools/tail_probe2.py
+export ANM_B200_LIB=$PWD/gym_anm_b200/lib/libanm_b200_diag.so
+python tools/tail_probe.py 1.0
+ANM_FORCE_DENSE=1 python tools/tail_probe.py 1.0

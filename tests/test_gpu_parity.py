@@ -292,19 +292,22 @@ def test_state_dict_roundtrip_and_simulator_view():
     assert set(d) >= {"bus_v_magn", "dev_p", "branch_s", "des_soc", "gen_p_max"} and abs(d["bus_v_magn"]["pu"][0] - 1.0) < 1e-12
 
 
-def test_generic_kernels_same_results_subprocess():
-    """The shared-memory (generic) kernels are used for N >= 10 buses; force them for the small
-    networks too (ANM_FORCE_GENERIC=1) and re-run the golden/oracle parity tests in a subprocess."""
+def test_other_solvers_same_results_subprocess():
+    """Re-run the golden / oracle parity tests with the other Newton back-ends forced (ANM_SOLVER):
+    the shared-memory generic kernels (default for N >= 10 buses) and the tree-elimination solver."""
     import os
     import subprocess
     import sys
 
-    env = dict(os.environ, ANM_FORCE_GENERIC="1")
     here = os.path.abspath(__file__)
-    sel = "test_anm6easy_golden_trajectory or test_transition_goldens or test_batch_vs_oracle"
-    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
-                       env=env, capture_output=True, text=True, timeout=900)  # fmt: skip
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    sel = "test_anm6easy_golden_trajectory or test_transition_goldens or test_batch_vs_oracle or test_radial_tree"
+    # ANM_SOLVER selects the Newton back-end: generic (shared memory), radial (tree elimination); default dense
+    for val in ("generic", "radial"):
+        var = "ANM_SOLVER=" + val
+        env = dict(os.environ, ANM_SOLVER=val)
+        r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
+                           env=env, capture_output=True, text=True, timeout=900)  # fmt: skip
+        assert r.returncode == 0, var + "\n" + r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_power_flow_identities_at_full_size():
@@ -371,3 +374,69 @@ def test_power_flow_identities_at_full_size():
     # terminal rows: zeros and the terminal reward
     bad = ~ok
     assert np.all(obs.cpu().numpy()[bad] == 0) and np.all(np.isin(r.cpu().numpy()[bad], [0.0, -100 / (1 - 0.995)]))
+
+
+def _tree_network(seed=5):
+    """8-bus radial feeder with an off-nominal, phase-shifting transformer and a bus with 3 children."""
+    N_ = None
+    rng = np.random.default_rng(seed)
+    bus = np.array([[0, 0, 132, 1.0, 1.0]] + [[i, 1, 33, 1.1, 0.9] for i in range(1, 8)], dtype=np.float64)
+    #          0-1 (transformer), 1-2, 1-3, 1-4 (3 children), 2-5, 5-6 (depth 4), 3-7
+    edges = [(0, 1, 1.03, 8.0), (1, 2, 1, 0), (1, 3, 1, 0), (4, 1, 1, 0), (2, 5, 0.98, 0), (5, 6, 1, 0), (7, 3, 1, 0)]
+    branch = np.array([[f, t, rng.uniform(0.005, 0.03), rng.uniform(0.02, 0.08), rng.uniform(0, 0.02), 40, tap, sh]
+                       for f, t, tap, sh in edges])
+    device = np.array([
+        [0, 0, 0, N_, 300, -300, 300, -300, N_, N_, N_, N_, N_, N_, N_],
+        [1, 2, -1, 0.25, 0, -12, N_, N_, N_, N_, N_, N_, N_, N_, N_],
+        [2, 4, -1, 0.2, 0, -8, N_, N_, N_, N_, N_, N_, N_, N_, N_],
+        [3, 6, -1, 0.3, 0, -15, N_, N_, N_, N_, N_, N_, N_, N_, N_],
+        [4, 7, -1, 0.2, 0, -10, N_, N_, N_, N_, N_, N_, N_, N_, N_],
+        [5, 5, 2, N_, 20, 0, 20, -20, 14, N_, 10, -10, N_, N_, N_],
+        [6, 3, 2, N_, 15, 0, 15, -15, 10, N_, 8, -8, N_, N_, N_],
+        [7, 6, 3, N_, 10, -10, 10, -10, 6, -6, 5, -5, 40, 0, 0.9],
+        [8, 1, 1, N_, 25, 0, 20, -20, N_, N_, N_, N_, N_, N_, N_],
+    ], dtype=object)
+    return {"baseMVA": 100.0, "bus": bus, "branch": branch, "device": device}
+
+
+@pytest.mark.parametrize("stress", [1.0, 4.0])
+def test_radial_tree_vs_oracle(stress):
+    """Tree elimination (RadialNR) on a general radial feeder: transformer tap + phase shift (asymmetric Y),
+    a bus with three children, depth 4; `stress` scales the ratings so that part of the batch diverges."""
+    import anm_oracle
+    from gym_anm_b200.env_spec import HostEnvSpec
+    from gym_anm_b200.native import NativeBatch
+
+    net = _tree_network()
+    for row in net["device"][1:]:
+        for c in (4, 5, 6, 7, 8, 9, 10, 11):
+            if row[c] is not None:
+                row[c] = row[c] * stress
+    spec = HostEnvSpec(net, "state", 0, 0.25, 0.9, 100)
+    cn = spec.cn
+    B = 1024
+    nb, cpu = NativeBatch(spec, B), anm_oracle.OracleEnv(spec, B)
+    assert nb.sizes["lanes_per_env"] in (8, 16, 32)
+    rng = np.random.default_rng(8)
+    soc0 = rng.uniform(0, 0.4, (B, 1))
+    nb.set_state(soc=soc0)
+    cpu.soc[:] = soc0
+    sl = spec.full_state_slices()
+    n_div = 0
+    for t in range(4):
+        p_load = rng.uniform([cn.devices[i].p_min * 100 for i in cn.load_ids], 0, (B, cn.N_load))
+        hi = np.array([cn.devices[i].p_max * 100 for i in cn.gen_ids])
+        p_pot = rng.uniform(0, hi, (B, len(hi)))
+        ctrl = list(cn.gen_ids) + list(cn.des_ids)
+        p_set = rng.uniform([cn.devices[i].p_min * 100 for i in ctrl], [cn.devices[i].p_max * 100 for i in ctrl], (B, len(ctrl)))
+        q_set = rng.uniform([cn.devices[i].q_min * 100 for i in ctrl], [cn.devices[i].q_max * 100 for i in ctrl], (B, len(ctrl)))
+        full, r, e, pe, conv = nb.transition(p_load, p_pot, p_set, q_set)
+        fc, rc, ec, pc, cc, nit = cpu.transition(p_load, p_pot, p_set, q_set)
+        cg = conv.cpu().numpy().astype(bool)
+        assert np.array_equal(cg, cc), (t, int((cg != cc).sum()))
+        n_div += int((~cc).sum())
+        f = full.cpu().numpy()
+        for k in ("bus_p", "bus_q", "bus_v_magn", "bus_v_ang", "dev_p", "dev_q", "des_soc", "branch_p", "branch_q", "branch_s"):
+            assert rel_err(f[cc][:, sl[k]], fc[cc][:, sl[k]]) < RTOL, (t, k)
+        assert rel_err(r.cpu().numpy()[cc], rc[cc]) < 1e-7
+    assert (n_div > 0) == (stress > 1.0)

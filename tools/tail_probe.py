@@ -36,10 +36,14 @@ G = 200
 graph = torch.cuda.CUDAGraph()
 side = torch.cuda.Stream()
 side.wait_stream(torch.cuda.current_stream())
+acc = torch.zeros_like(stats)      # per-instance maxima over all steps
+fbsum = torch.zeros(B, dtype=torch.int64, device="cuda")
 with torch.cuda.stream(side):
     with torch.cuda.graph(graph, stream=side):
         for t in range(G):
             nb.step(ring[t], None, out=(obs, rew, term), extras=ex)
+            torch.maximum(acc, stats, out=acc)
+            fbsum += stats[:, 0]
 torch.cuda.current_stream().wait_stream(side)
 graph.replay()
 torch.cuda.synchronize()
@@ -61,3 +65,7 @@ print("  ordinary : Newton-loop cycles  median %d  max %d  -> %.0f cycles / iter
       % (np.median(loop[~strag]), loop[~strag].max(), np.median(loop[~strag] / np.maximum(ni[~strag], 1)), np.median(st[~strag, 3]), st[~strag, 3].max()))
 if strag.any():
     print("  divergent: whole pass cycles median %d max %d" % (np.median(st[strag, 3]), st[strag, 3].max()))
+
+a = acc.cpu().numpy().astype(np.int64)
+print("  over all steps: max Newton-loop cycles %d (%.0f / iteration), max pass cycles %d (%.1f us @1.965 GHz), max fallback its in one solve %d, fallback its total %d"
+      % (a[:, 2].max() * 16, a[:, 2].max() * 16 / 100, a[:, 3].max(), a[:, 3].max() / 1965.0, a[:, 0].max(), int(fbsum.sum())))
