@@ -9,7 +9,8 @@ from .errors import *  # noqa: F401,F403
 from .network_spec import CompiledNetwork  # noqa: F401
 from .env_spec import HostEnvSpec, anm6easy_spec  # noqa: F401
 
-__all__ = ["ANM6Easy", "BatchedANM6Easy", "BatchedANMEnv", "BatchedSimulator", "CompiledNetwork", "HostEnvSpec"]
+__all__ = ["ANM6Easy", "BatchedANM6Easy", "BatchedANMEnv", "BatchedSimulator", "CompiledNetwork", "HostEnvSpec",
+           "MPCAgentConstant", "MPCAgentPerfect"]
 
 
 def __getattr__(name):  # torch-dependent modules are imported lazily
@@ -21,6 +22,10 @@ def __getattr__(name):  # torch-dependent modules are imported lazily
         from .anm_env import BatchedANMEnv
 
         return BatchedANMEnv
+    if name in ("MPCAgentConstant", "MPCAgentPerfect"):
+        from . import agents
+
+        return getattr(agents, name)
     if name == "BatchedSimulator":
         from .simulator import BatchedSimulator
 

@@ -440,3 +440,30 @@ def test_radial_tree_vs_oracle(stress):
             assert rel_err(f[cc][:, sl[k]], fc[cc][:, sl[k]]) < RTOL, (t, k)
         assert rel_err(r.cpu().numpy()[cc], rc[cc]) < 1e-7
     assert (n_div > 0) == (stress > 1.0)
+
+
+def test_mpc_constant_agent_drives_batched_env_config5():
+    """BASELINE config 5 in small: MPCAgentConstant(planning_steps=10, safety_margin=0.96)
+    (examples/mpc_constant.py:21) picks the actions from the batched env's own state; the same action
+    tensor is fed to the GPU path and the C oracle."""
+    import anm_oracle
+    from gym_anm_b200.agents import MPCAgentConstant
+    from gym_anm_b200.anm6 import BatchedANM6Easy
+
+    B = 32
+    env = BatchedANM6Easy(B, validate_actions=True)
+    env.reset(seed=16384)
+    agent = MPCAgentConstant(env.simulator, env.action_space, env.gamma, safety_margin=0.96, planning_steps=10)
+    cpu = anm_oracle.OracleEnv(env.spec, B)
+    soc, aux, term = env.native.get_state()
+    cpu.soc[:], cpu.aux[:], cpu.terminated[:] = soc.cpu().numpy(), aux.cpu().numpy(), 0
+    total = 0.0
+    for t in range(8):
+        a = agent.act(env)
+        assert a.shape == (B, 6)
+        obs_g, r_g, term_g, _, _ = env.step(a)
+        obs_c, r_c, term_c, _ = cpu.step(a)
+        assert not term_c.any() and np.array_equal(term_g.cpu().numpy(), term_c)
+        assert rel_err(obs_g.cpu().numpy(), obs_c) < RTOL and rel_err(r_g.cpu().numpy(), r_c) < RTOL
+        total += float(r_g.mean())
+    assert total / 8 > -5.0  # the MPC policy operates the grid at low cost
