@@ -343,6 +343,9 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
   return 0;
 }
 
+#ifndef ANM_HOST_IO_DEFAULT
+#define ANM_HOST_IO_DEFAULT 2 /* zero-copy when the caller's buffers are pinned: +14 % e2e on B200 (profiles/) */
+#endif
 typedef void (*kernel_fn)(const AnmLaunch);
 /* Solver selection (anm_kernels.cuh), overridable with the environment variable ANM_SOLVER:
  *   dense   (default for <= 9 buses)  Jacobian rows in registers, natural-order Gauss-Jordan     SmallNR
@@ -457,6 +460,33 @@ struct DeviceGuard {
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+
+/* Host-buffer I/O mode of anm_step_host (environment variable ANM_HOST_IO):
+ *   copy    stage through device buffers with cudaMemcpyAsync (works for any host memory)
+ *   zc      zero-copy: if a buffer is pinned (cudaHostAlloc / cudaHostRegister, e.g. a torch pinned tensor) the
+ *           kernel reads the actions from it / writes obs, reward, terminated into it directly over PCIe
+ *   zc_out  zero-copy for the outputs only
+ * Pageable buffers always take the copy path. */
+static int host_io_mode() {
+  static const int m = [] {
+    const char* e = getenv("ANM_HOST_IO");
+    if (e && !strcmp(e, "copy")) return 0;
+    if (e && !strcmp(e, "zc")) return 2;
+    if (e && !strcmp(e, "zc_out")) return 1;
+    return ANM_HOST_IO_DEFAULT;
+  }();
+  return m;
+}
+template <typename T>
+static T* mapped_device_pointer(T* host_ptr) { /* NULL unless the host buffer is pinned and mapped */
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, (const void*)host_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (attr.type == cudaMemoryTypeHost) ? (T*)attr.devicePointer : nullptr;
+}
 
 }  // namespace
 
@@ -615,13 +645,26 @@ int anm_step_host(anm_handle h, const double* action, const double* next_vars, d
   const AnmConstHeader& H = h->H;
   const size_t B = (size_t)h->B;
   cudaStream_t st = h->stream;
-  CUDA_TRY(cudaMemcpyAsync(h->s_action, action, B * H.n_action * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (next_vars) CUDA_TRY(cudaMemcpyAsync(h->s_nv, next_vars, B * H.n_next_vars * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = anm_step(h, h->s_action, next_vars ? h->s_nv : nullptr, h->s_obs, h->s_reward, h->s_term, nullptr, st);
+  const int mode = host_io_mode();
+  const double* d_action = (mode >= 2) ? mapped_device_pointer(action) : nullptr;
+  const double* d_nv = (mode >= 2 && next_vars) ? mapped_device_pointer(next_vars) : nullptr;
+  double* d_obs = (mode >= 1) ? mapped_device_pointer(obs) : nullptr;
+  double* d_reward = (mode >= 1) ? mapped_device_pointer(reward) : nullptr;
+  uint8_t* d_term = (mode >= 1) ? mapped_device_pointer(terminated) : nullptr;
+  if (!d_action) {
+    CUDA_TRY(cudaMemcpyAsync(h->s_action, action, B * H.n_action * sizeof(double), cudaMemcpyHostToDevice, st));
+    d_action = h->s_action;
+  }
+  if (next_vars && !d_nv) {
+    CUDA_TRY(cudaMemcpyAsync(h->s_nv, next_vars, B * H.n_next_vars * sizeof(double), cudaMemcpyHostToDevice, st));
+    d_nv = h->s_nv;
+  }
+  int rc = anm_step(h, d_action, next_vars ? d_nv : nullptr, d_obs ? d_obs : h->s_obs, d_reward ? d_reward : h->s_reward,
+                    d_term ? d_term : h->s_term, nullptr, st);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(obs, h->s_obs, B * H.n_obs * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(reward, h->s_reward, B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(terminated, h->s_term, B, cudaMemcpyDeviceToHost, st));
+  if (!d_obs) CUDA_TRY(cudaMemcpyAsync(obs, h->s_obs, B * H.n_obs * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (!d_reward) CUDA_TRY(cudaMemcpyAsync(reward, h->s_reward, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (!d_term) CUDA_TRY(cudaMemcpyAsync(terminated, h->s_term, B, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return ANM_OK;
 }

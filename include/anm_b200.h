@@ -205,7 +205,9 @@ int anm_set_state(anm_handle h, const double* soc_dev, const double* aux_dev,
 
 /* Host-buffer convenience path (what a NumPy caller uses): pinned-or-pageable HOST
  * arrays in, HOST arrays out; performs H2D copy, the step, D2H copies on the handle's
- * own stream and synchronises it before returning. */
+ * own stream and synchronises it before returning.  Pinned (page-locked, mapped) buffers are accessed by the
+ * kernel directly over PCIe (zero-copy); pageable buffers are staged with cudaMemcpyAsync.
+ * ANM_HOST_IO=copy|zc_out|zc (environment) overrides. */
 int anm_step_host(anm_handle h, const double* action_host, const double* next_vars_host_or_null,
                   double* obs_host, double* reward_host, uint8_t* terminated_host);
 int anm_reset_host(anm_handle h, const double* s0_host, const uint8_t* mask_host_or_null,
