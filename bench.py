@@ -409,7 +409,7 @@ def run_ours(args):
         },
         "clocks": clocks,
         "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 6 * 8,
-                "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "api": "anm_step_host (C ABI; pinned host buffers, read / written by the kernel over PCIe = zero-copy; "ANM_HOST_IO=copy stages through cudaMemcpyAsync instead)",
+                "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "api": "anm_step_host (C ABI; pinned host buffers, read / written by the kernel over PCIe = zero-copy; ANM_HOST_IO=copy stages through cudaMemcpyAsync instead)",
                 "checksum": checksum},  # fmt: skip
         "gpu_launches": gpu_launches,
         "roofline": roofline,
