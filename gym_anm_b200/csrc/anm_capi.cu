@@ -348,12 +348,10 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
 #endif
 typedef void (*kernel_fn)(const AnmLaunch);
 /* Solver selection (anm_kernels.cuh), overridable with the environment variable ANM_SOLVER:
- *   dense   (default for <= 9 buses)  Jacobian rows in registers, natural-order Gauss-Jordan     SmallNR
- *   radial  (opt-in, tree networks)   2x2-block elimination along the tree, one bus per lane    RadialNR
- *   generic (default for > 9 buses)   Jacobian in shared memory, partial pivoting                nr_generic
- * On B200 `radial` has a ~13 % shorter Newton iteration for a lone warp and packs 4 environments per warp, but its
- * dense fallback is slow and fires in ~0.5 % of the divergent solves; measured 0.29 vs 0.20 ms/step on the ANM6Easy
- * bench (profiles/r01_v3_register_kernel.md), so it stays opt-in until that is fixed.
+ *   radial  (default for tree networks <= 9 buses)   2x2-block elimination along the tree, one bus per lane  RadialNR
+ *   dense   (default for meshed networks <= 9 buses) Jacobian rows in registers, natural-order Gauss-Jordan   SmallNR
+ *   generic (default for > 9 buses)                  Jacobian in shared memory, partial pivoting              nr_generic
+ * B200, ANM6Easy bench: radial 0.149 ms/step, dense 0.198 ms/step (profiles/r01_v4_radial_kernel.md).
  * ANM_FORCE_GENERIC=1 / ANM_FORCE_DENSE=1 are kept as aliases (tests). */
 static int solver_env() { /* -1: no override */
   static const int v = [] {
@@ -370,7 +368,7 @@ static int solver_env() { /* -1: no override */
 static int solver_for(const AnmConstHeader& H) {
   const int want = solver_env();
   if (want == 0 || H.n_bus < 2 || H.n_bus > 9) return 0;
-  if (want == 2 && H.is_radial) return 2;
+  if (want != 1 && H.is_radial) return 2;
   return 1;
 }
 static int lanes_for(const AnmConstHeader& H) {

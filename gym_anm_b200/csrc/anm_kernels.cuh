@@ -232,6 +232,16 @@ __device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
   *cs = ((q + 1) & 2) ? -c1 : c1;
 }
 
+/* 1/x to ~1 ulp without the IEEE corner-case handling of `1.0 / x`: MUFU.RCP64H seed + two Newton steps.
+ * x = 0 / inf / NaN give inf / 0 / NaN-like garbage, which is what the callers want (the Newton loop then ends). */
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+
 struct Cst {  // resolved pointers into the staged blob
   const AnmConstHeader* H;
   const double *vmin, *vmax, *dev_param, *br_coef, *y_val, *ctrl_rows, *sv_mul, *sv_div, *ov_mul, *ov_div, *ov_low,
@@ -695,9 +705,10 @@ struct SmallNR {
  * along the tree: leaves first, every bus folds  U D^-1 [L | f]  into its parent's (D, f) (one shuffle
  * round per tree level), then the step is back-substituted from the root down -- the critical path is the
  * tree depth instead of 2(N-1) pivots, and an environment needs only N-1 lanes.  2x2 diagonal blocks are
- * inverted by the adjugate; a numerically singular block (|det| << |d00 d11| + |d01 d10|) sends that
- * iteration to the dense partial-pivoting solver in shared memory.  Lock-step lane groups, full-mask
- * intrinsics, like SmallNR. */
+ * inverted by the adjugate.  No pivoting across blocks: det J = prod det(D_b), so a singular block means a
+ * singular Jacobian, for which a pivoted solve returns garbage as well (the reference gets NaN from SuperLU,
+ * solve_load_flow.py:220) -- the instance then fails to converge either way.  Lock-step lane groups,
+ * full-mask intrinsics, like SmallNR. */
 #define ANM_RAD_MAXC 4
 template <int LPE, int NB>
 struct RadialNR {
@@ -709,7 +720,6 @@ struct RadialNR {
     const AnmConstHeader& H = *C.H;
     const double* busp = ws + H.w_busp; const double* busq = ws + H.w_busq;
     double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ire = ws + H.w_ire; double* iim = ws + H.w_iim;
-    double* J = ws + H.w_J; double* dxs = ws + H.w_dx;
     const bool active = lane < n;
     const int bl = active ? lane : 0;  /* clamp for the table reads of idle lanes */
     const int b = bl + 1;
@@ -802,19 +812,14 @@ struct RadialNR {
         u01 = pvr * gr + pvi * gi;
         u11 = pvi * gr - pvr * gi;
       }
-      const double o00 = d00, o01 = d01, o10 = d10, o11 = d11; /* untouched copies for the dense fallback */
       double r0 = f0, r1 = f1;
       double rdet = 0.0;
-      bool susp = false;
       /* leaves -> root: bus b (depth lev) folds U D^-1 [L | f] into its parent */
       for (int lev = maxd; lev >= 2; --lev) {
         const double det = d00 * d11 - d01 * d10;
-        const double rd = 1.0 / det;
+        const double rd = fast_rcp(det);
         const bool mine = (depth == lev);
-        if (mine) {
-          rdet = rd;
-          susp = susp || !(fabs(det) > 1e-10 * (fabs(d00 * d11) + fabs(d01 * d10)));
-        }
+        if (mine) rdet = rd;
         /* T = adj(D) [L | f],  C = U T / det */
         const double t00 = d11 * l00 - d01 * l10, t01 = d11 * l01 - d01 * l11;
         const double t10 = d00 * l10 - d10 * l00, t11 = d00 * l11 - d10 * l01;
@@ -839,8 +844,7 @@ struct RadialNR {
       {
         const double det = d00 * d11 - d01 * d10;
         if (depth == 1) {
-          rdet = 1.0 / det;
-          susp = susp || !(fabs(det) > 1e-10 * (fabs(d00 * d11) + fabs(d01 * d10)));
+          rdet = fast_rcp(det);
           x0 = (d11 * r0 - d01 * r1) * rdet;
           x1 = (d00 * r1 - d10 * r0) * rdet;
         }
@@ -853,32 +857,6 @@ struct RadialNR {
           x0 = (d11 * q0 - d01 * q1) * rdet;
           x1 = (d00 * q1 - d10 * q0) * rdet;
         }
-      }
-      /* rare: a numerically singular diagonal block -> dense partial-pivoting solve of this iteration */
-      const unsigned suspb = __ballot_sync(ANM_FULL, active && susp);
-#if ANM_DIAG
-      if (!done && (suspb & gm) != 0u) ++n_fb;
-#endif
-      if (suspb != 0u) {
-        for (int k = lane; k < M * (M + 1); k += LPE) J[k] = 0.0;
-        __syncwarp();
-        if (active) {
-          const int LD = M + 1, rp = b - 1, rq = n + b - 1;
-          J[rp * LD + rp] = o00; J[rp * LD + rq] = o01; J[rq * LD + rp] = o10; J[rq * LD + rq] = o11;
-          J[rp * LD + M] = f0; J[rq * LD + M] = f1;
-          if (pl >= 0) {
-            const int cp = pl, cq = n + pl;
-            J[rp * LD + cp] = l00; J[rp * LD + cq] = l01; J[rq * LD + cp] = l10; J[rq * LD + cq] = l11;
-            J[cp * LD + rp] = u00; J[cp * LD + rq] = u01; J[cq * LD + rp] = u10; J[cq * LD + rq] = u11;
-          }
-        }
-        __syncwarp();
-        gj_pivot_smem<LPE, true>(J, M, dxs, lane, gm);
-        if ((suspb & gm) != 0u && active) {
-          x0 = dxs[b - 1];
-          x1 = dxs[n + b - 1];
-        }
-        __syncwarp();
       }
       if (active && !done) { /* x <- x - J^{-1} F (:220) */
         th -= x0;
