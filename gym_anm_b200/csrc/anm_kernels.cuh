@@ -726,9 +726,13 @@ struct RadialNR {
     const int pl = active ? C.rad_parent[bl] : -1; /* parent's lane, -1: the slack bus */
     const int depth = active ? C.rad_depth[bl] : 0;
     const int maxc = H.rad_maxc, maxd = H.rad_maxdepth;
-    int cl[ANM_RAD_MAXC];
+    /* children's lanes packed into one register (byte s = lane of child s, 0xff = none): no local-memory array */
+    unsigned cpack = 0xffffffffu;
+    if (active) {
+      cpack = 0u;
 #pragma unroll
-    for (int s = 0; s < ANM_RAD_MAXC; ++s) cl[s] = active ? C.rad_child[bl * ANM_RAD_MAXC + s] : -1;
+      for (int s = 0; s < ANM_RAD_MAXC; ++s) cpack |= ((unsigned)C.rad_child[bl * ANM_RAD_MAXC + s] & 0xffu) << (8 * s);
+    }
     const double* yv = C.rad_y + 6 * bl;
     const double ybbr = yv[0], ybbi = yv[1], ybpr = yv[2], ybpi = yv[3], ypbr = yv[4], ypbi = yv[5];
     const double pb = busp[b], qb = busq[b];
@@ -761,10 +765,12 @@ struct RadialNR {
       const double cr = ypbr * vr - ypbi * vi, ci = ypbr * vi + ypbi * vr;     /* Y_pb V_b, for the parent */
       ir = tbr + tpr;
       ii = tbi + tpi;
-      for (int s = 0; s < maxc; ++s) {
-        const int c = cl[s], src = (c < 0) ? lane : c;
+#pragma unroll
+      for (int s = 0; s < ANM_RAD_MAXC; ++s) {
+        if (s >= maxc) break; /* warp-uniform */
+        const int cb = (int)((cpack >> (8 * s)) & 0xffu), src = (cb == 0xff) ? lane : cb;
         const double gr = __shfl_sync(ANM_FULL, cr, src, LPE), gi = __shfl_sync(ANM_FULL, ci, src, LPE);
-        if (c >= 0) { ir += gr; ii += gi; }
+        if (cb != 0xff) { ir += gr; ii += gi; }
       }
       /* mismatch rows (:84-120): S_b = V_b conj(I_b) */
       const double f0 = (vr * ir + vi * ii) - pb, f1 = (vi * ir - vr * ii) - qb;
@@ -815,7 +821,9 @@ struct RadialNR {
       double r0 = f0, r1 = f1;
       double rdet = 0.0;
       /* leaves -> root: bus b (depth lev) folds U D^-1 [L | f] into its parent */
-      for (int lev = maxd; lev >= 2; --lev) {
+#pragma unroll
+      for (int lev = NB - 1; lev >= 2; --lev) {
+        if (lev > maxd) continue; /* warp-uniform */
         const double det = d00 * d11 - d01 * d10;
         const double rd = fast_rcp(det);
         const bool mine = (depth == lev);
@@ -828,12 +836,14 @@ struct RadialNR {
         const double c10 = (u10 * t00 + u11 * t10) * rd, c11 = (u10 * t01 + u11 * t11) * rd;
         const double cf0 = (u00 * tf0 + u01 * tf1) * rd, cf1 = (u10 * tf0 + u11 * tf1) * rd;
         const bool gather = active && (depth + 1 == lev);
-        for (int s = 0; s < maxc; ++s) {
-          const int c = cl[s], src = (c < 0) ? lane : c;
+#pragma unroll
+        for (int s = 0; s < ANM_RAD_MAXC; ++s) {
+          if (s >= maxc) break; /* warp-uniform */
+          const int cb = (int)((cpack >> (8 * s)) & 0xffu), src = (cb == 0xff) ? lane : cb;
           const double g00 = __shfl_sync(ANM_FULL, c00, src, LPE), g01 = __shfl_sync(ANM_FULL, c01, src, LPE);
           const double g10 = __shfl_sync(ANM_FULL, c10, src, LPE), g11 = __shfl_sync(ANM_FULL, c11, src, LPE);
           const double gf0 = __shfl_sync(ANM_FULL, cf0, src, LPE), gf1 = __shfl_sync(ANM_FULL, cf1, src, LPE);
-          if (gather && c >= 0) {
+          if (gather && cb != 0xff) {
             d00 -= g00; d01 -= g01; d10 -= g10; d11 -= g11;
             r0 -= gf0; r1 -= gf1;
           }
@@ -850,7 +860,9 @@ struct RadialNR {
         }
       }
       /* root -> leaves: x_b = D^-1 (f - L x_p) */
-      for (int lev = 2; lev <= maxd; ++lev) {
+#pragma unroll
+      for (int lev = 2; lev <= NB - 1; ++lev) {
+        if (lev > maxd) break; /* warp-uniform */
         const double xp0 = __shfl_sync(ANM_FULL, x0, psrc, LPE), xp1 = __shfl_sync(ANM_FULL, x1, psrc, LPE);
         if (depth == lev) {
           const double q0 = r0 - (l00 * xp0 + l01 * xp1), q1 = r1 - (l10 * xp0 + l11 * xp1);
