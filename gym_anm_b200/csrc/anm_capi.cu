@@ -94,6 +94,36 @@ struct anm_handle_s {
 
 namespace {
 
+/* Solver selection (anm_kernels.cuh), decided when the handle is created; ANM_SOLVER (environment) overrides:
+ *   radial  (default for tree networks <= 9 buses)   2x2-block elimination along the tree, one bus per lane  RadialNR
+ *   dense   (default for meshed networks <= 9 buses) Jacobian rows in registers, natural-order Gauss-Jordan   SmallNR
+ *   sparse  (default for > 9 buses)                  block-sparse LU on the filled Y-bus pattern, host-side
+ *                                                    symbolic factorisation                                   nr_sparse
+ *   generic                                          dense Jacobian in shared memory, partial pivoting        nr_generic
+ * B200, ANM6Easy bench: radial 0.147 ms/step, dense 0.198 ms/step; synthetic 30-bus: see profiles/.
+ * ANM_FORCE_GENERIC=1 / ANM_FORCE_DENSE=1 are kept as aliases (tests). */
+static int solver_env() { /* -1: no override */
+  static const int v = [] {
+    const char* e = getenv("ANM_SOLVER");
+    if (e && !strcmp(e, "generic")) return 0;
+    if (e && !strcmp(e, "dense")) return 1;
+    if (e && !strcmp(e, "radial")) return 2;
+    if (e && !strcmp(e, "sparse")) return 4;
+    if (getenv("ANM_FORCE_GENERIC") && atoi(getenv("ANM_FORCE_GENERIC")) != 0) return 0;
+    if (getenv("ANM_FORCE_DENSE") && atoi(getenv("ANM_FORCE_DENSE")) != 0) return 1;
+    return -1;
+  }();
+  return v;
+}
+static int choose_solver(int n_bus, bool is_radial) {
+  const int want = solver_env();
+  if (want == 0 || want == 4) return want;
+  if (n_bus > 9) return 4;
+  if (want != 1 && is_radial) return 2;
+  return 1;
+}
+static int solver_for(const AnmConstHeader& H) { return H.solver; }
+
 int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHeader& H, std::vector<unsigned char>& out) {
   const int N = net->n_bus, D = net->n_dev, L = net->n_branch, K = env->K;
   if (N < 2 || N > 64) return fail(ANM_E_UNSUPPORTED, "n_bus=%d not in [2, 64]", N);
@@ -319,6 +349,76 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.o_rad_child = bb.add(rc);
     H.o_rad_y = bb.add(ry);
   }
+  H.solver = choose_solver(N, H.is_radial != 0);
+  {
+    /* Symbolic factorisation for the block-sparse solver: unknowns grouped per non-slack bus (2x2 blocks);
+     * greedy minimum-degree elimination order on the Y-bus graph, fill blocks added; per elimination step the
+     * blocks of the pivot row (b, j), of the pivot column (i, b) and the degree^2 targets (i, j). */
+    const int n = N - 1;
+    auto coupled = [&](int i, int j) {
+      return net->ybus[2 * ((size_t)i * N + j)] != 0.0 || net->ybus[2 * ((size_t)i * N + j) + 1] != 0.0 ||
+             net->ybus[2 * ((size_t)j * N + i)] != 0.0 || net->ybus[2 * ((size_t)j * N + i) + 1] != 0.0;
+    };
+    std::vector<std::vector<char>> A(N, std::vector<char>(N, 0));
+    for (int i = 1; i < N; ++i)
+      for (int j = 1; j < N; ++j) A[i][j] = (i == j) || coupled(i, j);
+    std::vector<int> bi, bj, by, diag(N, -1);
+    std::vector<std::vector<int>> idx(N, std::vector<int>(N, -1));
+    auto y_index = [&](int i, int j) { /* position of (i, j) in the CSR built above (diagonal always stored) */
+      int k = 0;
+      for (int r = 0; r < N; ++r)
+        for (int c = 0; c < N; ++c) {
+          const double re = net->ybus[2 * ((size_t)r * N + c)], im = net->ybus[2 * ((size_t)r * N + c) + 1];
+          if (r != c && re == 0.0 && im == 0.0) continue;
+          if (r == i && c == j) return k;
+          ++k;
+        }
+      return -1;
+    };
+    auto add_block = [&](int i, int j, bool original) {
+      if (idx[i][j] >= 0) return;
+      idx[i][j] = (int)bi.size();
+      bi.push_back(i); bj.push_back(j);
+      by.push_back(original ? y_index(i, j) : -1);
+      if (i == j) diag[i] = idx[i][j];
+    };
+    for (int i = 1; i < N; ++i)
+      for (int j = 1; j < N; ++j)
+        if (A[i][j]) add_block(i, j, true);
+    std::vector<char> gone(N, 0);
+    std::vector<int> step, rows, cols, nbrs, tgts;
+    for (int k = 0; k < n; ++k) {
+      int best = -1, bestdeg = 1 << 30;
+      for (int b = 1; b < N; ++b) {
+        if (gone[b]) continue;
+        int deg = 0;
+        for (int j = 1; j < N; ++j) deg += (!gone[j] && j != b && A[b][j]);
+        if (deg < bestdeg) bestdeg = deg, best = b;
+      }
+      const int b = best;
+      std::vector<int> nb;
+      for (int j = 1; j < N; ++j)
+        if (!gone[j] && j != b && A[b][j]) nb.push_back(j);
+      for (int i : nb)
+        for (int j : nb) {
+          if (!A[i][j]) A[i][j] = 1;
+          add_block(i, j, false); /* no-op when the block exists */
+        }
+      step.push_back(b); step.push_back(idx[b][b]); step.push_back((int)nb.size());
+      step.push_back((int)rows.size()); step.push_back((int)tgts.size());
+      for (int j : nb) { rows.push_back(idx[b][j]); cols.push_back(idx[j][b]); nbrs.push_back(j); }
+      for (int i : nb)
+        for (int j : nb) tgts.push_back(idx[i][j]);
+      gone[b] = 1;
+    }
+    H.sp_nblk = (int)bi.size();
+    H.sp_nsteps = n;
+    H.o_sp_blk_i = bb.add(bi); H.o_sp_blk_j = bb.add(bj); H.o_sp_blk_y = bb.add(by);
+    H.o_sp_step = bb.add(step);
+    H.o_sp_row = bb.add(rows); H.o_sp_col = bb.add(cols); H.o_sp_nbr = bb.add(nbrs);
+    H.o_sp_tgt = bb.add(tgts);
+    H.o_sp_diag = bb.add(diag);
+  }
   /* per-env shared-memory workspace (doubles) */
   {
     int w = 0;
@@ -329,11 +429,12 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_devp = take(D); H.w_devq = take(D); H.w_ppot = take(D); H.w_busp = take(N); H.w_busq = take(N);
     H.w_x = take(M); H.w_vre = take(N); H.w_vim = take(N); H.w_ere = take(N); H.w_eim = take(N);
     H.w_ire = take(N); H.w_iim = take(N);
-    H.w_J = take(M * (M + 1)); H.w_rowh = take(ANM_MAX_ROWS);
+    H.w_J = take(H.solver == 4 ? 0 : M * (M + 1)); H.w_rowh = take(ANM_MAX_ROWS);
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
     H.w_vx = take(4 * N);
     H.w_dx = take(M);
+    H.w_blk = take(H.solver == 4 ? 4 * H.sp_nblk : 0);
     H.ws_doubles = (w + 15) / 16 * 16;
   }
   bb.buf.resize((bb.buf.size() + 127) / 128 * 128, 0);
@@ -347,39 +448,19 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
 #define ANM_HOST_IO_DEFAULT 2 /* zero-copy when the caller's buffers are pinned: +14 % e2e on B200 (profiles/) */
 #endif
 typedef void (*kernel_fn)(const AnmLaunch);
-/* Solver selection (anm_kernels.cuh), overridable with the environment variable ANM_SOLVER:
- *   radial  (default for tree networks <= 9 buses)   2x2-block elimination along the tree, one bus per lane  RadialNR
- *   dense   (default for meshed networks <= 9 buses) Jacobian rows in registers, natural-order Gauss-Jordan   SmallNR
- *   generic (default for > 9 buses)                  Jacobian in shared memory, partial pivoting              nr_generic
- * B200, ANM6Easy bench: radial 0.149 ms/step, dense 0.198 ms/step (profiles/r01_v4_radial_kernel.md).
- * ANM_FORCE_GENERIC=1 / ANM_FORCE_DENSE=1 are kept as aliases (tests). */
-static int solver_env() { /* -1: no override */
-  static const int v = [] {
-    const char* e = getenv("ANM_SOLVER");
-    if (e && !strcmp(e, "generic")) return 0;
-    if (e && !strcmp(e, "dense")) return 1;
-    if (e && !strcmp(e, "radial")) return 2;
-    if (getenv("ANM_FORCE_GENERIC") && atoi(getenv("ANM_FORCE_GENERIC")) != 0) return 0;
-    if (getenv("ANM_FORCE_DENSE") && atoi(getenv("ANM_FORCE_DENSE")) != 0) return 1;
-    return -1;
-  }();
-  return v;
-}
-static int solver_for(const AnmConstHeader& H) {
-  const int want = solver_env();
-  if (want == 0 || H.n_bus < 2 || H.n_bus > 9) return 0;
-  if (want != 1 && H.is_radial) return 2;
-  return 1;
-}
 static int lanes_for(const AnmConstHeader& H) {
   const int M = H.n_unk;
   switch (solver_for(H)) {
     case 2: return 8;
     case 1: return (H.n_bus <= 5) ? 8 : 16;
+    case 4: return 32;
     default: return (M <= 8) ? 8 : (M <= 16 ? 16 : 32);
   }
 }
-static int threads_for(const AnmConstHeader& H) { return solver_for(H) ? ANM_VAR_THREADS : ANM_THREADS; }
+static int threads_for(const AnmConstHeader& H) {
+  const int sv = solver_for(H);
+  return (sv == 1 || sv == 2) ? ANM_VAR_THREADS : ANM_THREADS;
+}
 
 kernel_fn kernel_for(const AnmConstHeader& H) {
   const int solver = solver_for(H);
@@ -407,6 +488,7 @@ kernel_fn kernel_for(const AnmConstHeader& H) {
       default: return anm::anm_env_kernel<16, 9, 1>;
     }
   }
+  if (solver == 4) return anm::anm_env_kernel<32, 0, 4>;
   switch (lanes_for(H)) {
     case 8: return anm::anm_env_kernel<8, 0, 0>;
     case 16: return anm::anm_env_kernel<16, 0, 0>;

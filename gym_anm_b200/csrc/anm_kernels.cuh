@@ -21,11 +21,12 @@
  * working set lives in shared memory / registers; cross-lane traffic is warp shuffles inside
  * the lane group.  All arithmetic is IEEE fp64.
  *
- * Two Newton-Raphson back-ends:
- *   nr_small<LPE, NB>  compile-time bus count NB <= 9: one Jacobian row per lane, held in registers,
- *                      fully unrolled Gauss-Jordan; the warp runs its environments in lock-step
- *                      so every warp intrinsic uses the full mask (single SASS instruction).
- *   nr_generic<LPE>    any size: Jacobian in shared memory, runtime loops (30-bus network, ...).
+ * Newton-Raphson back-ends (selected per network by the host, anm_capi.cu):
+ *   RadialNR<LPE, NB>  tree networks, NB <= 9 buses: one bus per lane, 2x2-block elimination along the tree.
+ *   SmallNR<LPE, NB>   meshed networks, NB <= 9: one Jacobian row per lane in registers, unrolled Gauss-Jordan.
+ *                      (both: the lane groups of a warp run in lock-step, every intrinsic uses the full mask)
+ *   nr_sparse<LPE>     any size (default above 9 buses): block-sparse LU in shared memory, host-side symbolic phase.
+ *   nr_generic<LPE>    any size: dense Jacobian in shared memory, partial pivoting.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -247,7 +248,8 @@ struct Cst {  // resolved pointers into the staged blob
   const double *vmin, *vmax, *dev_param, *br_coef, *y_val, *ctrl_rows, *sv_mul, *sv_div, *ov_mul, *ov_div, *ov_low,
       *ov_high, *table, *y_dense;
   const int *dev_bus, *dev_type, *dev_slot, *bus_dev_ptr, *bus_dev_idx, *br_from, *br_to, *y_ptr, *y_col, *jac_row,
-      *jac_col, *jac_y, *ctrl_dev, *sv_off, *ov_off, *pair_i, *pair_j, *rad_parent, *rad_depth, *rad_child;
+      *jac_col, *jac_y, *ctrl_dev, *sv_off, *ov_off, *pair_i, *pair_j, *rad_parent, *rad_depth, *rad_child, *sp_blk_i, *sp_blk_j,
+      *sp_blk_y, *sp_step, *sp_row, *sp_col, *sp_nbr, *sp_tgt;
   const double* rad_y;
   __device__ explicit Cst(const unsigned char* b) {
     H = reinterpret_cast<const AnmConstHeader*>(b);
@@ -262,6 +264,8 @@ struct Cst {  // resolved pointers into the staged blob
     IP(jac_row, o_jac_row); IP(jac_col, o_jac_col); IP(jac_y, o_jac_y); IP(ctrl_dev, o_ctrl_dev);
     IP(sv_off, o_sv_off); IP(ov_off, o_ov_off); IP(pair_i, o_pair_i); IP(pair_j, o_pair_j);
     IP(rad_parent, o_rad_parent); IP(rad_depth, o_rad_depth); IP(rad_child, o_rad_child);
+    IP(sp_blk_i, o_sp_blk_i); IP(sp_blk_j, o_sp_blk_j); IP(sp_blk_y, o_sp_blk_y); IP(sp_step, o_sp_step);
+    IP(sp_row, o_sp_row); IP(sp_col, o_sp_col); IP(sp_nbr, o_sp_nbr); IP(sp_tgt, o_sp_tgt);
 #undef DP
 #undef IP
   }
@@ -466,6 +470,171 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
   it_out = it;
   converged_out = (diff == diff);
   stable_out = converged_out && diff <= ANM_NR_TOL; /* solve_load_flow.py:49 */
+}
+
+/* ---- Newton-Raphson with a block-sparse LU (any network; default above 9 buses) -------------------------
+ * The Jacobian (solve_load_flow.py:123-164) has the sparsity of the Y-bus: one 2x2 block [dP,dQ] x [dtheta,d|V|]
+ * per coupled bus pair.  The host computed a minimum-degree elimination order and the fill (anm_capi.cu);
+ * the blocks of one environment live in shared memory (4 doubles each: ~3 KB for a 30-bus feeder instead of
+ * 27 KB for the dense 58 x 59 system).  Per elimination step the pivot block is inverted by its adjugate
+ * (fast reciprocal of the determinant), the pivot row is scaled in place (W_j = D_b^-1 J_bj, w = D_b^-1 f_b,
+ * kept for the back-substitution) and the degree^2 + degree Schur updates J_ij -= J_ib W_j, f_i -= J_ib w
+ * are spread over the lanes.  No pivoting across blocks (a singular Schur block with a regular Jacobian is
+ * non-generic; ANM_SOLVER=generic gives the dense partial-pivoting solver).  One environment per warp. */
+template <int LPE, bool FULL>
+__device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
+                                          int& it_out, bool& converged_out, bool& stable_out) {
+  const AnmConstHeader& H = *C.H;
+  const int N = H.n_bus, n = N - 1, M = H.n_unk, nblk = H.sp_nblk;
+  double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* x = ws + H.w_x;
+  double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* f = ws + H.w_dx; /* rhs, then the step */
+  double* blk = ws + H.w_blk;
+  it_out = 0;
+  converged_out = stable_out = true;
+  if (!live) return; /* group-uniform (one environment per warp) */
+  for (int j = lane; j < n; j += LPE) { /* flat start (solve_load_flow.py:42) */
+    x[j] = 0.0;
+    x[n + j] = 1.0;
+  }
+  gsync<FULL>(gm);
+  int it = 0;
+  double diff;
+  for (;;) {
+    for (int b = lane; b < N; b += LPE) { /* V = |V| e^{j theta}, E = V/|V| */
+      double re = 1.0, im = 0.0, er = 1.0, ei = 0.0;
+      if (b > 0) {
+        double sn, cs;
+        sincos_fast(x[b - 1], &sn, &cs);
+        const double vm = x[n + b - 1];
+        const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN);
+        re = vm * cs; im = vm * sn; er = sg * cs; ei = sg * sn;
+      }
+      vre[b] = re; vim[b] = im; ere[b] = er; eim[b] = ei;
+    }
+    gsync<FULL>(gm);
+    double lmax = 0.0;
+    bool bad = false;
+    for (int b = lane; b < N; b += LPE) { /* I = Y V, mismatch (:84-120) */
+      double sr = 0.0, si = 0.0;
+      for (int k = C.y_ptr[b]; k < C.y_ptr[b + 1]; ++k) {
+        const int j = C.y_col[k];
+        const double yr = C.y_val[2 * k], yi = C.y_val[2 * k + 1];
+        sr += yr * vre[j] - yi * vim[j];
+        si += yr * vim[j] + yi * vre[j];
+      }
+      ire[b] = sr; iim[b] = si;
+      if (b > 0) {
+        const double fr = (vre[b] * sr + vim[b] * si) - busp[b];
+        const double fi = (vim[b] * sr - vre[b] * si) - busq[b];
+        f[2 * (b - 1)] = fr;
+        f[2 * (b - 1) + 1] = fi;
+        bad = bad || (fr != fr) || (fi != fi);
+        lmax = fmax(lmax, fmax(fabs(fr), fabs(fi)));
+      }
+    }
+    lmax = g_max<LPE, FULL>(lmax, gm);
+    bad = g_any<FULL>(bad, gm);
+    diff = bad ? CUDART_NAN : lmax;
+    if (!(diff > ANM_NR_TOL) || it >= ANM_NR_MAXIT) break;
+    ++it;
+    gsync<FULL>(gm);
+
+    /* Jacobian blocks [ (P,theta) (P,V) (Q,theta) (Q,V) ]; fill blocks start at zero */
+    for (int t = lane; t < nblk; t += LPE) {
+      const int i = C.sp_blk_i[t], j = C.sp_blk_j[t], yk = C.sp_blk_y[t];
+      double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+      if (yk >= 0) {
+        const double yr = C.y_val[2 * yk], yi = C.y_val[2 * yk + 1];
+        const bool dg = (i == j);
+        const double tr = yr * vre[j] - yi * vim[j], ti = yr * vim[j] + yi * vre[j]; /* Y_ij V_j */
+        const double inr = (dg ? ire[i] : 0.0) - tr, ini = (dg ? iim[i] : 0.0) - ti;
+        const double jr = -vim[i], ji = vre[i];                                       /* j V_i */
+        b0 = jr * inr + ji * ini;
+        b2 = ji * inr - jr * ini;
+        const double gr = yr * ere[j] - yi * eim[j], gi = yr * eim[j] + yi * ere[j];
+        b1 = vre[i] * gr + vim[i] * gi;
+        b3 = vim[i] * gr - vre[i] * gi;
+        if (dg) {
+          b1 += ere[i] * ire[i] + eim[i] * iim[i];
+          b3 += eim[i] * ire[i] - ere[i] * iim[i];
+        }
+      }
+      blk[4 * t] = b0; blk[4 * t + 1] = b1; blk[4 * t + 2] = b2; blk[4 * t + 3] = b3;
+    }
+    gsync<FULL>(gm);
+
+    /* forward elimination in the host's order */
+    for (int k = 0; k < H.sp_nsteps; ++k) {
+      const int* st = C.sp_step + 5 * k;
+      const int b = st[0], pb = st[1], d = st[2], off = st[3], toff = st[4];
+      const double p0 = blk[4 * pb], p1 = blk[4 * pb + 1], p2 = blk[4 * pb + 2], p3 = blk[4 * pb + 3];
+      const double rd = fast_rcp(p0 * p3 - p1 * p2);
+      const double i0 = p3 * rd, i1 = -p1 * rd, i2 = -p2 * rd, i3 = p0 * rd; /* D_b^-1 */
+      /* W_j = D_b^-1 J_bj (in place), w = D_b^-1 f_b (in place) */
+      for (int t = lane; t <= d; t += LPE) {
+        if (t < d) {
+          double* r = blk + 4 * C.sp_row[off + t];
+          const double r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
+          r[0] = i0 * r0 + i1 * r2; r[1] = i0 * r1 + i1 * r3;
+          r[2] = i2 * r0 + i3 * r2; r[3] = i2 * r1 + i3 * r3;
+        } else {
+          const double f0 = f[2 * (b - 1)], f1 = f[2 * (b - 1) + 1];
+          f[2 * (b - 1)] = i0 * f0 + i1 * f1;
+          f[2 * (b - 1) + 1] = i2 * f0 + i3 * f1;
+        }
+      }
+      gsync<FULL>(gm);
+      /* Schur updates: J_ij -= J_ib W_j (d^2 blocks), f_i -= J_ib w (d vectors) */
+      const int items = d * d + d;
+      for (int t = lane; t < items; t += LPE) {
+        if (t < d * d) {
+          const int ii = t / d, jj = t - ii * d;
+          const double* Lb = blk + 4 * C.sp_col[off + ii];
+          const double* W = blk + 4 * C.sp_row[off + jj];
+          double* T = blk + 4 * C.sp_tgt[toff + t];
+          const double l0 = Lb[0], l1 = Lb[1], l2 = Lb[2], l3 = Lb[3], w0 = W[0], w1 = W[1], w2 = W[2], w3 = W[3];
+          T[0] -= l0 * w0 + l1 * w2; T[1] -= l0 * w1 + l1 * w3;
+          T[2] -= l2 * w0 + l3 * w2; T[3] -= l2 * w1 + l3 * w3;
+        } else {
+          const int ii = t - d * d;
+          const double* Lb = blk + 4 * C.sp_col[off + ii];
+          const int bi = C.sp_nbr[off + ii];
+          const double w0 = f[2 * (b - 1)], w1 = f[2 * (b - 1) + 1];
+          f[2 * (bi - 1)] -= Lb[0] * w0 + Lb[1] * w1;
+          f[2 * (bi - 1) + 1] -= Lb[2] * w0 + Lb[3] * w1;
+        }
+      }
+      gsync<FULL>(gm);
+    }
+    /* back-substitution in reverse order: x_b = w - sum_j W_j x_j (the step overwrites f) */
+    for (int k = H.sp_nsteps - 1; k >= 0; --k) {
+      const int* st = C.sp_step + 5 * k;
+      const int b = st[0], d = st[2], off = st[3];
+      if (lane == 0) {
+        double s0 = f[2 * (b - 1)], s1 = f[2 * (b - 1) + 1];
+        for (int t = 0; t < d; ++t) {
+          const double* W = blk + 4 * C.sp_row[off + t];
+          const int bj = C.sp_nbr[off + t];
+          const double x0 = f[2 * (bj - 1)], x1 = f[2 * (bj - 1) + 1];
+          s0 -= W[0] * x0 + W[1] * x1;
+          s1 -= W[2] * x0 + W[3] * x1;
+        }
+        f[2 * (b - 1)] = s0;
+        f[2 * (b - 1) + 1] = s1;
+      }
+      gsync<FULL>(gm);
+    }
+    for (int b = lane + 1; b < N; b += LPE) { /* x <- x - J^{-1} F (:220) */
+      x[b - 1] -= f[2 * (b - 1)];
+      x[n + b - 1] -= f[2 * (b - 1) + 1];
+    }
+    gsync<FULL>(gm);
+  }
+  it_out = it;
+  converged_out = (diff == diff);
+  stable_out = converged_out && diff <= ANM_NR_TOL;
+  (void)M;
 }
 
 /* ---- Newton-Raphson, compile-time bus count NB: everything in registers -----------------------
@@ -705,9 +874,9 @@ struct SmallNR {
  * along the tree: leaves first, every bus folds  U D^-1 [L | f]  into its parent's (D, f) (one shuffle
  * round per tree level), then the step is back-substituted from the root down -- the critical path is the
  * tree depth instead of 2(N-1) pivots, and an environment needs only N-1 lanes.  2x2 diagonal blocks are
- * inverted by the adjugate.  No pivoting across blocks: det J = prod det(D_b), so a singular block means a
- * singular Jacobian, for which a pivoted solve returns garbage as well (the reference gets NaN from SuperLU,
- * solve_load_flow.py:220) -- the instance then fails to converge either way.  Lock-step lane groups,
+ * inverted by the adjugate.  No pivoting across blocks: a (near-)singular Schur block while the Jacobian itself
+ * is regular is non-generic (never observed in 5e5 instance-steps against the pivoting oracle, divergent
+ * instances included); ANM_SOLVER=generic selects the dense partial-pivoting solver.  Lock-step lane groups,
  * full-mask intrinsics, like SmallNR. */
 #define ANM_RAD_MAXC 4
 template <int LPE, int NB>
@@ -992,7 +1161,9 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   int it = 0;
   bool converged = false, stable = false;
   n_fb = n_big = 0;
-  if constexpr (SOLVER == 2)
+  if constexpr (SOLVER == 4)
+    nr_sparse<LPE, FULL>(C, ws, lane, gm, live, it, converged, stable);
+  else if constexpr (SOLVER == 2)
     RadialNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable, n_fb, n_big);
   else if constexpr (SOLVER == 1)
     SmallNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable, n_fb, n_big);
@@ -1098,7 +1269,8 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
 enum { ACT_NONE = 0, ACT_ZERO = 1, ACT_STEP = 2, ACT_RESET = 3, ACT_TRANSITION = 4 };
 
 template <int LPE, int NB, int SOLVER>
-__global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_THREADS, (NB > 0 && LPE <= 16) ? ANM_VAR_MINB : 1)
+__global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_THREADS,
+                                   (NB > 0 && LPE <= 16) ? ANM_VAR_MINB : (SOLVER == 4 ? 4 : 1))
     anm_env_kernel(const AnmLaunch P) {
   constexpr bool FULL = (NB > 0) || (LPE == 32);
   extern __shared__ __align__(128) unsigned char smem[];

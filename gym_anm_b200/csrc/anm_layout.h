@@ -48,10 +48,20 @@ struct AnmConstHeader {
   int32_t o_rad_parent, o_rad_depth;         /* int[n_bus-1]: parent's lane (-1 = slack), depth >= 1 */
   int32_t o_rad_child;                       /* int[n_bus-1][4]: children's lanes, -1 padded         */
   int32_t o_rad_y;                           /* double[n_bus-1][6]: Y_bb, Y_b,parent, Y_parent,b     */
+  /* block-sparse LU of the Newton system (any network; default above 9 buses): 2x2 blocks on the filled
+   * Y-bus pattern, elimination order and fill computed once on the host (anm_capi.cu: sparse_symbolic) */
+  int32_t solver;                            /* 0 dense smem, 1 dense register rows, 2 radial tree, 4 block-sparse */
+  int32_t sp_nblk, sp_nsteps;
+  int32_t o_sp_blk_i, o_sp_blk_j, o_sp_blk_y; /* int[sp_nblk]: bus i, bus j, index into y_val (-1: fill)       */
+  int32_t o_sp_step;                         /* int[sp_nsteps][5]: pivot bus, pivot block, degree, list offset, target offset */
+  int32_t o_sp_row, o_sp_col, o_sp_nbr;      /* int lists: blocks (b,j), blocks (i,b), neighbour buses          */
+  int32_t o_sp_tgt;                          /* int list: target blocks (i,j), degree^2 per step                */
+  int32_t o_sp_diag;                         /* int[n_bus]: diagonal block of each bus (-1 for the slack)       */
   /* per-env workspace offsets (in doubles) */
   int32_t w_in_pl, w_in_pp, w_in_ps, w_in_qs, w_soc, w_aux, w_devp, w_devq, w_ppot, w_busp, w_busq;
   int32_t w_x, w_vre, w_vim, w_ere, w_eim, w_ire, w_iim, w_J, w_rowh;
   int32_t w_brp, w_brq, w_brs, w_brire, w_briim, w_full, w_s0;
   int32_t w_vx; /* (Vre, Vim, Ere, Eim) x n_bus exchange buffer of the register-resident solver */
   int32_t w_dx; /* Newton step written by the shared-memory solver */
+  int32_t w_blk; /* block-sparse solver: 4 doubles per block */
 };

@@ -306,9 +306,9 @@ def test_other_solvers_same_results_subprocess():
 
     here = os.path.abspath(__file__)
     sel = "test_anm6easy_golden_trajectory or test_transition_goldens or test_batch_vs_oracle or test_radial_tree"
-    # ANM_SOLVER selects the Newton back-end: generic (shared memory), dense (register rows); default for the
-    # radial test networks is the tree elimination
-    for val in ("generic", "dense"):
+    # ANM_SOLVER selects the Newton back-end: generic (dense, shared memory), dense (register rows), sparse
+    # (block-sparse LU, default above 9 buses); the default for the radial test networks is the tree elimination
+    for val in ("generic", "dense", "sparse"):
         var = "ANM_SOLVER=" + val
         env = dict(os.environ, ANM_SOLVER=val)
         r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
