@@ -97,6 +97,7 @@ def numpy_port_rate(n_proc, n_steps, n_warm=10):
 
 
 def c_port_rate(B=4096, steps=100):
+    os.environ["OMP_NUM_THREADS"] = str(usable_cores())  # before libgomp is loaded: no oversubscription under a CPU quota
     import numpy as np
 
     import anm_numpy

@@ -473,3 +473,48 @@ def test_mpc_constant_agent_drives_batched_env_config5():
         assert rel_err(obs_g.cpu().numpy(), obs_c) < RTOL and rel_err(r_g.cpu().numpy(), r_c) < RTOL
         total += float(r_g.mean())
     assert total / 8 > -5.0  # the MPC policy operates the grid at low cost
+
+
+def test_c_abi_error_paths_and_edge_inputs():
+    """The C ABI reports errors through return codes + anm_last_error (nothing throws), refuses networks the
+    reference solver cannot handle, and treats NaN / out-of-range inputs like the reference's arithmetic
+    would (NaN mismatch -> not converged -> terminated)."""
+    import ctypes as C
+
+    from gym_anm_b200 import _capi
+    from gym_anm_b200.anm6 import BatchedANM6Easy
+    from gym_anm_b200.env_spec import HostEnvSpec, anm6easy_spec
+    from gym_anm_b200.errors import BusSpecError, NativeLibraryError
+    from gym_anm_b200.native import NativeBatch
+    from gym_anm_b200.networks import anm6_network
+
+    lib = _capi.load_library()
+    spec = anm6easy_spec()
+    net, env, keep = spec.descs()
+    h = C.c_void_p()
+    assert lib.anm_create(C.byref(net), C.byref(env), 8, 99, C.byref(h)) != 0 and b"device" in lib.anm_last_error()
+    env.n_state = 17
+    assert lib.anm_create(C.byref(net), C.byref(env), 8, 0, C.byref(h)) != 0 and b"n_state" in lib.anm_last_error()
+    # slack bus must be bus 0 (solve_load_flow.py:171): refused on the host before the library is reached
+    bad = anm6_network()
+    bad["bus"][0, 1], bad["bus"][1, 1] = 1, 0
+    bad["device"][0][1] = 1
+    with pytest.raises(BusSpecError):
+        NativeBatch(HostEnvSpec(bad, "state", 0, 0.25, 0.9, 100), 4)
+    # a step without next_vars on an environment that has no built-in table is an error, not a crash
+    nb = NativeBatch(HostEnvSpec(anm6_network(), "state", 1, 0.25, 0.9, 100, np.array([[0, 95]])), 4)
+    with pytest.raises(NativeLibraryError):
+        nb.step(np.zeros((4, 6)), None)
+    # NaN action -> NaN injections -> NaN mismatch -> terminated, like `nan > tol == False` in the reference
+    e = BatchedANM6Easy(4, validate_actions=False)
+    e.reset(seed=1)
+    a = np.tile(e.spec.action_high * 0.5, (4, 1))
+    a[2, 0] = np.nan
+    obs, r, term, _, _ = e.step(a)
+    assert term.cpu().numpy().tolist() == [False, False, True, False]
+    assert float(r[2]) == -100 / (1 - 0.995) and np.all(obs[2].cpu().numpy() == 0)
+    # out-of-box actions are rejected by the Python layer exactly like `assert action_space.contains(action)`
+    e2 = BatchedANM6Easy(2)
+    e2.reset(seed=2)
+    with pytest.raises(AssertionError):
+        e2.step(np.tile(e2.spec.action_high * 2, (2, 1)))
