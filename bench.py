@@ -12,10 +12,17 @@ instance does one full transition per step.
 
 * `value`      : K steps replayed from a CUDA graph, actions already resident in HBM
                  (a 1000-slot x B x 6 fp64 ring, 197 MB > the 126 MB L2), timed with CUDA
-                 events, max over ranks.
-* `e2e`        : the same metric through the C-ABI host call `anm_step_host` -- pinned HOST
-                 action buffer in, HOST obs / reward / terminated out, H2D + D2H inside the timed
-                 region every step.
+                 events, max over ranks.  The random agent is open-loop, so the steps are enqueued
+                 CHAINED (ANM_STEP_CHAINED, include/anm_b200.h): launch t+1 is ordered against
+                 launch t per environment instance, and the ~1 % of instances whose Newton iteration
+                 diverges (100 iterations) finish step t while the others are already in step t+1.
+                 `lockstep` reports the same loop with every launch fully ordered after the previous
+                 one (what a closed-loop policy sees).
+* `e2e`        : the same metric through the C-ABI host calls `anm_step_host_async` + `anm_host_sync`
+                 -- pinned HOST action buffer in, HOST obs / reward / terminated out, every step,
+                 H2D + D2H inside the timed region (zero-copy: the kernel reads / writes the pinned
+                 buffers over PCIe); a ring of Q output buffers, one host sync per Q steps.
+                 `e2e.sync_every_step` is the synchronous `anm_step_host` (Q = 1).
 * `roofline`   : algorithmic bytes (234 B / env-step) x B / mean kernel time
                  against the measured HBM copy bandwidth (MEASURED_PEAKS.json).  The path is NOT
                  HBM-bound (arithmetic intensity ~30 fp64 FLOP/B); the fraction is reported
@@ -265,56 +272,90 @@ def run_ours(args):
 
     # ---- value: K steps replayed from a CUDA graph ------------------------------------------------------
     G = min(K, RING)
-    graph = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for t in range(G):
-                nb.step(ring[t], None, out=(obs, rew, term))
-    torch.cuda.current_stream().wait_stream(side)
-    graph.replay()  # untimed replay: graph upload + instruction cache
+
+    def capture(chained):
+        g = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for t in range(G):
+                    nb.step(ring[t], None, out=(obs, rew, term), chained=chained)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()  # untimed replay: graph upload + instruction cache
+        return g
+
+    def timed_replays(g, n_rep, rem, chained):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_host0 = time.perf_counter()
+        ev0.record()
+        for _ in range(n_rep):
+            g.replay()
+        for t in range(rem):
+            nb.step(ring[t], None, out=(obs, rew, term), chained=chained)
+        ev1.record()
+        barrier()
+        t_host1 = time.perf_counter()
+        sampler.mark(t_host0, t_host1)
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    graph = capture(True)
     n_rep, rem = divmod(K, G)
     launches0 = nb.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_host0 = time.perf_counter()
-    ev0.record()
-    for _ in range(n_rep):
-        graph.replay()
-    for t in range(rem):
-        nb.step(ring[t], None, out=(obs, rew, term))
-    ev1.record()
-    barrier()
-    t_host1 = time.perf_counter()
-    sampler.mark(t_host0, t_host1)
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    ms_total = timed_replays(graph, n_rep, rem, True)
     gpu_launches = n_rep * G + (nb.launch_count - launches0)
     frac_reset = float((term != 0).double().mean())
+    # the same loop with every launch fully ordered after the previous one (closed-loop view)
+    graph_ls = capture(False)
+    n_ls = max(1, min(n_rep, 4))
+    ms_lockstep = timed_replays(graph_ls, n_ls, 0, False)
+    lockstep_rate = world * B * n_ls * G / (ms_lockstep / 1000.0)
+    del graph_ls
 
-    # ---- e2e: host buffers through anm_step_host (H2D + kernel + D2H every step) ------------------------
-    Ke = min(K, 4000)
-    for t in range(3):
-        nb.step_host(ring_host[t], None, obs_h, rew_h, term_h)
+    # ---- e2e: host buffers through the C ABI's host calls (H2D + kernel + D2H every step) ---------------
     hs = nb.host_stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_host0 = time.perf_counter()
-    e0.record(hs)
-    for t in range(Ke):
-        nb.step_host(ring_host[t % RING], None, obs_h, rew_h, term_h)
-    e1.record(hs)
-    barrier()
-    t_host1 = time.perf_counter()
-    sampler.mark(t_host0, t_host1)
-    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 1000.0 * (t_host1 - t_host0))], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_rate = world * B * Ke / (float(e2e_ms) / 1000.0)
-    checksum = float(obs_h.sum()) + float(rew_h.sum())
+    Q = 16  # queued steps between two host synchronisations (each has its own pinned output buffers)
+    obs_q = torch.empty(Q, B, 18, dtype=torch.float64).pin_memory()
+    rew_q = torch.empty(Q, B, dtype=torch.float64).pin_memory()
+    term_q = torch.empty(Q, B, dtype=torch.uint8).pin_memory()
+    act_ptr = [ring_host[t].data_ptr() for t in range(RING)]
+    out_ptr = [(obs_q[q].data_ptr(), rew_q[q].data_ptr(), term_q[q].data_ptr()) for q in range(Q)]
+
+    def e2e_loop(n, queued):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_host0 = time.perf_counter()
+        e0.record(hs)
+        if queued:
+            for t in range(n):
+                o, r, d = out_ptr[t % Q]
+                nb.step_host_async(act_ptr[t % RING], None, o, r, d)
+                if t % Q == Q - 1:
+                    nb.host_sync()
+            nb.host_sync()
+        else:
+            for t in range(n):
+                nb.step_host(act_ptr[t % RING], None, out_ptr[0][0], out_ptr[0][1], out_ptr[0][2])
+        e1.record(hs)
+        barrier()
+        t_host1 = time.perf_counter()
+        sampler.mark(t_host0, t_host1)
+        ms = torch.tensor([max(e0.elapsed_time(e1), 1000.0 * (t_host1 - t_host0))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return world * B * n / (float(ms) / 1000.0)
+
+    Ke = max(Q, min(K, 8000) // Q * Q)
+    e2e_loop(3 * Q, True)
+    e2e_rate = e2e_loop(Ke, True)
+    checksum = float(obs_q.sum()) + float(rew_q.sum())
+    e2e_loop(3, False)
+    Ks = min(K, 2000)
+    e2e_sync_rate = e2e_loop(Ks, False)
 
     # ---- optional: the single collective of the path (all-gather of the batched observation) ------------
     gather_rate = None
@@ -329,7 +370,7 @@ def run_ours(args):
         barrier()
         g0.record()
         for t in range(Kg):
-            nb.step(ring[t % RING], None, out=(obs, rew, term))
+            nb.step(ring[t % RING], None, out=(obs, rew, term), chained=True)
             packed[:, :18] = obs
             packed[:, 18] = rew
             packed[:, 19] = term
@@ -368,6 +409,8 @@ def run_ours(args):
         "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src,
         "algorithmic_bytes_per_env_step": B_MIN_BYTES, "env_steps_per_launch": B,
         "kernel_us_mean": kernel_s * 1e6,
+        "kernel_time": "timed region / launches (consecutive launches overlap; an isolated launch takes longer, "
+                       "see lockstep.ms_per_step)",
         "note": "compute/latency-bound path (fp64 FMA pipe + shuffle/LDS latency), not HBM-bound; see fp64 fields",
         "fp64_pipe_pct_ncu": ncu.get("fp64_pipe_pct"), "issue_slot_pct_ncu": ncu.get("issue_active_pct"),
         "ncu_profile": ncu.get("source"),
@@ -404,13 +447,22 @@ def run_ours(args):
             "envs_per_gpu": B, "global_envs": world * B, "parallelism": "dp%d (independent env shards)" % world,
             "autoreset": "next-step, from a pool of %d convergent initial states" % pool.shape[0],
             "l2": "inputs cycle through a %d-slot action ring of %.0f MB (> 126 MB L2)" % (RING, ring.numel() * 8 / 1e6),
-            "launch": "CUDA graph of %d step kernels replayed %d times (+%d eager)" % (G, n_rep, rem),
+            "launch": "CUDA graph of %d step kernels replayed %d times (+%d eager); one kernel launch per step, "
+                      "launches chained per instance (programmatic dependent launch + per-instance sequence "
+                      "numbers): the tail of step t overlaps step t+1" % (G, n_rep, rem),
             "lanes_per_env": nb.sizes["lanes_per_env"], "smem_bytes_per_cta": nb.sizes["smem_bytes"],
             "frac_envs_reset_last_step": frac_reset,
         },
         "clocks": clocks,
+        "lockstep": {"value": lockstep_rate, "unit": "env-steps/s", "ms_per_step": ms_lockstep / (n_ls * G),
+                     "steps": n_ls * G, "what": "same graph loop, every launch fully ordered after the previous one "
+                     "(no cross-launch overlap): the rate a closed-loop policy on the same stream can reach"},
         "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 6 * 8,
-                "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "api": "anm_step_host (C ABI; pinned host buffers, read / written by the kernel over PCIe = zero-copy; ANM_HOST_IO=copy stages through cudaMemcpyAsync instead)",
+                "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "queue_depth": Q,
+                "api": "anm_step_host_async x %d + anm_host_sync (C ABI; pinned host buffers, read / written by the "
+                       "kernel over PCIe = zero-copy; ANM_HOST_IO=copy stages through cudaMemcpyAsync instead)" % Q,
+                "sync_every_step": {"value": e2e_sync_rate, "unit": "env-steps/s", "steps": Ks,
+                                    "api": "anm_step_host (synchronous)"},
                 "checksum": checksum},  # fmt: skip
         "gpu_launches": gpu_launches,
         "roofline": roofline,

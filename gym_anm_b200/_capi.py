@@ -60,7 +60,11 @@ class Sizes(C.Structure):
 
 class StepExtras(C.Structure):
     _fields_ = [("state", C.c_void_p), ("e_loss", C.c_void_p), ("penalty", C.c_void_p), ("n_iter", C.c_void_p),
-                ("full_state", C.c_void_p), ("solver_stats", C.c_void_p)]  # fmt: skip
+                ("full_state", C.c_void_p), ("solver_stats", C.c_void_p), ("flags", C.c_uint32),
+                ("reserved", C.c_uint32)]  # fmt: skip
+
+
+STEP_CHAINED = 1  # anm_step_extras.flags: ANM_STEP_CHAINED (include/anm_b200.h)
 
 
 def _dp(a):
@@ -110,12 +114,15 @@ _PROTOS = {
     "anm_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     "anm_reset": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "anm_step": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(StepExtras), C.c_void_p]),
+    "anm_rollout": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_void_p]),
     "anm_set_autoreset_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "anm_transition": (C.c_int, [C.c_void_p] + [C.c_void_p] * 9 + [C.c_void_p]),
     "anm_get_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 3 + [C.c_void_p]),
     "anm_set_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 3 + [C.c_void_p]),
     "anm_step_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "anm_reset_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
+    "anm_step_host_async": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
+    "anm_host_sync": (C.c_int, [C.c_void_p]),
     "anm_host_stream": (C.c_void_p, [C.c_void_p]),
     "anm_launch_count": (C.c_int64, [C.c_void_p]),
 }
@@ -140,7 +147,7 @@ def load_library(path=None):
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.anm_abi_version() != 1:
+    if lib.anm_abi_version() != 2:
         raise NativeLibraryError("ABI version mismatch in %s" % path)
     _LIB = lib
     return lib

@@ -81,6 +81,8 @@ struct anm_handle_s {
   double* d_aux = nullptr;
   uint8_t* d_term = nullptr;
   uint32_t* d_episode = nullptr;
+  uint32_t* d_seq = nullptr; /* [B] per-instance launch sequence numbers (launch chaining, anm_kernels.cuh) */
+  uint32_t seq = 0;          /* sequence number of the last launch enqueued for this handle               */
   const double* pool = nullptr;
   int64_t pool_size = 0;
   /* launch geometry */
@@ -522,15 +524,43 @@ int choose_geometry(anm_handle h) {
   return 0;
 }
 
-int launch(anm_handle h, AnmLaunch& p, cudaStream_t st) {
+/* ANM_PDL=0 (environment) turns programmatic dependent launch off: every launch then waits for the
+ * complete previous one, as in a plain stream (A/B switch; results are identical either way). */
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ANM_PDL");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+
+int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
   p.blob = h->d_blob;
   p.blob_bytes = h->blob_bytes;
   p.B = h->B;
   p.soc = h->d_soc; p.aux = h->d_aux; p.terminated = h->d_term; p.episode = h->d_episode;
   p.pool = h->pool; p.pool_size = h->pool_size;
-  kernel_for(h->H)<<<h->grid, h->gpb * h->lpe, h->smem, st>>>(p);
+  /* launch chaining: wait for the previous launch per instance, publish this one (anm_kernels.cuh) */
+  p.seq = h->d_seq;
+  p.seq_wait = h->seq;
+  p.seq_post = ++h->seq;
+  const bool pdl = pdl_enabled();
+  p.flags = pdl ? flags : (flags & ~ANM_LF_CHAINED);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)h->grid);
+  cfg.blockDim = dim3((unsigned)(h->gpb * h->lpe));
+  cfg.dynamicSmemBytes = (size_t)h->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const AnmLaunch arg = p;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel_for(h->H), arg);
   ++h->launches;
-  cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess) e = cudaPeekAtLastError();
   if (e != cudaSuccess) return fail(ANM_E_CUDA, "kernel launch: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -603,6 +633,7 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   ALLOC(h->d_aux, B * H.K * sizeof(double));
   ALLOC(h->d_term, B);
   ALLOC(h->d_episode, B * sizeof(uint32_t));
+  ALLOC(h->d_seq, B * sizeof(uint32_t));
   ALLOC(h->s_action, B * H.n_action * sizeof(double));
   ALLOC(h->s_nv, B * H.n_next_vars * sizeof(double));
   ALLOC(h->s_obs, B * H.n_obs * sizeof(double));
@@ -617,7 +648,9 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, B * H.K * sizeof(double) + (H.K ? 0 : 16));
   if (e == cudaSuccess) e = cudaMemset(h->d_term, 1, B); /* nothing is runnable before the first reset */
   if (e == cudaSuccess) e = cudaMemset(h->d_episode, 0, B * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->d_seq, 0, B * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy); /* the memsets above, before any other stream uses them */
   if (e != cudaSuccess) { anm_destroy(h); return fail(ANM_E_CUDA, "handle init: %s", cudaGetErrorString(e)); }
   rc = choose_geometry(h);
   if (rc) { anm_destroy(h); return rc; }
@@ -629,6 +662,7 @@ int anm_destroy(anm_handle h) {
   if (!h) return ANM_OK;
   DeviceGuard guard(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_soc); cudaFree(h->d_aux); cudaFree(h->d_term); cudaFree(h->d_episode);
+  cudaFree(h->d_seq);
   cudaFree(h->s_action); cudaFree(h->s_nv); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_s0);
   cudaFree(h->s_state); cudaFree(h->s_term); cudaFree(h->s_mask);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -669,8 +703,36 @@ int anm_step(anm_handle h, const double* action, const double* next_vars, double
   memset(&p, 0, sizeof(p));
   p.mode = ANM_MODE_STEP;
   p.action = action; p.next_vars = next_vars; p.obs = obs; p.reward = reward; p.term_out = terminated;
-  if (ex) { p.state = ex->state; p.e_loss = ex->e_loss; p.penalty = ex->penalty; p.n_iter = ex->n_iter; p.full_state = ex->full_state; p.solver_stats = ex->solver_stats; }
-  return launch(h, p, (cudaStream_t)stream);
+  uint32_t lf = 0;
+  if (ex) {
+    p.state = ex->state; p.e_loss = ex->e_loss; p.penalty = ex->penalty; p.n_iter = ex->n_iter;
+    p.full_state = ex->full_state; p.solver_stats = ex->solver_stats;
+    if (ex->flags & ANM_STEP_CHAINED) lf |= ANM_LF_CHAINED;
+  }
+  return launch(h, p, (cudaStream_t)stream, lf);
+}
+
+int anm_rollout(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs, double* reward,
+                uint8_t* terminated, void* stream) {
+  if (!h || !action || !obs || !reward || !terminated || T < 0) return fail(ANM_E_INVALID, "anm_rollout: bad argument");
+  if (!next_vars && h->H.table_len == 0)
+    return fail(ANM_E_INVALID, "anm_rollout: next_vars is NULL but the environment has no built-in table");
+  DeviceGuard guard(h->device);
+  const AnmConstHeader& H = h->H;
+  const size_t B = (size_t)h->B;
+  for (int64_t t = 0; t < T; ++t) {
+    AnmLaunch p;
+    memset(&p, 0, sizeof(p));
+    p.mode = ANM_MODE_STEP;
+    p.action = action + (size_t)t * B * H.n_action;
+    p.next_vars = next_vars ? next_vars + (size_t)t * B * H.n_next_vars : nullptr;
+    p.obs = obs + (size_t)t * B * H.n_obs;
+    p.reward = reward + (size_t)t * B;
+    p.term_out = terminated + (size_t)t * B;
+    int rc = launch(h, p, (cudaStream_t)stream, t > 0 ? ANM_LF_CHAINED : 0u);
+    if (rc) return rc;
+  }
+  return ANM_OK;
 }
 
 int anm_set_autoreset_pool(anm_handle h, const double* pool, int64_t pool_size) {
@@ -718,9 +780,8 @@ int anm_set_state(anm_handle h, const double* soc, const double* aux, const uint
   return ANM_OK;
 }
 
-int anm_step_host(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
-                  uint8_t* terminated) {
-  if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_host: null argument");
+static int step_host_enqueue(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
+                             uint8_t* terminated, bool queued) {
   DeviceGuard guard(h->device);
   const AnmConstHeader& H = h->H;
   const size_t B = (size_t)h->B;
@@ -731,6 +792,7 @@ int anm_step_host(anm_handle h, const double* action, const double* next_vars, d
   double* d_obs = (mode >= 1) ? mapped_device_pointer(obs) : nullptr;
   double* d_reward = (mode >= 1) ? mapped_device_pointer(reward) : nullptr;
   uint8_t* d_term = (mode >= 1) ? mapped_device_pointer(terminated) : nullptr;
+  const bool zc_in = d_action && (!next_vars || d_nv); /* every input is read straight from mapped host memory */
   if (!d_action) {
     CUDA_TRY(cudaMemcpyAsync(h->s_action, action, B * H.n_action * sizeof(double), cudaMemcpyHostToDevice, st));
     d_action = h->s_action;
@@ -739,13 +801,47 @@ int anm_step_host(anm_handle h, const double* action, const double* next_vars, d
     CUDA_TRY(cudaMemcpyAsync(h->s_nv, next_vars, B * H.n_next_vars * sizeof(double), cudaMemcpyHostToDevice, st));
     d_nv = h->s_nv;
   }
-  int rc = anm_step(h, d_action, next_vars ? d_nv : nullptr, d_obs ? d_obs : h->s_obs, d_reward ? d_reward : h->s_reward,
-                    d_term ? d_term : h->s_term, nullptr, st);
+  AnmLaunch p;
+  memset(&p, 0, sizeof(p));
+  p.mode = ANM_MODE_STEP;
+  p.action = d_action; p.next_vars = next_vars ? d_nv : nullptr;
+  p.obs = d_obs ? d_obs : h->s_obs; p.reward = d_reward ? d_reward : h->s_reward; p.term_out = d_term ? d_term : h->s_term;
+  /* Inputs that the kernel reads straight from mapped host memory cannot depend on earlier device work:
+   * a queued step is chained to the previous launch per instance.  Staged inputs are ordered by the copies. */
+  uint32_t lf = 0;
+  if (queued && zc_in) lf |= ANM_LF_CHAINED;
+  if (d_obs || d_reward || d_term) lf |= ANM_LF_SYSOUT;
+  int rc = launch(h, p, st, lf);
   if (rc) return rc;
   if (!d_obs) CUDA_TRY(cudaMemcpyAsync(obs, h->s_obs, B * H.n_obs * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (!d_reward) CUDA_TRY(cudaMemcpyAsync(reward, h->s_reward, B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (!d_term) CUDA_TRY(cudaMemcpyAsync(terminated, h->s_term, B, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  return ANM_OK;
+}
+
+int anm_step_host(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
+                  uint8_t* terminated) {
+  if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_host: null argument");
+  if (!next_vars && h->H.table_len == 0)
+    return fail(ANM_E_INVALID, "anm_step_host: next_vars is NULL but the environment has no built-in table");
+  int rc = step_host_enqueue(h, action, next_vars, obs, reward, terminated, false);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ANM_OK;
+}
+
+int anm_step_host_async(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
+                        uint8_t* terminated) {
+  if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_host_async: null argument");
+  if (!next_vars && h->H.table_len == 0)
+    return fail(ANM_E_INVALID, "anm_step_host_async: next_vars is NULL but the environment has no built-in table");
+  return step_host_enqueue(h, action, next_vars, obs, reward, terminated, true);
+}
+
+int anm_host_sync(anm_handle h) {
+  if (!h) return fail(ANM_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
   return ANM_OK;
 }
 

@@ -95,11 +95,48 @@ struct AnmLaunch {
   uint8_t* converged;
   int32_t* solver_stats; /* [B, 4] diagnostics: fallback iterations, large-angle iterations, SM cycles in the
                             Newton loop, SM cycles of the whole pass -- or NULL */
+  /* cross-launch ordering (see "launch chaining" below) */
+  uint32_t* seq;         /* [B] sequence number of the last launch that finished with this instance */
+  uint32_t seq_wait;     /* this launch may touch instance e once seq[e] has reached seq_wait ...      */
+  uint32_t seq_post;     /* ... and publishes seq_post when it is done with it                         */
+  uint32_t flags;        /* ANM_LF_* */
 };
+#define ANM_LF_CHAINED 1u /* inputs do not depend on earlier work in the stream: skip griddepcontrol.wait */
+#define ANM_LF_SYSOUT 2u  /* outputs live in mapped host memory: system-scope fence before publishing   */
 
 namespace anm {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+/* ---- launch chaining ------------------------------------------------------------------
+ * Environment instances are independent, so launch t+1 only depends on launch t *per instance*: instance e of
+ * step t+1 needs the carried state (SoC, aux, terminated, episode) that step t wrote for instance e, nothing else.
+ * Every launch is enqueued with programmatic stream serialisation (PDL): it signals `launch_dependents` at once,
+ * so the next launch of the stream becomes resident while this one is still running; what orders the two is
+ *   - `griddepcontrol.wait` (full completion + visibility of everything earlier in the stream) -- the default; or,
+ *   - for a CHAINED launch (the caller guarantees that its inputs were not produced by earlier work of the stream:
+ *     open-loop action sequences, host-supplied actions), only the per-instance sequence numbers seq[e]: the
+ *     instances whose Newton iteration diverged in step t (~1 %, 100 iterations, solve_load_flow.py:218) finish
+ *     their step while the other 99 % are already in step t+1 (and t+2, ...).
+ * seq[e] is published with a release store after a fence that covers the whole lane group's writes and consumed
+ * with an acquire load; the carried state is read with ld.global.cg (L2), never from a possibly stale L1 line.
+ * No deadlock: a launch only becomes resident after every CTA of its predecessor has started, so by induction
+ * every CTA that is being waited for is already running. */
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void seq_wait_for(const uint32_t* p, uint32_t want) {
+  uint32_t v;
+  int spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if ((int32_t)(v - want) >= 0) break;
+    __nanosleep(100);
+    if (++spins > (1 << 24)) __trap(); /* > 1.6 s: the launch that owns this instance never ran -- fail loudly */
+  }
+}
+__device__ __forceinline__ void seq_publish(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 /* ---- TMA bulk staging of the constant blob ------------------------------------------ */
 __device__ __forceinline__ void stage_constants(unsigned char* smem, const unsigned char* gblob, int bytes) {
@@ -1274,7 +1311,9 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
     anm_env_kernel(const AnmLaunch P) {
   constexpr bool FULL = (NB > 0) || (LPE == 32);
   extern __shared__ __align__(128) unsigned char smem[];
-  stage_constants(smem, P.blob, P.blob_bytes);
+  pdl_launch_dependents();                         /* the next launch may become resident now               */
+  stage_constants(smem, P.blob, P.blob_bytes);     /* constants never change: staged before any ordering   */
+  if (!(P.flags & ANM_LF_CHAINED)) pdl_wait();     /* everything earlier in the stream is complete+visible */
   const Cst C(smem + ANM_BLOB_SMEM_OFF);
   const AnmConstHeader& H = *C.H;
 
@@ -1297,14 +1336,15 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
     int act = ACT_NONE;
     const double* s0row = nullptr;
     if (e < P.B) {
+      seq_wait_for(P.seq + e, P.seq_wait); /* the previous launch is done with this instance */
       if (P.mode == ANM_MODE_TRANSITION) {
         act = ACT_TRANSITION;
       } else if (P.mode == ANM_MODE_RESET) {
         if (!P.mask || P.mask[e]) act = ACT_RESET, s0row = P.s0 + e * S;
-      } else if (!P.terminated[e]) {
+      } else if (!__ldcg(P.terminated + e)) {
         act = ACT_STEP;
       } else if (P.pool_size > 0) { /* optional next-step auto-reset (not in the reference) */
-        const uint32_t ep = P.episode[e];
+        const uint32_t ep = __ldcg(P.episode + e);
         const uint64_t h = ((uint64_t)e * 0x9E3779B97F4A7C15ull + (uint64_t)ep * 0xD1B54A32D192ED03ull) >> 17;
         s0row = P.pool + (int64_t)(h % (uint64_t)P.pool_size) * S;
         act = ACT_RESET;
@@ -1326,8 +1366,8 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
         if (P.n_iter) P.n_iter[e] = 0;
       }
     } else if (act != ACT_NONE) {
-      for (int k = lane; k < ns; k += LPE) soc[k] = P.soc[e * ns + k];
-      for (int k = lane; k < K; k += LPE) aux[k] = P.aux[e * K + k];
+      for (int k = lane; k < ns; k += LPE) soc[k] = __ldcg(P.soc + e * ns + k);
+      for (int k = lane; k < K; k += LPE) aux[k] = __ldcg(P.aux + e * K + k);
       if (act == ACT_STEP) {
         /* next_vars (anm6_easy.py:54-65) or caller-supplied vars (anm_env.py:370-380);
          * the new aux values wait in s0w until the step is known to be non-terminal */
@@ -1337,11 +1377,11 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
           for (int k = lane; k < ng; k += LPE) in_pp[k] = nv[nl + k];
           for (int k = lane; k < K; k += LPE) s0w[k] = nv[nl + ng + k];
         } else {
-          const int a = (int)fmod(P.aux[e * K + K - 1] + 1.0, (double)H.table_len);
+          const int a = (int)fmod(__ldcg(P.aux + e * K + K - 1) + 1.0, (double)H.table_len);
           const double* row = C.table + a * (nl + ng);
           for (int k = lane; k < nl; k += LPE) in_pl[k] = row[k];
           for (int k = lane; k < ng; k += LPE) in_pp[k] = row[nl + k];
-          for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : P.aux[e * K + k];
+          for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : __ldcg(P.aux + e * K + k);
         }
         /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410) */
         const double* av = P.action + e * A;
@@ -1436,7 +1476,7 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
           P.terminated[e] = stable ? 0 : 1;
           if (P.converged) P.converged[e] = stable ? 1 : 0;
           if (P.mode == ANM_MODE_STEP) { /* auto-reset inside a step call */
-            P.episode[e] = P.episode[e] + 1;
+            P.episode[e] = __ldcg(P.episode + e) + 1;
             P.reward[e] = 0.0;
             P.term_out[e] = stable ? 0 : 1;
             if (P.e_loss) P.e_loss[e] = 0.0;
@@ -1467,7 +1507,10 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
         if (P.n_iter) P.n_iter[e] = nit;
       }
     }
+    /* publish: the whole group's writes first (fence by every lane, then the group barrier), then seq[e] */
+    if (P.flags & ANM_LF_SYSOUT) __threadfence_system(); else __threadfence();
     gsync<FULL>(gm);
+    if (lane == 0 && e < P.B) seq_publish(P.seq + e, P.seq_post);
   }
 }
 

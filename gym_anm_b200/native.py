@@ -17,6 +17,15 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _host_ptr(a):
+    """Host buffer -> void*: NumPy array, CPU torch tensor, or a raw address (int) the caller computed once."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+
+
 class NativeBatch:
     def __init__(self, spec, num_envs, device=None):
         if not torch.cuda.is_available():
@@ -76,22 +85,47 @@ class NativeBatch:
                                        self._stream()), self.lib)  # fmt: skip
         return obs, state, converged
 
-    def step(self, action, next_vars=None, out=None, extras=None):
+    def step(self, action, next_vars=None, out=None, extras=None, chained=False):
         """out = (obs, reward, terminated) preallocated tensors or None; extras = dict of
-        optional preallocated tensors among state / e_loss / penalty / n_iter / full_state."""
+        optional preallocated tensors among state / e_loss / penalty / n_iter / full_state.
+        chained=True asserts that `action` / `next_vars` were not produced by work enqueued on the
+        current stream after the previous call on this handle (ANM_STEP_CHAINED, include/anm_b200.h)."""
         action = self._f64(action, self.A)
         nv = None if next_vars is None else self._f64(next_vars, self.NV)
         if out is None:
             out = (self.empty(self.B, self.O), self.empty(self.B), self.empty(self.B, dtype=torch.uint8))
         obs, reward, term = out
         ex = None
-        if extras:
+        if extras or chained:
             ex = _capi.StepExtras()
             for k in ("state", "e_loss", "penalty", "n_iter", "full_state", "solver_stats"):
-                t = extras.get(k)
+                t = (extras or {}).get(k)
                 setattr(ex, k, None if t is None else t.data_ptr())
+            ex.flags = _capi.STEP_CHAINED if chained else 0
         _capi.check(self.lib.anm_step(self.h, _ptr(action), _ptr(nv), _ptr(obs), _ptr(reward), _ptr(term),
                                       None if ex is None else C.byref(ex), self._stream()), self.lib)  # fmt: skip
+        return obs, reward, term
+
+    def rollout(self, actions, next_vars=None, out=None):
+        """T open-loop steps: actions [T, B, A] (next_vars [T, B, NV]) -> obs [T, B, O], reward [T, B],
+        terminated [T, B]; slice t equals the t-th step() (anm_rollout)."""
+        ok = lambda t, c: (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()  # noqa: E731
+                           and t.ndim == 3 and tuple(t.shape[1:]) == (self.B, c))
+        if not ok(actions, self.A):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float64) if not isinstance(actions, torch.Tensor) else actions,
+                                      dtype=torch.float64, device=self.device).contiguous()  # fmt: skip
+        if not ok(actions, self.A):
+            raise ValueError("expected actions of shape (T, %d, %d), got %s" % (self.B, self.A, tuple(actions.shape)))
+        T = actions.shape[0]
+        if next_vars is not None:
+            next_vars = torch.as_tensor(next_vars, dtype=torch.float64, device=self.device).contiguous()
+            if tuple(next_vars.shape) != (T, self.B, self.NV):
+                raise ValueError("expected next_vars of shape (%d, %d, %d)" % (T, self.B, self.NV))
+        if out is None:
+            out = (self.empty(T, self.B, self.O), self.empty(T, self.B), self.empty(T, self.B, dtype=torch.uint8))
+        obs, reward, term = out
+        _capi.check(self.lib.anm_rollout(self.h, C.c_int64(T), _ptr(actions), _ptr(next_vars), _ptr(obs), _ptr(reward),
+                                         _ptr(term), self._stream()), self.lib)  # fmt: skip
         return obs, reward, term
 
     def transition(self, p_load, p_pot, p_set, q_set):
@@ -130,8 +164,18 @@ class NativeBatch:
 
     def step_host(self, action, next_vars, obs, reward, terminated):
         """NumPy / pinned-host path: H2D + step + D2H inside the library, synchronous."""
-        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())  # noqa: E731
+        p = _host_ptr
         _capi.check(self.lib.anm_step_host(self.h, p(action), p(next_vars), p(obs), p(reward), p(terminated)), self.lib)
+
+    def step_host_async(self, action, next_vars, obs, reward, terminated):
+        """Queued step_host: returns at once; outputs are valid after host_sync().  One set of output buffers per
+        queued step."""
+        p = _host_ptr
+        _capi.check(self.lib.anm_step_host_async(self.h, p(action), p(next_vars), p(obs), p(reward), p(terminated)),
+                    self.lib)  # fmt: skip
+
+    def host_sync(self):
+        _capi.check(self.lib.anm_host_sync(self.h), self.lib)
 
     def reset_host(self, s0, mask, obs, state, converged):
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())  # noqa: E731

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ANM_ABI_VERSION 1
+#define ANM_ABI_VERSION 2
 
 /* error codes */
 #define ANM_OK 0
@@ -151,7 +151,18 @@ typedef struct anm_step_extras {
                                      partial-pivoting fallback, iterations with |theta| > 1e5,
                                      SM cycles/16 spent in the Newton loop, SM cycles of the pass.
                                      Only written by diagnostic builds (-DANM_DIAG=1, tools/).   */
+  uint32_t flags;                 /* ANM_STEP_* (ABI 2)                                              */
+  uint32_t reserved;
 } anm_step_extras;
+
+/* anm_step_extras.flags.  ANM_STEP_CHAINED: the caller guarantees that this step's inputs (action,
+ * next_vars) were NOT produced by work enqueued on `stream` after the previous anm_* call on this
+ * handle (open-loop action sequences, actions uploaded earlier, ...).  The step is then ordered
+ * against the previous launch per environment instance instead of per launch: instances whose
+ * Newton iteration diverged (100 iterations, solve_load_flow.py:218) finish step t while the rest
+ * of the batch is already in step t+1.  Results are identical with and without the flag; any later
+ * non-anm work on the stream still sees every earlier step complete (normal stream order). */
+#define ANM_STEP_CHAINED 1u
 
 typedef struct anm_handle_s* anm_handle;
 
@@ -178,6 +189,14 @@ int anm_reset(anm_handle h, const double* s0_dev, const uint8_t* mask_dev, doubl
 int anm_step(anm_handle h, const double* action_dev, const double* next_vars_dev_or_null,
              double* obs_dev, double* reward_dev, uint8_t* terminated_dev,
              const anm_step_extras* extras_or_null, void* stream);
+
+/* T consecutive ANMEnv.step calls with an open-loop action sequence (the random agent of
+ * examples/random_agent.py, a pre-computed MPC plan, a replayed log): action [T, B, n_action],
+ * next_vars [T, B, n_next_vars] or NULL, outputs obs [T, B, n_obs], reward [T, B],
+ * terminated [T, B] -- slice t is exactly what the t-th anm_step would have returned.
+ * Enqueues T step kernels, chained (ANM_STEP_CHAINED) after the first. */
+int anm_rollout(anm_handle h, int64_t T, const double* action_dev, const double* next_vars_dev_or_null,
+                double* obs_dev, double* reward_dev, uint8_t* terminated_dev, void* stream);
 
 /* Optional "next-step" auto-reset (not in the reference; off by default): an env that
  * enters anm_step terminated is re-initialised from a row of the s0 pool
@@ -212,6 +231,15 @@ int anm_step_host(anm_handle h, const double* action_host, const double* next_va
                   double* obs_host, double* reward_host, uint8_t* terminated_host);
 int anm_reset_host(anm_handle h, const double* s0_host, const uint8_t* mask_host_or_null,
                    double* obs_host, double* state_host_or_null, uint8_t* converged_host);
+
+/* Queued variant of anm_step_host: enqueues the H2D copy / step / D2H copy (or the zero-copy
+ * kernel) on the handle's stream and returns at once; the outputs are valid after anm_host_sync.
+ * The caller must keep every buffer of a queued step alive and untouched until then, and gives each
+ * queued step its own output buffers.  Consecutive queued steps are chained (see ANM_STEP_CHAINED:
+ * host-supplied actions cannot depend on earlier device work). */
+int anm_step_host_async(anm_handle h, const double* action_host, const double* next_vars_host_or_null,
+                        double* obs_host, double* reward_host, uint8_t* terminated_host);
+int anm_host_sync(anm_handle h);
 
 /* The handle's own cudaStream_t (the one the *_host calls run on), e.g. to record events. */
 void* anm_host_stream(anm_handle h);
