@@ -114,7 +114,7 @@ _PROTOS = {
     "anm_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     "anm_reset": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "anm_step": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(StepExtras), C.c_void_p]),
-    "anm_rollout": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "anm_rollout": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p]),
     "anm_set_autoreset_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "anm_transition": (C.c_int, [C.c_void_p] + [C.c_void_p] * 9 + [C.c_void_p]),
     "anm_get_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 3 + [C.c_void_p]),
@@ -123,8 +123,10 @@ _PROTOS = {
     "anm_reset_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "anm_step_host_async": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "anm_host_sync": (C.c_int, [C.c_void_p]),
+    "anm_rollout_host_async": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "anm_host_stream": (C.c_void_p, [C.c_void_p]),
     "anm_launch_count": (C.c_int64, [C.c_void_p]),
+    "anm_watchdog": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 

@@ -81,8 +81,10 @@ struct anm_handle_s {
   double* d_aux = nullptr;
   uint8_t* d_term = nullptr;
   uint32_t* d_episode = nullptr;
-  uint32_t* d_seq = nullptr; /* [B] per-instance launch sequence numbers (launch chaining, anm_kernels.cuh) */
-  uint32_t seq = 0;          /* sequence number of the last launch enqueued for this handle               */
+  uint32_t* d_seq = nullptr; /* [B + 64] per-instance launch ordinals, then the ticket counter (launch chaining,
+                                anm_kernels.cuh) */
+  uint32_t* wd_host = nullptr; /* [ANM_WD_WORDS] mapped host memory: chaining watchdog record */
+  uint32_t* wd_dev = nullptr;
   const double* pool = nullptr;
   int64_t pool_size = 0;
   /* launch geometry */
@@ -260,6 +262,44 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     }
     H.o_ctrl_dev = bb.add(ctrl);
     H.o_ctrl_rows = bb.add(rows);
+    /* candidate_table: every candidate of the exact projection (project_polygon, anm_kernels.cuh) as an affine map
+     * of (p, q, h[s1], h[s2]) -- the point, its projection on each row's line, each pairwise intersection, in the
+     * order of oracle/shims/cvxpy/_projection.py (ties go to the lowest candidate); parallel pairs are dropped. */
+    std::vector<int> cptr(1, 0), cinfo;
+    std::vector<double> ccoef;
+    for (int c = 0; c < H.n_ctrl; ++c) {
+      const double* a = &rows[(size_t)c * 3 * ANM_MAX_ROWS];
+      const double* b = a + ANM_MAX_ROWS;
+      const int R = (c < H.n_gen) ? 7 : 10;
+      auto push = [&](int s1, int s2, unsigned need, const double (&kx)[4], const double (&ky)[4]) {
+        cinfo.push_back(s1 | (s2 << 8) | (int)(need << 16));
+        ccoef.insert(ccoef.end(), kx, kx + 4);
+        ccoef.insert(ccoef.end(), ky, ky + 4);
+      };
+      push(0, 0, 0u, {1, 0, 0, 0}, {0, 1, 0, 0});
+      for (int k = 0; k < R; ++k) {
+        if (a[k] == 0.0 && b[k] == 0.0) continue;
+        if (b[k] == 0.0) {
+          push(k, k, 1u << k, {0, 0, 1.0 / a[k], 0}, {0, 1, 0, 0});
+        } else if (a[k] == 0.0) {
+          push(k, k, 1u << k, {1, 0, 0, 0}, {0, 0, 1.0 / b[k], 0});
+        } else {
+          const double w = 1.0 / (a[k] * a[k] + b[k] * b[k]);
+          push(k, k, 1u << k, {1.0 - a[k] * a[k] * w, -a[k] * b[k] * w, a[k] * w, 0},
+               {-a[k] * b[k] * w, 1.0 - b[k] * b[k] * w, b[k] * w, 0});
+        }
+      }
+      for (int j = 1; j < R; ++j)
+        for (int i = 0; i < j; ++i) {
+          const double det = a[i] * b[j] - a[j] * b[i];
+          if (det == 0.0) continue;
+          push(i, j, (1u << i) | (1u << j), {0, 0, b[j] / det, -b[i] / det}, {0, 0, -a[j] / det, a[i] / det});
+        }
+      cptr.push_back((int)cinfo.size());
+    }
+    H.o_cand_ptr = bb.add(cptr);
+    H.o_cand_info = bb.add(cinfo);
+    H.o_cand_coef = bb.add(ccoef);
   }
   {
     auto pack = [&](int n, const anm_var_spec* v, std::vector<int>& off, std::vector<double>& mul,
@@ -286,11 +326,7 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     std::vector<double> table;
     if (H.table_len > 0) table.assign(env->table, env->table + (size_t)H.table_len * (H.n_load + H.n_gen));
     H.o_table = bb.add(table);
-    std::vector<int> pi, pj;
-    for (int j = 1; j < ANM_MAX_ROWS; ++j)
-      for (int i = 0; i < j; ++i) pi.push_back(i), pj.push_back(j);
-    H.o_pair_i = bb.add(pi);
-    H.o_pair_j = bb.add(pj);
+    H.o_pair_i = H.o_pair_j = 0; /* superseded by the candidate table */
   }
   {
     /* Radial network?  The bus graph (branches) must be a tree rooted at the slack bus and no bus may have
@@ -431,7 +467,7 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_devp = take(D); H.w_devq = take(D); H.w_ppot = take(D); H.w_busp = take(N); H.w_busq = take(N);
     H.w_x = take(M); H.w_vre = take(N); H.w_vim = take(N); H.w_ere = take(N); H.w_eim = take(N);
     H.w_ire = take(N); H.w_iim = take(N);
-    H.w_J = take(H.solver == 4 ? 0 : M * (M + 1)); H.w_rowh = take(ANM_MAX_ROWS);
+    H.w_J = take(H.solver == 4 ? 0 : M * (M + 1)); H.w_rowh = take(H.n_ctrl * ANM_MAX_ROWS);
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
     H.w_vx = take(4 * N);
@@ -542,8 +578,8 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
   p.pool = h->pool; p.pool_size = h->pool_size;
   /* launch chaining: wait for the previous launch per instance, publish this one (anm_kernels.cuh) */
   p.seq = h->d_seq;
-  p.seq_wait = h->seq;
-  p.seq_post = ++h->seq;
+  p.ticket = h->d_seq + h->B + 32; /* its own 128-byte line */
+  p.watchdog = h->wd_dev;
   const bool pdl = pdl_enabled();
   p.flags = pdl ? flags : (flags & ~ANM_LF_CHAINED);
   cudaLaunchConfig_t cfg;
@@ -633,7 +669,7 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   ALLOC(h->d_aux, B * H.K * sizeof(double));
   ALLOC(h->d_term, B);
   ALLOC(h->d_episode, B * sizeof(uint32_t));
-  ALLOC(h->d_seq, B * sizeof(uint32_t));
+  ALLOC(h->d_seq, (B + 64) * sizeof(uint32_t));
   ALLOC(h->s_action, B * H.n_action * sizeof(double));
   ALLOC(h->s_nv, B * H.n_next_vars * sizeof(double));
   ALLOC(h->s_obs, B * H.n_obs * sizeof(double));
@@ -648,7 +684,12 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, B * H.K * sizeof(double) + (H.K ? 0 : 16));
   if (e == cudaSuccess) e = cudaMemset(h->d_term, 1, B); /* nothing is runnable before the first reset */
   if (e == cudaSuccess) e = cudaMemset(h->d_episode, 0, B * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(h->d_seq, 0, B * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->d_seq, 0, (B + 64) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->wd_host, ANM_WD_WORDS * sizeof(uint32_t), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    memset(h->wd_host, 0, ANM_WD_WORDS * sizeof(uint32_t));
+    e = cudaHostGetDevicePointer((void**)&h->wd_dev, h->wd_host, 0);
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy); /* the memsets above, before any other stream uses them */
   if (e != cudaSuccess) { anm_destroy(h); return fail(ANM_E_CUDA, "handle init: %s", cudaGetErrorString(e)); }
@@ -663,6 +704,7 @@ int anm_destroy(anm_handle h) {
   DeviceGuard guard(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_soc); cudaFree(h->d_aux); cudaFree(h->d_term); cudaFree(h->d_episode);
   cudaFree(h->d_seq);
+  if (h->wd_host) cudaFreeHost(h->wd_host);
   cudaFree(h->s_action); cudaFree(h->s_nv); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_s0);
   cudaFree(h->s_state); cudaFree(h->s_term); cudaFree(h->s_mask);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -707,32 +749,30 @@ int anm_step(anm_handle h, const double* action, const double* next_vars, double
   if (ex) {
     p.state = ex->state; p.e_loss = ex->e_loss; p.penalty = ex->penalty; p.n_iter = ex->n_iter;
     p.full_state = ex->full_state; p.solver_stats = ex->solver_stats;
+#if ANM_DIAG
+    if (ex->solver_stats) p.phase_stats = ex->solver_stats + 4 * h->B; /* diagnostic builds: the buffer is [B, 4 + 16] */
+#endif
     if (ex->flags & ANM_STEP_CHAINED) lf |= ANM_LF_CHAINED;
   }
   return launch(h, p, (cudaStream_t)stream, lf);
 }
 
 int anm_rollout(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs, double* reward,
-                uint8_t* terminated, void* stream) {
+                uint8_t* terminated, uint32_t flags, void* stream) {
   if (!h || !action || !obs || !reward || !terminated || T < 0) return fail(ANM_E_INVALID, "anm_rollout: bad argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_rollout: next_vars is NULL but the environment has no built-in table");
+  if (T > INT32_MAX) return fail(ANM_E_INVALID, "anm_rollout: T too large");
+  if (T == 0) return ANM_OK;
   DeviceGuard guard(h->device);
-  const AnmConstHeader& H = h->H;
-  const size_t B = (size_t)h->B;
-  for (int64_t t = 0; t < T; ++t) {
-    AnmLaunch p;
-    memset(&p, 0, sizeof(p));
-    p.mode = ANM_MODE_STEP;
-    p.action = action + (size_t)t * B * H.n_action;
-    p.next_vars = next_vars ? next_vars + (size_t)t * B * H.n_next_vars : nullptr;
-    p.obs = obs + (size_t)t * B * H.n_obs;
-    p.reward = reward + (size_t)t * B;
-    p.term_out = terminated + (size_t)t * B;
-    int rc = launch(h, p, (cudaStream_t)stream, t > 0 ? ANM_LF_CHAINED : 0u);
-    if (rc) return rc;
-  }
-  return ANM_OK;
+  /* ONE launch: every lane group takes its instance through the T steps (its carried state stays on chip), so an
+   * instance whose Newton iteration diverges delays nobody but the instances of its own warp */
+  AnmLaunch p;
+  memset(&p, 0, sizeof(p));
+  p.mode = ANM_MODE_STEP;
+  p.T = (int32_t)T;
+  p.action = action; p.next_vars = next_vars; p.obs = obs; p.reward = reward; p.term_out = terminated;
+  return launch(h, p, (cudaStream_t)stream, (flags & ANM_STEP_CHAINED) ? ANM_LF_CHAINED : 0u);
 }
 
 int anm_set_autoreset_pool(anm_handle h, const double* pool, int64_t pool_size) {
@@ -780,11 +820,13 @@ int anm_set_state(anm_handle h, const double* soc, const double* aux, const uint
   return ANM_OK;
 }
 
-static int step_host_enqueue(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
-                             uint8_t* terminated, bool queued) {
+static int step_host_enqueue(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs,
+                             double* reward, uint8_t* terminated, bool queued) {
   DeviceGuard guard(h->device);
   const AnmConstHeader& H = h->H;
-  const size_t B = (size_t)h->B;
+  const size_t B = (size_t)h->B * (size_t)T; /* rows of the [T, B, .] host arrays */
+  if (T > 1 && host_io_mode() < 2)
+    return fail(ANM_E_UNSUPPORTED, "anm_rollout_host_async needs the zero-copy path (ANM_HOST_IO=zc)");
   cudaStream_t st = h->stream;
   const int mode = host_io_mode();
   const double* d_action = (mode >= 2) ? mapped_device_pointer(action) : nullptr;
@@ -793,6 +835,8 @@ static int step_host_enqueue(anm_handle h, const double* action, const double* n
   double* d_reward = (mode >= 1) ? mapped_device_pointer(reward) : nullptr;
   uint8_t* d_term = (mode >= 1) ? mapped_device_pointer(terminated) : nullptr;
   const bool zc_in = d_action && (!next_vars || d_nv); /* every input is read straight from mapped host memory */
+  if (T > 1 && !(zc_in && d_obs && d_reward && d_term))
+    return fail(ANM_E_INVALID, "anm_rollout_host_async: every buffer must be pinned (page-locked, mapped) host memory");
   if (!d_action) {
     CUDA_TRY(cudaMemcpyAsync(h->s_action, action, B * H.n_action * sizeof(double), cudaMemcpyHostToDevice, st));
     d_action = h->s_action;
@@ -804,6 +848,7 @@ static int step_host_enqueue(anm_handle h, const double* action, const double* n
   AnmLaunch p;
   memset(&p, 0, sizeof(p));
   p.mode = ANM_MODE_STEP;
+  p.T = (int32_t)T;
   p.action = d_action; p.next_vars = next_vars ? d_nv : nullptr;
   p.obs = d_obs ? d_obs : h->s_obs; p.reward = d_reward ? d_reward : h->s_reward; p.term_out = d_term ? d_term : h->s_term;
   /* Inputs that the kernel reads straight from mapped host memory cannot depend on earlier device work:
@@ -824,7 +869,7 @@ int anm_step_host(anm_handle h, const double* action, const double* next_vars, d
   if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_host: null argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_step_host: next_vars is NULL but the environment has no built-in table");
-  int rc = step_host_enqueue(h, action, next_vars, obs, reward, terminated, false);
+  int rc = step_host_enqueue(h, 1, action, next_vars, obs, reward, terminated, false);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return ANM_OK;
@@ -835,7 +880,16 @@ int anm_step_host_async(anm_handle h, const double* action, const double* next_v
   if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_host_async: null argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_step_host_async: next_vars is NULL but the environment has no built-in table");
-  return step_host_enqueue(h, action, next_vars, obs, reward, terminated, true);
+  return step_host_enqueue(h, 1, action, next_vars, obs, reward, terminated, true);
+}
+
+int anm_rollout_host_async(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs,
+                           double* reward, uint8_t* terminated) {
+  if (!h || !action || !obs || !reward || !terminated || T < 1 || T > INT32_MAX)
+    return fail(ANM_E_INVALID, "anm_rollout_host_async: bad argument");
+  if (!next_vars && h->H.table_len == 0)
+    return fail(ANM_E_INVALID, "anm_rollout_host_async: next_vars is NULL but the environment has no built-in table");
+  return step_host_enqueue(h, T, action, next_vars, obs, reward, terminated, true);
 }
 
 int anm_host_sync(anm_handle h) {
@@ -869,5 +923,11 @@ int anm_reset_host(anm_handle h, const double* s0, const uint8_t* mask, double* 
 void* anm_host_stream(anm_handle h) { return h ? (void*)h->stream : nullptr; }
 
 int64_t anm_launch_count(anm_handle h) { return h ? h->launches : 0; }
+
+int anm_watchdog(anm_handle h, uint32_t* out8) {
+  if (!h || !out8) return fail(ANM_E_INVALID, "null argument");
+  for (int i = 0; i < ANM_WD_WORDS; ++i) out8[i] = h->wd_host ? ((volatile uint32_t*)h->wd_host)[i] : 0u;
+  return ANM_OK;
+}
 
 }  // extern "C"

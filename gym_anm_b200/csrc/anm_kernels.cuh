@@ -56,7 +56,7 @@
 #define ANM_VAR_THREADS 64 /* CTA size of the small-network kernels */
 #endif
 #ifndef ANM_VAR_MINB
-#define ANM_VAR_MINB 7 /* CTAs per SM they are register-limited to: 7 x 64 threads x 144 regs -> 28 envs/SM, one wave at B=4096 */
+#define ANM_VAR_MINB 5 /* CTAs per SM the small-network kernels are built for: 5 x 44 KB of shared memory per SM, <= 204 registers */
 #endif
 #ifndef ANM_VAR_YREG
 #define ANM_VAR_YREG 1 /* 1: the lane's dense Y row lives in registers; 0: re-read from shared memory */
@@ -96,11 +96,14 @@ struct AnmLaunch {
   int32_t* solver_stats; /* [B, 4] diagnostics: fallback iterations, large-angle iterations, SM cycles in the
                             Newton loop, SM cycles of the whole pass -- or NULL */
   /* cross-launch ordering (see "launch chaining" below) */
-  uint32_t* seq;         /* [B] sequence number of the last launch that finished with this instance */
-  uint32_t seq_wait;     /* this launch may touch instance e once seq[e] has reached seq_wait ...      */
-  uint32_t seq_post;     /* ... and publishes seq_post when it is done with it                         */
+  uint32_t* seq;         /* [B] ordinal of the last launch that finished with this instance          */
+  uint32_t* ticket;      /* [1] CTAs started so far on this handle: ordinal of a launch = ticket / grid + 1 */
+  uint32_t* watchdog;    /* [ANM_WD_WORDS] mapped host memory: record of a chaining time-out, or zeros */
   uint32_t flags;        /* ANM_LF_* */
+  int32_t* phase_stats;  /* [B, 16] diagnostic builds only: SM cycles at the end of each phase -- or NULL */
+  int32_t T;             /* step mode: consecutive steps in this launch; inputs / outputs are [T, B, .] (anm_rollout) */
 };
+#define ANM_WD_WORDS 8
 #define ANM_LF_CHAINED 1u /* inputs do not depend on earlier work in the stream: skip griddepcontrol.wait */
 #define ANM_LF_SYSOUT 2u  /* outputs live in mapped host memory: system-scope fence before publishing   */
 
@@ -118,20 +121,41 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
  *     open-loop action sequences, host-supplied actions), only the per-instance sequence numbers seq[e]: the
  *     instances whose Newton iteration diverged in step t (~1 %, 100 iterations, solve_load_flow.py:218) finish
  *     their step while the other 99 % are already in step t+1 (and t+2, ...).
+ * Launch k (k = 1, 2, ...) may touch instance e once seq[e] == k-1 and publishes seq[e] = k when it is done with it.
+ * k is not a kernel argument (a CUDA graph replays its arguments): every CTA draws a ticket from a device counter
+ * when it starts, and because all launches of a handle have the same grid and a launch only becomes resident after
+ * every CTA of its predecessor has started (and drawn), k = ticket / gridDim.x + 1 in every CTA of the launch.
  * seq[e] is published with a release store after a fence that covers the whole lane group's writes and consumed
  * with an acquire load; the carried state is read with ld.global.cg (L2), never from a possibly stale L1 line.
- * No deadlock: a launch only becomes resident after every CTA of its predecessor has started, so by induction
- * every CTA that is being waited for is already running. */
+ * No deadlock: by the same induction every CTA that is being waited for is already running.  A wait that lasts
+ * longer than 2 s writes a record to the handle's watchdog words (mapped host memory) and traps. */
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void seq_wait_for(const uint32_t* p, uint32_t want) {
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void chain_timeout(uint32_t* wd, int64_t e, uint32_t want, uint32_t seen) {
+  if (wd && atomicCAS(wd, 0u, 1u) == 0u) {
+    wd[1] = (uint32_t)e; wd[2] = want; wd[3] = seen; wd[4] = blockIdx.x; wd[5] = gridDim.x; wd[6] = threadIdx.x;
+    __threadfence_system();
+  }
+  __trap(); /* fail loudly: the launch that owns this instance never finished with it */
+}
+__device__ __forceinline__ void seq_wait_for(const uint32_t* p, uint32_t want, uint32_t* wd, int64_t e) {
   uint32_t v;
-  int spins = 0;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   for (;;) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if ((int32_t)(v - want) >= 0) break;
     __nanosleep(100);
-    if (++spins > (1 << 24)) __trap(); /* > 1.6 s: the launch that owns this instance never ran -- fail loudly */
+    if ((++spins & 1023u) == 0u) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) chain_timeout(wd, e, want, v);
+    }
   }
 }
 __device__ __forceinline__ void seq_publish(uint32_t* p, uint32_t v) {
@@ -139,15 +163,16 @@ __device__ __forceinline__ void seq_publish(uint32_t* p, uint32_t v) {
 }
 
 /* ---- TMA bulk staging of the constant blob ------------------------------------------ */
-__device__ __forceinline__ void stage_constants(unsigned char* smem, const unsigned char* gblob, int bytes) {
+/* Also draws the CTA's ticket (launch ordinal, see "launch chaining") while the copy is in flight and signals
+ * launch_dependents once the ticket is drawn; returns the ordinal of this launch. */
+__device__ __forceinline__ uint32_t stage_constants(unsigned char* smem, const unsigned char* gblob, int bytes,
+                                                    uint32_t* ticket) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* ord = reinterpret_cast<uint32_t*>(smem + 16);
   const uint32_t bar_a = smem_u32(bar);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
     int done = 0;
     while (done < bytes) {
@@ -159,7 +184,10 @@ __device__ __forceinline__ void stage_constants(unsigned char* smem, const unsig
           : "memory");
       done += chunk;
     }
+    *ord = atomicAdd(ticket, 1u) / gridDim.x + 1u;
   }
+  __syncthreads();         /* the ticket is drawn (its value has come back) before ...                        */
+  pdl_launch_dependents(); /* ... this CTA lets the next launch of the stream become resident                 */
   /* one warp polls the mbarrier (try_wait), the others park on the CTA barrier instead of spinning */
   if (threadIdx.x < 32) {
     uint32_t ok = 0;
@@ -174,6 +202,7 @@ __device__ __forceinline__ void stage_constants(unsigned char* smem, const unsig
     }
   }
   __syncthreads();
+  return *ord;
 }
 
 /* ---- lane-group collectives -----------------------------------------------------------
@@ -288,6 +317,8 @@ struct Cst {  // resolved pointers into the staged blob
       *jac_col, *jac_y, *ctrl_dev, *sv_off, *ov_off, *pair_i, *pair_j, *rad_parent, *rad_depth, *rad_child, *sp_blk_i, *sp_blk_j,
       *sp_blk_y, *sp_step, *sp_row, *sp_col, *sp_nbr, *sp_tgt;
   const double* rad_y;
+  const double4* cand_coef; /* [ncand_total][2]: kx, ky of every candidate */
+  const int *cand_info, *cand_ptr;
   __device__ explicit Cst(const unsigned char* b) {
     H = reinterpret_cast<const AnmConstHeader*>(b);
 #define DP(name, off) name = reinterpret_cast<const double*>(b + H->off)
@@ -303,59 +334,64 @@ struct Cst {  // resolved pointers into the staged blob
     IP(rad_parent, o_rad_parent); IP(rad_depth, o_rad_depth); IP(rad_child, o_rad_child);
     IP(sp_blk_i, o_sp_blk_i); IP(sp_blk_j, o_sp_blk_j); IP(sp_blk_y, o_sp_blk_y); IP(sp_step, o_sp_step);
     IP(sp_row, o_sp_row); IP(sp_col, o_sp_col); IP(sp_nbr, o_sp_nbr); IP(sp_tgt, o_sp_tgt);
+    cand_coef = reinterpret_cast<const double4*>(b + H->o_cand_coef);
+    IP(cand_info, o_cand_info); IP(cand_ptr, o_cand_ptr);
 #undef DP
 #undef IP
   }
 };
 
-/* ---- exact projection of (p,q) on the polygon rows a[],b[],h[] (R rows, h=inf unused) ---------
- * Candidates: the point itself, its projection on each boundary line, every pairwise line
- * intersection; closest feasible one wins (oracle/shims/cvxpy/_projection.py is the definition). */
-template <int LPE, bool FULL>
+/* ---- exact projection of (p,q) on the polygon rows a[],b[],h[] (R rows, non-finite h = unused) ----
+ * Candidates: the point itself, its projection on each boundary line, every pairwise line intersection;
+ * the closest feasible one wins, ties to the lowest candidate (oracle/shims/cvxpy/_projection.py is the
+ * definition; map_pq at devices.py:280-304, 472-522).  The normals (a, b) are constants of the device, only a
+ * few right-hand sides change per step (p_pot, the two SoC rows), so every candidate is an affine function
+ *     x = kx . (p, q, h[s1], h[s2]),   y = ky . (p, q, h[s1], h[s2])
+ * whose coefficients the host tabulated (anm_capi.cu: candidate_table; parallel pairs are dropped there):
+ * no divisions, no data-dependent control flow.  Axis-aligned rows have coefficients 0 / +-1, so box clipping
+ * stays exact (the reference's assertEqual tests, tests/simulator/test_devices.py:541-549).  `info` packs
+ * s1 | s2 << 8 | need << 16, need = bit mask of the rows the candidate lies on: they must have a finite h and are
+ * not tested against themselves.  Fully unrolled over the rounds: the rounds are independent, the compiler
+ * overlaps them. */
+template <int LPE, bool FULL, int R>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
-                                                const double* __restrict__ rh, const int* __restrict__ pair_i,
-                                                const int* __restrict__ pair_j, int R, double p, double q, int lane,
+                                                const double* __restrict__ rh, const double4* __restrict__ coef,
+                                                const int* __restrict__ info, int ncand, double p, double q, int lane,
                                                 unsigned gm, double& po, double& qo) {
+  constexpr int NC_MAX = 1 + R + R * (R - 1) / 2;
+  constexpr int ROUNDS = (NC_MAX + LPE - 1) / LPE;
+  double a[R], b[R], h[R];
+  unsigned fin = 0u;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    a[k] = ra[k];
+    b[k] = rb[k];
+    const double hk = rh[k];
+    const bool f = fabs(hk) < CUDART_INF; /* false for NaN */
+    fin |= f ? (1u << k) : 0u;
+    h[k] = f ? hk : CUDART_INF; /* a x + b y - inf > tol is never true: the row is skipped */
+  }
   double best = CUDART_INF, bx = CUDART_NAN, by = CUDART_NAN;
   int bidx = 1 << 20;
-  /* pairs are ordered (0,1),(0,2),(1,2),(0,3).. so the first R(R-1)/2 of them stay below R */
-  const int ncand = 1 + R + R * (R - 1) / 2;
-  for (int c = lane; c < ncand; c += LPE) {
-    double x = p, y = q;
-    int s1 = -1, s2 = -1;
-    bool valid = true;
-    if (c >= 1 && c <= R) {
-      s1 = c - 1;
-      const double a = ra[s1], b = rb[s1], h = rh[s1];
-      valid = isfinite(h);
-      if (b == 0.0) {
-        x = h / a;
-      } else if (a == 0.0) {
-        y = h / b;
-      } else {
-        const double t = (a * p + b * q - h) / (a * a + b * b);
-        x = p - t * a;
-        y = q - t * b;
-      }
-    } else if (c > R) {
-      s1 = pair_i[c - 1 - R];
-      s2 = pair_j[c - 1 - R];
-      const double a1 = ra[s1], b1 = rb[s1], h1 = rh[s1], a2 = ra[s2], b2 = rb[s2], h2 = rh[s2];
-      const double det = a1 * b2 - a2 * b1;
-      valid = isfinite(h1) && isfinite(h2) && det != 0.0;
-      x = (h1 * b2 - h2 * b1) / det;
-      y = (a1 * h2 - a2 * h1) / det;
-    }
-    if (valid) {
-      for (int k = 0; k < R; ++k) {
-        const double h = rh[k];
-        if (k != s1 && k != s2 && isfinite(h) && (ra[k] * x + rb[k] * y - h > ANM_FEAS_TOL)) valid = false;
-      }
-    }
-    if (valid) {
-      const double d = (x - p) * (x - p) + (y - q) * (y - q);
-      if (d < best) best = d, bx = x, by = y, bidx = c;
-    }
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const int c = lane + r * LPE;
+    const bool in = c < ncand;
+    const int cc = in ? c : 0;
+    const int nf = info[cc];
+    const int s1 = nf & 0xff, s2 = (nf >> 8) & 0xff;
+    const unsigned need = (unsigned)nf >> 16;
+    const double h1 = ((fin >> s1) & 1u) ? rh[s1] : 0.0, h2 = ((fin >> s2) & 1u) ? rh[s2] : 0.0;
+    const double4 kx = coef[2 * cc], ky = coef[2 * cc + 1];
+    const double x = fma(kx.x, p, fma(kx.y, q, fma(kx.z, h1, kx.w * h2)));
+    const double y = fma(ky.x, p, fma(ky.y, q, fma(ky.z, h1, ky.w * h2)));
+    bool ok = in && ((fin & need) == need);
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      ok = ok && (((need >> k) & 1u) || !(fma(a[k], x, fma(b[k], y, -h[k])) > ANM_FEAS_TOL));
+    const double dx = x - p, dy = y - q;
+    const double d = fma(dx, dx, dy * dy);
+    if (ok && d < best) best = d, bx = x, by = y, bidx = c;
   }
   /* arg-min over the group (ties -> lowest candidate index, like a serial scan) */
   double key = best;
@@ -1116,7 +1152,16 @@ struct RadialNR {
  * environment (a dead group runs along for lock-step but skips the Newton iterations). */
 template <int LPE, int NB, int SOLVER, bool FULL>
 __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
-                                           double& e_loss, double& penalty, int& n_iter_out, int& n_fb, int& n_big) {
+                                           double& e_loss, double& penalty, int& n_iter_out, int& n_fb, int& n_big
+#if ANM_DIAG
+                                           , long long* stamp
+#endif
+) {
+#if ANM_DIAG
+#define ANM_STAMP(i) stamp[i] = clock64()
+#else
+#define ANM_STAMP(i)
+#endif
   const AnmConstHeader& H = *C.H;
   const int N = H.n_bus, D = H.n_dev, L = H.n_branch;
   const double m = H.base_mva, dt = H.delta_t;
@@ -1143,33 +1188,43 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     }
     ppot[d] = pp;
   }
+  /* right-hand sides of every polygon row of every controllable device (no barrier needed before: the rows that
+   * depend on this step are recomputed from the inputs) */
+  for (int i = lane; i < H.n_ctrl * ANM_MAX_ROWS; i += LPE) {
+    const int c = i / ANM_MAX_ROWS, r = i - c * ANM_MAX_ROWS;
+    const int d = C.ctrl_dev[c];
+    const double* P = C.dev_param + d * ANM_DEV_NPARAM;
+    double h = C.ctrl_rows[c * 3 * ANM_MAX_ROWS + 2 * ANM_MAX_ROWS + r];
+    if (c < H.n_gen) {
+      if (r == 2) h = clipd(in_pp[c] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]); /* p <= p_pot, devices.py:296 */
+    } else {
+      const double sc = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
+      if (r == 8) h = -(sc - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
+      if (r == 9) h = eff * (sc - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
+    }
+    rowh[i] = h;
+  }
   gsync<FULL>(gm);
+  ANM_STAMP(0);
 
   /* 2. generators / storage units: exact projection on the feasible polygon, SoC update */
   for (int c = 0; c < H.n_ctrl; ++c) {
     const int d = C.ctrl_dev[c];
-    const double* P = C.dev_param + d * ANM_DEV_NPARAM;
     const double* rows = C.ctrl_rows + c * 3 * ANM_MAX_ROWS;
     const bool is_des = (c >= H.n_gen);
-    for (int r = lane; r < ANM_MAX_ROWS; r += LPE) {
-      double h = rows[2 * ANM_MAX_ROWS + r];
-      if (!is_des) {
-        if (r == 2) h = ppot[d]; /* p <= p_pot, devices.py:296 */
-      } else {
-        const double s = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
-        if (r == 8) h = -(s - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
-        if (r == 9) h = eff * (s - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
-      }
-      rowh[r] = h;
-    }
-    gsync<FULL>(gm);
+    const int c0 = C.cand_ptr[c], nc = C.cand_ptr[c + 1] - c0;
     double po, qo;
-    project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rowh, C.pair_i, C.pair_j, is_des ? 10 : 7, in_ps[c] / m,
-                               in_qs[c] / m, lane, gm, po, qo);
+    if (is_des)
+      project_polygon<LPE, FULL, 10>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, C.cand_coef + 2 * c0,
+                                     C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
+    else
+      project_polygon<LPE, FULL, 7>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, C.cand_coef + 2 * c0,
+                                    C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
     if (lane == 0) {
       devp[d] = po;
       devq[d] = qo;
-      if (is_des) { /* update_soc, devices.py:524-545 */
+      if (is_des && live) { /* update_soc, devices.py:524-545 (an idle group must not touch its carried SoC) */
+        const double* P = C.dev_param + d * ANM_DEV_NPARAM;
         double s = soc[c - H.n_gen];
         if (po <= 0.0)
           s -= dt * P[ANM_DP_EFF] * po;
@@ -1178,9 +1233,10 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
         soc[c - H.n_gen] = clipd(s, P[ANM_DP_SOCMIN], P[ANM_DP_SOCMAX]);
       }
     }
-    gsync<FULL>(gm);
   }
+  gsync<FULL>(gm);
 
+  ANM_STAMP(1);
   /* 3. bus injections, device-id order (simulator.py:539-549) */
   for (int b = lane; b < N; b += LPE) {
     double sp = 0.0, sq = 0.0;
@@ -1194,6 +1250,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   }
   gsync<FULL>(gm);
 
+  ANM_STAMP(2);
   /* 4. Newton-Raphson (solve_load_flow.py:176-226) */
   int it = 0;
   bool converged = false, stable = false;
@@ -1209,6 +1266,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   (void)converged;
   n_iter_out = it;
 
+  ANM_STAMP(3);
   /* 5. slack injection (:63-72) and branch flows (branch.py:153-198) */
   if (lane == 0) {
     const double sr = vre[0] * ire[0] + vim[0] * iim[0];
@@ -1258,6 +1316,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   pen = g_sum<LPE, FULL>(pen, gm) * (dt * H.lamb);
   e_loss = el;
   penalty = pen;
+  ANM_STAMP(4);
   return stable;
 }
 
@@ -1311,8 +1370,12 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
     anm_env_kernel(const AnmLaunch P) {
   constexpr bool FULL = (NB > 0) || (LPE == 32);
   extern __shared__ __align__(128) unsigned char smem[];
-  pdl_launch_dependents();                         /* the next launch may become resident now               */
-  stage_constants(smem, P.blob, P.blob_bytes);     /* constants never change: staged before any ordering   */
+#if ANM_DIAG
+  const long long t_k0 = clock64();
+  long long stamp[8];
+#endif
+  /* constants never change: staged before any ordering; `ord` = ordinal of this launch on its handle */
+  const uint32_t ord = stage_constants(smem, P.blob, P.blob_bytes, P.ticket);
   if (!(P.flags & ANM_LF_CHAINED)) pdl_wait();     /* everything earlier in the stream is complete+visible */
   const Cst C(smem + ANM_BLOB_SMEM_OFF);
   const AnmConstHeader& H = *C.H;
@@ -1330,187 +1393,234 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
   double* in_qs = ws + H.w_in_qs; double* soc = ws + H.w_soc; double* aux = ws + H.w_aux;
   double* s0w = ws + H.w_s0; double* full = ws + H.w_full;
 
-  /* every group of the block makes the same number of passes (lock-step warps) */
+  /* every group of the block makes the same number of passes (lock-step warps); a pass takes one instance
+   * through the T consecutive steps of this launch (T = 1 except for anm_rollout), its carried state staying in
+   * the workspace / registers in between */
+  const int T = (P.mode == ANM_MODE_STEP && P.T > 1) ? P.T : 1;
   for (int64_t base = (int64_t)blockIdx.x * GPB; base < P.B; base += (int64_t)gridDim.x * GPB) {
     const int64_t e = base + grp;
-    int act = ACT_NONE;
-    const double* s0row = nullptr;
-    if (e < P.B) {
-      seq_wait_for(P.seq + e, P.seq_wait); /* the previous launch is done with this instance */
-      if (P.mode == ANM_MODE_TRANSITION) {
-        act = ACT_TRANSITION;
-      } else if (P.mode == ANM_MODE_RESET) {
-        if (!P.mask || P.mask[e]) act = ACT_RESET, s0row = P.s0 + e * S;
-      } else if (!__ldcg(P.terminated + e)) {
-        act = ACT_STEP;
-      } else if (P.pool_size > 0) { /* optional next-step auto-reset (not in the reference) */
-        const uint32_t ep = __ldcg(P.episode + e);
-        const uint64_t h = ((uint64_t)e * 0x9E3779B97F4A7C15ull + (uint64_t)ep * 0xD1B54A32D192ED03ull) >> 17;
-        s0row = P.pool + (int64_t)(h % (uint64_t)P.pool_size) * S;
-        act = ACT_RESET;
-      } else {
-        act = ACT_ZERO;
-      }
-    }
-
-    /* ---- per-group prologue (no group collectives inside) ------------------------------------ */
-    if (act == ACT_ZERO) { /* anm_env.py:365-367 */
-      for (int k = lane; k < O; k += LPE) P.obs[e * O + k] = 0.0;
-      if (P.state) for (int k = lane; k < S; k += LPE) P.state[e * S + k] = 0.0;
-      if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = 0.0;
-      if (lane == 0) {
-        P.reward[e] = 0.0;
-        P.term_out[e] = 1;
-        if (P.e_loss) P.e_loss[e] = H.clip_e;
-        if (P.penalty) P.penalty[e] = H.clip_pen;
-        if (P.n_iter) P.n_iter[e] = 0;
-      }
-    } else if (act != ACT_NONE) {
+    const bool have = e < P.B;
+#if ANM_DIAG
+    const long long t_staged = clock64();
+#endif
+    bool term_c = true;  /* carried: ANMEnv.terminated */
+    uint32_t ep_c = 0;   /* carried: auto-reset counter */
+    if (have) {
+      seq_wait_for(P.seq + e, ord - 1u, P.watchdog, e); /* the previous launch is done with this instance */
+      term_c = __ldcg(P.terminated + e) != 0;
+      ep_c = __ldcg(P.episode + e);
       for (int k = lane; k < ns; k += LPE) soc[k] = __ldcg(P.soc + e * ns + k);
       for (int k = lane; k < K; k += LPE) aux[k] = __ldcg(P.aux + e * K + k);
-      if (act == ACT_STEP) {
+    }
+    gsync<FULL>(gm);
+
+    for (int t = 0; t < T; ++t) {
+      const int64_t row = (int64_t)t * P.B + e; /* this step's slice of the [T, B, .] inputs / outputs */
+      int act = ACT_NONE;
+      const double* s0row = nullptr;
+      if (have) {
+        if (P.mode == ANM_MODE_TRANSITION) {
+          act = ACT_TRANSITION;
+        } else if (P.mode == ANM_MODE_RESET) {
+          if (!P.mask || P.mask[e]) act = ACT_RESET, s0row = P.s0 + e * S;
+        } else if (!term_c) {
+          act = ACT_STEP;
+        } else if (P.pool_size > 0) { /* optional next-step auto-reset (not in the reference) */
+          const uint64_t h = ((uint64_t)e * 0x9E3779B97F4A7C15ull + (uint64_t)ep_c * 0xD1B54A32D192ED03ull) >> 17;
+          s0row = P.pool + (int64_t)(h % (uint64_t)P.pool_size) * S;
+          act = ACT_RESET;
+        } else {
+          act = ACT_ZERO;
+        }
+      }
+
+      /* ---- per-group prologue (no group collectives inside) ------------------------------------ */
+      if (act == ACT_ZERO) { /* anm_env.py:365-367 */
+        for (int k = lane; k < O; k += LPE) P.obs[row * O + k] = 0.0;
+        if (P.state) for (int k = lane; k < S; k += LPE) P.state[row * S + k] = 0.0;
+        if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = 0.0;
+        if (lane == 0) {
+          P.reward[row] = 0.0;
+          P.term_out[row] = 1;
+          if (P.e_loss) P.e_loss[row] = H.clip_e;
+          if (P.penalty) P.penalty[row] = H.clip_pen;
+          if (P.n_iter) P.n_iter[row] = 0;
+        }
+      } else if (act == ACT_STEP) {
         /* next_vars (anm6_easy.py:54-65) or caller-supplied vars (anm_env.py:370-380);
          * the new aux values wait in s0w until the step is known to be non-terminal */
         if (P.next_vars) {
-          const double* nv = P.next_vars + e * NV;
+          const double* nv = P.next_vars + row * NV;
           for (int k = lane; k < nl; k += LPE) in_pl[k] = nv[k];
           for (int k = lane; k < ng; k += LPE) in_pp[k] = nv[nl + k];
           for (int k = lane; k < K; k += LPE) s0w[k] = nv[nl + ng + k];
         } else {
-          const int a = (int)fmod(__ldcg(P.aux + e * K + K - 1) + 1.0, (double)H.table_len);
-          const double* row = C.table + a * (nl + ng);
-          for (int k = lane; k < nl; k += LPE) in_pl[k] = row[k];
-          for (int k = lane; k < ng; k += LPE) in_pp[k] = row[nl + k];
-          for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : __ldcg(P.aux + e * K + k);
+          const int a = (int)fmod(aux[K - 1] + 1.0, (double)H.table_len);
+          const double* trow = C.table + a * (nl + ng);
+          for (int k = lane; k < nl; k += LPE) in_pl[k] = trow[k];
+          for (int k = lane; k < ng; k += LPE) in_pp[k] = trow[nl + k];
+          for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : aux[k];
         }
         /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410) */
-        const double* av = P.action + e * A;
+        const double* av = P.action + row * A;
         for (int k = lane; k < ng; k += LPE) { in_ps[k] = av[k]; in_qs[k] = av[ng + k]; }
         for (int k = lane; k < ns; k += LPE) { in_ps[ng + k] = av[2 * ng + k]; in_qs[ng + k] = av[2 * ng + ns + k]; }
       } else if (act == ACT_TRANSITION) {
         for (int k = lane; k < nl; k += LPE) in_pl[k] = P.p_load[e * nl + k];
         for (int k = lane; k < ng; k += LPE) in_pp[k] = P.p_pot[e * ng + k];
         for (int k = lane; k < nc; k += LPE) { in_ps[k] = P.p_set[e * nc + k]; in_qs[k] = P.q_set[e * nc + k]; }
-      } else { /* ACT_RESET: Simulator.reset (simulator.py:225-293); s0 row kept in s0w */
+      } else if (act == ACT_RESET) { /* Simulator.reset (simulator.py:225-293); s0 row kept in s0w */
         for (int k = lane; k < S; k += LPE) s0w[k] = s0row[k];
       }
-    }
-    gsync<FULL>(gm);
-    if (act == ACT_RESET) {
-      for (int d = lane; d < D; d += LPE) {
-        const int t = C.dev_type[d], slot = C.dev_slot[d];
-        if (t == ANM_DEV_LOAD) {
-          in_pl[slot] = s0w[d];
-        } else if (t == ANM_DEV_GEN || t == ANM_DEV_RENEWABLE) {
-          in_ps[slot] = s0w[d];
-          in_qs[slot] = s0w[D + d];
-          in_pp[slot] = s0w[2 * D + ns + slot];
-        } else if (t == ANM_DEV_STORAGE) {
-          const double* Pp = C.dev_param + d * ANM_DEV_NPARAM;
-          in_ps[ng + slot] = s0w[d];
-          in_qs[ng + slot] = s0w[D + d];
-          soc[slot] = (s0w[d] <= 0.0) ? Pp[ANM_DP_SOCMIN] : Pp[ANM_DP_SOCMAX]; /* :273-278 */
+      gsync<FULL>(gm);
+      if (act == ACT_RESET) {
+        for (int d = lane; d < D; d += LPE) {
+          const int ty = C.dev_type[d], slot = C.dev_slot[d];
+          if (ty == ANM_DEV_LOAD) {
+            in_pl[slot] = s0w[d];
+          } else if (ty == ANM_DEV_GEN || ty == ANM_DEV_RENEWABLE) {
+            in_ps[slot] = s0w[d];
+            in_qs[slot] = s0w[D + d];
+            in_pp[slot] = s0w[2 * D + ns + slot];
+          } else if (ty == ANM_DEV_STORAGE) {
+            const double* Pp = C.dev_param + d * ANM_DEV_NPARAM;
+            in_ps[ng + slot] = s0w[d];
+            in_qs[ng + slot] = s0w[D + d];
+            soc[slot] = (s0w[d] <= 0.0) ? Pp[ANM_DP_SOCMIN] : Pp[ANM_DP_SOCMAX]; /* :273-278 */
+          }
         }
       }
-    }
-    gsync<FULL>(gm);
+      gsync<FULL>(gm);
 
-    /* ---- the transition itself: all groups of the warp together ---------------------------------- */
-    const bool run = (act >= ACT_STEP);
-    double el, pe;
-    int nit, nfb, nbig;
+      /* ---- the transition itself: all groups of the warp together ---------------------------------- */
+      const bool run = (act >= ACT_STEP);
+      double el, pe;
+      int nit, nfb, nbig;
 #if ANM_DIAG
-    const long long t_pass0 = P.solver_stats ? clock64() : 0;
+      const long long t_pass0 = clock64();
+      const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig, stamp);
+      const long long t_trans = clock64();
+      if (P.solver_stats && run && lane == 0) {
+        P.solver_stats[4 * e] = nfb & 0xffff;
+        P.solver_stats[4 * e + 1] = nbig;
+        P.solver_stats[4 * e + 2] = nfb >> 16; /* Newton-loop cycles / 16 (see SmallNR::run) */
+        P.solver_stats[4 * e + 3] = (int)(t_trans - t_pass0);
+      }
+#else
+      const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig);
 #endif
-    const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig);
+
+      /* ---- carried-state updates that feed the state vector ----------------------------------------- */
+      const bool term = !stable;
+      if (act == ACT_RESET) {
+        /* SoC <- s0 (simulator.py:284-288); aux <- s0 tail (anm_env.py:587) */
+        for (int k = lane; k < ns; k += LPE) soc[k] = s0w[2 * D + k] / H.base_mva;
+        for (int k = lane; k < K; k += LPE) aux[k] = s0w[S - K + k];
+      } else if (act == ACT_STEP && !term) {
+        for (int k = lane; k < K; k += LPE) aux[k] = s0w[k];
+      }
+      gsync<FULL>(gm);
+      gather_full_state<LPE, FULL>(C, ws, lane, gm,
+                                   P.mode == ANM_MODE_TRANSITION || H.need_angles || P.full_state != nullptr);
 #if ANM_DIAG
-    if (P.solver_stats && run && lane == 0) {
-      P.solver_stats[4 * e] = nfb & 0xffff;
-      P.solver_stats[4 * e + 1] = nbig;
-      P.solver_stats[4 * e + 2] = nfb >> 16; /* Newton-loop cycles / 16 (see SmallNR::run) */
-      P.solver_stats[4 * e + 3] = (int)(clock64() - t_pass0);
-    }
+      const long long t_gather = clock64();
 #endif
 
-    /* ---- carried-state updates that feed the state vector ----------------------------------------- */
-    const bool term = !stable;
-    if (act == ACT_RESET) {
-      /* SoC <- s0 (simulator.py:284-288); aux <- s0 tail (anm_env.py:587) */
-      for (int k = lane; k < ns; k += LPE) soc[k] = s0w[2 * D + k] / H.base_mva;
-      for (int k = lane; k < K; k += LPE) aux[k] = s0w[S - K + k];
-    } else if (act == ACT_STEP && !term) {
-      for (int k = lane; k < K; k += LPE) aux[k] = s0w[k];
-    }
-    gsync<FULL>(gm);
-    gather_full_state<LPE, FULL>(C, ws, lane, gm,
-                                 P.mode == ANM_MODE_TRANSITION || H.need_angles || P.full_state != nullptr);
-
-    /* ---- per-group epilogue (no group collectives inside) ------------------------------------------- */
-    if (act == ACT_TRANSITION) {
-      if (P.full_state) for (int k = lane; k < F - K; k += LPE) P.full_state[e * (F - K) + k] = full[k];
-      for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
-      if (lane == 0) {
-        if (P.reward) P.reward[e] = -(el + pe);
-        if (P.e_loss) P.e_loss[e] = el;
-        if (P.penalty) P.penalty[e] = pe;
-        if (P.converged) P.converged[e] = stable ? 1 : 0;
-        if (P.n_iter) P.n_iter[e] = nit;
-      }
-    } else if (act == ACT_RESET || (act == ACT_STEP && !term)) {
-      for (int k = lane; k < O; k += LPE) {
-        double v = full[C.ov_off[k]] * C.ov_mul[k];
-        if (C.ov_div[k] != 1.0) v /= C.ov_div[k];
-        P.obs[e * O + k] = clipd(v, C.ov_low[k], C.ov_high[k]);
-      }
-      if (P.state)
-        for (int k = lane; k < S; k += LPE) {
-          double v = full[C.sv_off[k]] * C.sv_mul[k];
-          if (C.sv_div[k] != 1.0) v /= C.sv_div[k];
-          P.state[e * S + k] = v;
+      /* ---- per-group epilogue (no group collectives inside) ------------------------------------------- */
+      if (act == ACT_TRANSITION) {
+        if (P.full_state) for (int k = lane; k < F - K; k += LPE) P.full_state[e * (F - K) + k] = full[k];
+        if (lane == 0) {
+          if (P.reward) P.reward[e] = -(el + pe);
+          if (P.e_loss) P.e_loss[e] = el;
+          if (P.penalty) P.penalty[e] = pe;
+          if (P.converged) P.converged[e] = stable ? 1 : 0;
+          if (P.n_iter) P.n_iter[e] = nit;
         }
-      if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = full[k];
+      } else if (act == ACT_RESET || (act == ACT_STEP && !term)) {
+        for (int k = lane; k < O; k += LPE) {
+          double v = full[C.ov_off[k]] * C.ov_mul[k];
+          if (C.ov_div[k] != 1.0) v /= C.ov_div[k];
+          P.obs[row * O + k] = clipd(v, C.ov_low[k], C.ov_high[k]);
+        }
+        if (P.state)
+          for (int k = lane; k < S; k += LPE) {
+            double v = full[C.sv_off[k]] * C.sv_mul[k];
+            if (C.sv_div[k] != 1.0) v /= C.sv_div[k];
+            P.state[row * S + k] = v;
+          }
+        if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = full[k];
+        if (act == ACT_RESET) {
+          term_c = !stable;
+          if (P.mode == ANM_MODE_STEP) ++ep_c; /* auto-reset inside a step call */
+        } else {
+          term_c = false;
+        }
+        if (lane == 0) {
+          if (act == ACT_RESET) {
+            if (P.converged) P.converged[e] = stable ? 1 : 0;
+            if (P.mode == ANM_MODE_STEP) {
+              P.reward[row] = 0.0;
+              P.term_out[row] = stable ? 0 : 1;
+              if (P.e_loss) P.e_loss[row] = 0.0;
+              if (P.penalty) P.penalty[row] = 0.0;
+            }
+          } else { /* anm_env.py:424-427 */
+            const double elc = sign_nan(el) * clipd(fabs(el), 0.0, H.clip_e);
+            const double pec = clipd(pe, 0.0, H.clip_pen);
+            P.term_out[row] = 0;
+            P.reward[row] = -(elc + pec);
+            if (P.e_loss) P.e_loss[row] = elc;
+            if (P.penalty) P.penalty[row] = pec;
+          }
+          if (P.n_iter) P.n_iter[row] = nit;
+        }
+      } else if (act == ACT_STEP) { /* terminal step: anm_env.py:428-432, 446-448 */
+        for (int k = lane; k < O; k += LPE) P.obs[row * O + k] = 0.0;
+        if (P.state) for (int k = lane; k < S; k += LPE) P.state[row * S + k] = 0.0;
+        if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = 0.0;
+        term_c = true;
+        if (lane == 0) {
+          P.term_out[row] = 1;
+          P.reward[row] = H.term_reward; /* -clip_pen / (1 - gamma), anm_env.py:430 */
+          if (P.e_loss) P.e_loss[row] = H.clip_e;
+          if (P.penalty) P.penalty[row] = H.clip_pen;
+          if (P.n_iter) P.n_iter[row] = nit;
+        }
+      }
+#if ANM_DIAG
+      if (P.phase_stats && run && lane == 0) { /* SM cycles since kernel entry at the end of each phase */
+        int32_t* o = P.phase_stats + 16 * e;
+        o[0] = (int)(t_staged - t_k0);   /* constants staged, launch-level wait done */
+        o[1] = (int)(t_pass0 - t_k0);    /* instance wait + prologue loads           */
+        o[2] = (int)(stamp[0] - t_k0);   /* loads / p_pot clamps / polygon rows      */
+        o[3] = (int)(stamp[1] - t_k0);   /* projections + SoC                        */
+        o[4] = (int)(stamp[2] - t_k0);   /* bus injections                           */
+        o[5] = (int)(stamp[3] - t_k0);   /* Newton-Raphson                           */
+        o[6] = (int)(stamp[4] - t_k0);   /* branch flows + reward                    */
+        o[7] = (int)(t_gather - t_k0);   /* gather_full_state                        */
+        o[8] = (int)(clock64() - t_k0);  /* epilogue stores                          */
+        o[10] = nit;
+      }
+#endif
+      gsync<FULL>(gm); /* the workspace is reused by the next step */
+    }
+
+    /* ---- carried state back to global memory, then publish: the whole group's writes first (fence by every
+     * lane, then the group barrier), then seq[e] ------------------------------------------------------------ */
+    if (have) {
       for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
       for (int k = lane; k < K; k += LPE) P.aux[e * K + k] = aux[k];
       if (lane == 0) {
-        if (act == ACT_RESET) {
-          P.terminated[e] = stable ? 0 : 1;
-          if (P.converged) P.converged[e] = stable ? 1 : 0;
-          if (P.mode == ANM_MODE_STEP) { /* auto-reset inside a step call */
-            P.episode[e] = __ldcg(P.episode + e) + 1;
-            P.reward[e] = 0.0;
-            P.term_out[e] = stable ? 0 : 1;
-            if (P.e_loss) P.e_loss[e] = 0.0;
-            if (P.penalty) P.penalty[e] = 0.0;
-          }
-        } else { /* anm_env.py:424-427 */
-          const double elc = sign_nan(el) * clipd(fabs(el), 0.0, H.clip_e);
-          const double pec = clipd(pe, 0.0, H.clip_pen);
-          P.terminated[e] = 0;
-          P.term_out[e] = 0;
-          P.reward[e] = -(elc + pec);
-          if (P.e_loss) P.e_loss[e] = elc;
-          if (P.penalty) P.penalty[e] = pec;
-        }
-        if (P.n_iter) P.n_iter[e] = nit;
-      }
-    } else if (act == ACT_STEP) { /* terminal step: anm_env.py:428-432, 446-448 */
-      for (int k = lane; k < O; k += LPE) P.obs[e * O + k] = 0.0;
-      if (P.state) for (int k = lane; k < S; k += LPE) P.state[e * S + k] = 0.0;
-      if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[e * F + k] = 0.0;
-      for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
-      if (lane == 0) {
-        P.terminated[e] = 1;
-        P.term_out[e] = 1;
-        P.reward[e] = H.term_reward; /* -clip_pen / (1 - gamma), anm_env.py:430 */
-        if (P.e_loss) P.e_loss[e] = H.clip_e;
-        if (P.penalty) P.penalty[e] = H.clip_pen;
-        if (P.n_iter) P.n_iter[e] = nit;
+        P.terminated[e] = term_c ? 1 : 0;
+        P.episode[e] = ep_c;
       }
     }
-    /* publish: the whole group's writes first (fence by every lane, then the group barrier), then seq[e] */
     if (P.flags & ANM_LF_SYSOUT) __threadfence_system(); else __threadfence();
     gsync<FULL>(gm);
-    if (lane == 0 && e < P.B) seq_publish(P.seq + e, P.seq_post);
+    if (lane == 0 && have) seq_publish(P.seq + e, ord);
+#if ANM_DIAG
+    if (P.phase_stats && have && lane == 0) P.phase_stats[16 * e + 9] = (int)(clock64() - t_k0); /* fence + publish */
+#endif
   }
 }
 

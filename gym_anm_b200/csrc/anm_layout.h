@@ -43,6 +43,10 @@ struct AnmConstHeader {
   int32_t o_ov_off, o_ov_mul, o_ov_div, o_ov_low, o_ov_high; /* obs vars                       */
   int32_t o_table;                           /* double[table_len][n_load+n_gen]                */
   int32_t o_pair_i, o_pair_j;                /* int[ANM_NPAIRS]                                */
+  /* projection candidates of every controllable device (anm_capi.cu: candidate_table) */
+  int32_t o_cand_ptr;                        /* int[n_ctrl+1]: first candidate of each device               */
+  int32_t o_cand_info;                       /* int[ncand]: s1 | s2 << 8 | need << 16                       */
+  int32_t o_cand_coef;                       /* double[ncand][8]: kx[4], ky[4] on (p, q, h[s1], h[s2])      */
   /* radial networks (bus graph = tree rooted at the slack): per non-slack bus b (lane b-1) */
   int32_t is_radial, rad_maxc, rad_maxdepth;
   int32_t o_rad_parent, o_rad_depth;         /* int[n_bus-1]: parent's lane (-1 = slack), depth >= 1 */

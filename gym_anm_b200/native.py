@@ -106,9 +106,9 @@ class NativeBatch:
                                       None if ex is None else C.byref(ex), self._stream()), self.lib)  # fmt: skip
         return obs, reward, term
 
-    def rollout(self, actions, next_vars=None, out=None):
-        """T open-loop steps: actions [T, B, A] (next_vars [T, B, NV]) -> obs [T, B, O], reward [T, B],
-        terminated [T, B]; slice t equals the t-th step() (anm_rollout)."""
+    def rollout(self, actions, next_vars=None, out=None, chained=False):
+        """T open-loop steps in one kernel launch: actions [T, B, A] (next_vars [T, B, NV]) -> obs [T, B, O],
+        reward [T, B], terminated [T, B]; slice t equals the t-th step() (anm_rollout)."""
         ok = lambda t, c: (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()  # noqa: E731
                            and t.ndim == 3 and tuple(t.shape[1:]) == (self.B, c))
         if not ok(actions, self.A):
@@ -125,7 +125,8 @@ class NativeBatch:
             out = (self.empty(T, self.B, self.O), self.empty(T, self.B), self.empty(T, self.B, dtype=torch.uint8))
         obs, reward, term = out
         _capi.check(self.lib.anm_rollout(self.h, C.c_int64(T), _ptr(actions), _ptr(next_vars), _ptr(obs), _ptr(reward),
-                                         _ptr(term), self._stream()), self.lib)  # fmt: skip
+                                         _ptr(term), _capi.STEP_CHAINED if chained else 0, self._stream()),
+                    self.lib)  # fmt: skip
         return obs, reward, term
 
     def transition(self, p_load, p_pot, p_set, q_set):
@@ -174,6 +175,12 @@ class NativeBatch:
         _capi.check(self.lib.anm_step_host_async(self.h, p(action), p(next_vars), p(obs), p(reward), p(terminated)),
                     self.lib)  # fmt: skip
 
+    def rollout_host_async(self, T, actions, next_vars, obs, reward, terminated):
+        """Queued rollout on pinned host arrays [T, B, .] (zero-copy); valid after host_sync()."""
+        p = _host_ptr
+        _capi.check(self.lib.anm_rollout_host_async(self.h, C.c_int64(T), p(actions), p(next_vars), p(obs), p(reward),
+                                                    p(terminated)), self.lib)  # fmt: skip
+
     def host_sync(self):
         _capi.check(self.lib.anm_host_sync(self.h), self.lib)
 
@@ -185,6 +192,12 @@ class NativeBatch:
     def host_stream(self):
         """torch view of the library's own stream (the one step_host / reset_host run on)."""
         return torch.cuda.ExternalStream(int(self.lib.anm_host_stream(self.h)), device=self.device)
+
+    def watchdog(self):
+        """Record left by a chained launch that timed out (all zeros normally); readable after a launch failure."""
+        out = (C.c_uint32 * 8)()
+        _capi.check(self.lib.anm_watchdog(self.h, out), self.lib)
+        return list(out)
 
     @property
     def launch_count(self):

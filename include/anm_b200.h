@@ -194,9 +194,11 @@ int anm_step(anm_handle h, const double* action_dev, const double* next_vars_dev
  * examples/random_agent.py, a pre-computed MPC plan, a replayed log): action [T, B, n_action],
  * next_vars [T, B, n_next_vars] or NULL, outputs obs [T, B, n_obs], reward [T, B],
  * terminated [T, B] -- slice t is exactly what the t-th anm_step would have returned.
- * Enqueues T step kernels, chained (ANM_STEP_CHAINED) after the first. */
+ * ONE kernel launch: every environment instance is taken through its T steps with its carried
+ * state on chip, so instances do not wait for each other between steps.  flags: ANM_STEP_CHAINED
+ * (same contract as for anm_step: the inputs do not depend on earlier work of the stream). */
 int anm_rollout(anm_handle h, int64_t T, const double* action_dev, const double* next_vars_dev_or_null,
-                double* obs_dev, double* reward_dev, uint8_t* terminated_dev, void* stream);
+                double* obs_dev, double* reward_dev, uint8_t* terminated_dev, uint32_t flags, void* stream);
 
 /* Optional "next-step" auto-reset (not in the reference; off by default): an env that
  * enters anm_step terminated is re-initialised from a row of the s0 pool
@@ -240,12 +242,22 @@ int anm_reset_host(anm_handle h, const double* s0_host, const uint8_t* mask_host
 int anm_step_host_async(anm_handle h, const double* action_host, const double* next_vars_host_or_null,
                         double* obs_host, double* reward_host, uint8_t* terminated_host);
 int anm_host_sync(anm_handle h);
+/* Queued anm_rollout on host buffers: [T, B, .] arrays, all of them pinned (page-locked, mapped) host
+ * memory that the kernel reads / writes directly; valid after anm_host_sync. */
+int anm_rollout_host_async(anm_handle h, int64_t T, const double* action_host,
+                           const double* next_vars_host_or_null, double* obs_host, double* reward_host,
+                           uint8_t* terminated_host);
 
 /* The handle's own cudaStream_t (the one the *_host calls run on), e.g. to record events. */
 void* anm_host_stream(anm_handle h);
 
 /* Number of kernels this library has launched on behalf of `h` (for bench accounting). */
 int64_t anm_launch_count(anm_handle h);
+
+/* Diagnostic: a chained launch that waited more than 2 s for an instance records
+ * [1, instance, ordinal waited for, ordinal seen, CTA, grid, thread, 0] here (host memory, readable
+ * even after the CUDA context reported the launch failure) and traps; all zeros otherwise. */
+int anm_watchdog(anm_handle h, uint32_t* out8);
 
 #ifdef __cplusplus
 }

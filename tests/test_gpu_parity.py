@@ -535,15 +535,17 @@ def _two_envs(B, seed, pool=True):
 
 @pytest.mark.parametrize("autoreset", [True, False])
 def test_rollout_equals_stepwise(autoreset):
-    """anm_rollout (chained launches: step t+1 overlaps the divergent instances of step t) returns, slice by
-    slice, bit-identical results to T separate anm_step calls -- with and without auto-reset (terminated
+    """anm_rollout (one launch, every instance runs its T steps on its own) returns, slice by slice,
+    bit-identical results to T separate anm_step calls -- with and without auto-reset (terminated
     instances then stay at zeros / 0.0 / True, anm_env.py:365-367)."""
     B, T = 4096, 96
     a_env, b_env = _two_envs(B, 21, pool=autoreset)
     na, nb = a_env.native, b_env.native
     rng = np.random.default_rng(5)
     acts = torch.as_tensor(rng.uniform(a_env.spec.action_low, a_env.spec.action_high, size=(T, B, 6)), device=na.device)
-    obs_r, rew_r, term_r = nb.rollout(acts)
+    obs_r, rew_r, term_r = nb.rollout(acts[:T // 2])
+    obs_2, rew_2, term_2 = nb.rollout(acts[T // 2:], chained=True)  # second launch ordered per instance
+    obs_r, rew_r, term_r = torch.cat([obs_r, obs_2]), torch.cat([rew_r, rew_2]), torch.cat([term_r, term_2])
     n_term = 0
     for t in range(T):
         obs, rew, term = na.step(acts[t])
@@ -622,6 +624,27 @@ def test_queued_host_steps_equal_synchronous_ones():
     assert term_q.sum() > 0
 
 
+def test_rollout_on_pinned_host_buffers():
+    """anm_rollout_host_async: [T, B, .] pinned host arrays read / written by the kernel == device rollout."""
+    B, T = 512, 32
+    a_env, b_env = _two_envs(B, 44)
+    na, nb = a_env.native, b_env.native
+    rng = np.random.default_rng(10)
+    acts = torch.as_tensor(rng.uniform(a_env.spec.action_low, a_env.spec.action_high, size=(2 * T, B, 6)))
+    acts_pin = acts.pin_memory()
+    obs_q = torch.zeros(2 * T, B, 18, dtype=torch.float64).pin_memory()
+    rew_q = torch.zeros(2 * T, B, dtype=torch.float64).pin_memory()
+    term_q = torch.zeros(2 * T, B, dtype=torch.uint8).pin_memory()
+    for i in range(2):
+        sl = slice(i * T, (i + 1) * T)
+        nb.rollout_host_async(T, acts_pin[sl], None, obs_q[sl], rew_q[sl], term_q[sl])
+    nb.host_sync()
+    obs_d, rew_d, term_d = na.rollout(acts.to(na.device))
+    assert torch.equal(obs_d.cpu(), obs_q) and torch.equal(rew_d.cpu(), rew_q) and torch.equal(term_d.cpu(), term_q)
+    with pytest.raises(Exception):  # pageable memory is refused loudly (no silent staging for T > 1)
+        nb.rollout_host_async(T, acts[:T], None, obs_q[:T], rew_q[:T], term_q[:T])
+
+
 def test_chaining_off_same_results_subprocess():
     """ANM_PDL=0 (no programmatic dependent launch, every launch fully ordered) gives the same results."""
     import os
@@ -629,7 +652,8 @@ def test_chaining_off_same_results_subprocess():
     import sys
 
     here = os.path.abspath(__file__)
-    sel = "test_rollout_equals_stepwise or test_chained_steps_graph_replay_and_oracle or test_queued_host_steps"
+    sel = ("test_rollout_equals_stepwise or test_chained_steps_graph_replay_and_oracle or test_queued_host_steps "
+           "or test_rollout_on_pinned")
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
                        env=dict(os.environ, ANM_PDL="0"), capture_output=True, text=True, timeout=900)  # fmt: skip
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
