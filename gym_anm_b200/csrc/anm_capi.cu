@@ -308,7 +308,10 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
         if (v[k].quantity < 0 || v[k].quantity >= ANM_NQUANTITY) return fail(ANM_E_INVALID, "var %d: bad quantity", k);
         if (v[k].index < 0 || v[k].index >= var_limit(H, v[k].quantity)) return fail(ANM_E_INVALID, "var %d: bad index", k);
         if (v[k].quantity == ANM_Q_BUS_V_ANG || v[k].quantity == ANM_Q_BUS_I_ANG || v[k].quantity == ANM_Q_BRANCH_I_ANG)
-          H.need_angles = 1;
+          H.need_angles = 1, H.need_mask |= ANM_NEED_ANGLES;
+        if (v[k].quantity == ANM_Q_BUS_V_MAGN) H.need_mask |= ANM_NEED_BUS_V;
+        if (v[k].quantity == ANM_Q_BUS_I_MAGN) H.need_mask |= ANM_NEED_BUS_I;
+        if (v[k].quantity == ANM_Q_BRANCH_I_MAGN) H.need_mask |= ANM_NEED_BRANCH_I;
         off.push_back(full_offset(H, v[k].quantity) + v[k].index);
         mul.push_back(v[k].mul); dv.push_back(v[k].div); lo.push_back(v[k].low); hi.push_back(v[k].high);
       }

@@ -253,6 +253,10 @@ __device__ __forceinline__ unsigned g_umax(unsigned key, unsigned gm, int grp_in
   return res;
 }
 
+/* |x + jy| as sqrt(x^2 + y^2): within 1 ulp of hypot (numpy's abs of a complex) for the per-unit magnitudes of a power
+ * flow, a fraction of its instructions; inf / NaN propagate (an overflowing square gives +inf like the true magnitude
+ * of a diverged iterate would for all purposes here: the step is then terminal and its outputs are constants). */
+__device__ __forceinline__ double cabs2(double x, double y) { return sqrt(fma(x, x, y * y)); }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ double relu_nan(double x) { return (x != x) ? x : (x > 0.0 ? x : 0.0); }
 __device__ __forceinline__ double sign_nan(double x) { return (x != x) ? x : (x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0)); }
@@ -309,6 +313,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
+/* int(v % len) of ANM6Easy.next_vars (anm6_easy.py:56): v is an integer-valued counter in practice, for which
+ * v - floor(v / len) * len is exact and a dozen instructions; anything else takes fmod. */
+__device__ __forceinline__ int next_slot(double v, double len) {
+  if (v >= 0.0 && v < 4503599627370496.0 && v == floor(v)) return (int)fma(-floor(v / len), len, v);
+  return (int)fmod(v, len);
+}
+
 struct Cst {  // resolved pointers into the staged blob
   const AnmConstHeader* H;
   const double *vmin, *vmax, *dev_param, *br_coef, *y_val, *ctrl_rows, *sv_mul, *sv_div, *ov_mul, *ov_div, *ov_low,
@@ -351,15 +362,13 @@ struct Cst {  // resolved pointers into the staged blob
  * no divisions, no data-dependent control flow.  Axis-aligned rows have coefficients 0 / +-1, so box clipping
  * stays exact (the reference's assertEqual tests, tests/simulator/test_devices.py:541-549).  `info` packs
  * s1 | s2 << 8 | need << 16, need = bit mask of the rows the candidate lies on: they must have a finite h and are
- * not tested against themselves.  Fully unrolled over the rounds: the rounds are independent, the compiler
- * overlaps them. */
-template <int LPE, bool FULL, int R>
+ * not tested against themselves. */
+template <int LPE, bool FULL>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
                                                 const double* __restrict__ rh, const double4* __restrict__ coef,
                                                 const int* __restrict__ info, int ncand, double p, double q, int lane,
                                                 unsigned gm, double& po, double& qo) {
-  constexpr int NC_MAX = 1 + R + R * (R - 1) / 2;
-  constexpr int ROUNDS = (NC_MAX + LPE - 1) / LPE;
+  constexpr int R = ANM_MAX_ROWS; /* generators: rows 7..9 carry h = +inf (never active) */
   double a[R], b[R], h[R];
   unsigned fin = 0u;
 #pragma unroll
@@ -373,9 +382,10 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
   }
   double best = CUDART_INF, bx = CUDART_NAN, by = CUDART_NAN;
   int bidx = 1 << 20;
-#pragma unroll
-  for (int r = 0; r < ROUNDS; ++r) {
-    const int c = lane + r * LPE;
+  /* a compact loop on purpose (the body stays in the instruction cache); every lane makes the same trips */
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncand; c0 += LPE) {
+    const int c = c0 + lane;
     const bool in = c < ncand;
     const int cc = in ? c : 0;
     const int nf = info[cc];
@@ -385,13 +395,17 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
     const double4 kx = coef[2 * cc], ky = coef[2 * cc + 1];
     const double x = fma(kx.x, p, fma(kx.y, q, fma(kx.z, h1, kx.w * h2)));
     const double y = fma(ky.x, p, fma(ky.y, q, fma(ky.z, h1, ky.w * h2)));
-    bool ok = in && ((fin & need) == need);
+    /* branch-free: the R residuals are independent; viol collects the rows that the candidate breaks */
+    unsigned viol = 0u;
 #pragma unroll
-    for (int k = 0; k < R; ++k)
-      ok = ok && (((need >> k) & 1u) || !(fma(a[k], x, fma(b[k], y, -h[k])) > ANM_FEAS_TOL));
+    for (int k = 0; k < R; ++k) viol |= (fma(a[k], x, fma(b[k], y, -h[k])) > ANM_FEAS_TOL) ? (1u << k) : 0u;
     const double dx = x - p, dy = y - q;
     const double d = fma(dx, dx, dy * dy);
-    if (ok && d < best) best = d, bx = x, by = y, bidx = c;
+    const bool take = in & ((fin & need) == need) & ((viol & ~need) == 0u) & (d < best);
+    best = take ? d : best;
+    bx = take ? x : bx;
+    by = take ? y : by;
+    bidx = take ? c : bidx;
   }
   /* arg-min over the group (ties -> lowest candidate index, like a serial scan) */
   double key = best;
@@ -478,7 +492,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
         re = vm * c;
         im = vm * s;
       }
-      const double a = hypot(re, im);
+      const double a = cabs2(re, im);
       vre[b] = re; vim[b] = im;
       ere[b] = re / a; eim[b] = im / a;
     }
@@ -1172,6 +1186,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* rowh = ws + H.w_rowh;
 
   /* 1. loads, p_pot, slack (devices.py:156-167, simulator.py:511, 521-523) */
+#pragma unroll 1
   for (int d = lane; d < D; d += LPE) {
     const int t = C.dev_type[d], slot = C.dev_slot[d];
     const double* P = C.dev_param + d * ANM_DEV_NPARAM;
@@ -1190,6 +1205,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   }
   /* right-hand sides of every polygon row of every controllable device (no barrier needed before: the rows that
    * depend on this step are recomputed from the inputs) */
+#pragma unroll 1
   for (int i = lane; i < H.n_ctrl * ANM_MAX_ROWS; i += LPE) {
     const int c = i / ANM_MAX_ROWS, r = i - c * ANM_MAX_ROWS;
     const int d = C.ctrl_dev[c];
@@ -1208,18 +1224,15 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   ANM_STAMP(0);
 
   /* 2. generators / storage units: exact projection on the feasible polygon, SoC update */
+#pragma unroll 1
   for (int c = 0; c < H.n_ctrl; ++c) {
     const int d = C.ctrl_dev[c];
     const double* rows = C.ctrl_rows + c * 3 * ANM_MAX_ROWS;
     const bool is_des = (c >= H.n_gen);
     const int c0 = C.cand_ptr[c], nc = C.cand_ptr[c + 1] - c0;
     double po, qo;
-    if (is_des)
-      project_polygon<LPE, FULL, 10>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, C.cand_coef + 2 * c0,
-                                     C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
-    else
-      project_polygon<LPE, FULL, 7>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, C.cand_coef + 2 * c0,
-                                    C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
+    project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, C.cand_coef + 2 * c0,
+                               C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
     if (lane == 0) {
       devp[d] = po;
       devq[d] = qo;
@@ -1238,8 +1251,10 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
 
   ANM_STAMP(1);
   /* 3. bus injections, device-id order (simulator.py:539-549) */
+#pragma unroll 1
   for (int b = lane; b < N; b += LPE) {
     double sp = 0.0, sq = 0.0;
+#pragma unroll 1
     for (int k = C.bus_dev_ptr[b]; k < C.bus_dev_ptr[b + 1]; ++k) {
       const int d = C.bus_dev_idx[k];
       sp += devp[d];
@@ -1274,6 +1289,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const double bp = (sr != sr) ? CUDART_INF : sr, bq = (si != si) ? CUDART_INF : si;
     busp[0] = bp;
     busq[0] = bq;
+#pragma unroll 1
     for (int k = C.bus_dev_ptr[0]; k < C.bus_dev_ptr[1]; ++k) {
       const int d = C.bus_dev_idx[k];
       if (C.dev_type[d] == ANM_DEV_SLACK) devp[d] = bp, devq[d] = bq;
@@ -1282,6 +1298,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   double* brp = ws + H.w_brp; double* brq = ws + H.w_brq; double* brs = ws + H.w_brs;
   double* brire = ws + H.w_brire; double* briim = ws + H.w_briim;
   double pen = 0.0;
+#pragma unroll 1
   for (int l = lane; l < L; l += LPE) {
     const double* A = C.br_coef + l * 10;
     const int f = C.br_from[l], t = C.br_to[l];
@@ -1293,7 +1310,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const double iti = (A[6] * ti + A[7] * tr) + (A[4] * fi + A[5] * fr);
     const double pf = fr * ifr + fi * ifi, qf = fi * ifr - fr * ifi; /* s_from = v_f conj(i_from) */
     const double pt = tr * itr + ti * iti, qt = ti * itr - tr * iti;
-    const double af = hypot(pf, qf), at = hypot(pt, qt);
+    const double af = cabs2(pf, qf), at = cabs2(pt, qt);
     const double mx = (af != af || at != at) ? CUDART_NAN : fmax(af, at);
     const double s = sign_nan(pf) * mx; /* branch.py:198 */
     brp[l] = pf; brq[l] = qf; brs[l] = s; brire[l] = ifr; briim[l] = ifi;
@@ -1303,13 +1320,15 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
 
   /* 6. reward terms (simulator.py:638-683) */
   double el = 0.0;
+#pragma unroll 1
   for (int d = lane; d < D; d += LPE) {
     const int t = C.dev_type[d];
     if (t != ANM_DEV_STORAGE) el += devp[d];
     if (t == ANM_DEV_RENEWABLE) el += relu_nan(ppot[d] - devp[d]);
   }
+#pragma unroll 1
   for (int b = lane; b < N; b += LPE) {
-    const double vm = hypot(vre[b], vim[b]);
+    const double vm = cabs2(vre[b], vim[b]);
     pen += relu_nan(vm - C.vmax[b]) + relu_nan(C.vmin[b] - vm);
   }
   el = g_sum<LPE, FULL>(el, gm) * dt;
@@ -1321,9 +1340,15 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
 }
 
 /* Simulator._gather_state (simulator.py:551-636), p.u. / rad, layout of anm_b200.h */
+/* `need` = ANM_NEED_* bits: only the groups of quantities that some state / observation entry (or the caller's
+ * full-state output) asks for are evaluated -- ANM6Easy's state needs no voltage / current magnitude at all. */
+#define ANM_NEED_BUS_V 1u    /* bus_v_magn (hypot)            */
+#define ANM_NEED_BUS_I 2u    /* bus_i_magn (hypot)            */
+#define ANM_NEED_ANGLES 4u   /* the three angle groups (atan2) */
+#define ANM_NEED_BRANCH_I 8u /* branch_i_magn                  */
 template <int LPE, bool FULL>
 __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restrict__ ws, int lane, unsigned gm,
-                                                  bool angles) {
+                                                  unsigned need) {
   const AnmConstHeader& H = *C.H;
   const int N = H.n_bus, D = H.n_dev, L = H.n_branch;
   double* full = ws + H.w_full;
@@ -1331,15 +1356,18 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
                *ire = ws + H.w_ire, *iim = ws + H.w_iim, *devp = ws + H.w_devp, *devq = ws + H.w_devq,
                *ppot = ws + H.w_ppot, *soc = ws + H.w_soc, *brp = ws + H.w_brp, *brq = ws + H.w_brq,
                *brs = ws + H.w_brs, *brire = ws + H.w_brire, *briim = ws + H.w_briim, *aux = ws + H.w_aux;
+  const bool angles = (need & ANM_NEED_ANGLES) != 0u;
+#pragma unroll 1
   for (int b = lane; b < N; b += LPE) {
     full[b] = busp[b];
     full[N + b] = busq[b];
-    full[2 * N + b] = hypot(vre[b], vim[b]);
+    full[2 * N + b] = (need & ANM_NEED_BUS_V) ? cabs2(vre[b], vim[b]) : 0.0;
     full[3 * N + b] = angles ? atan2(vim[b], vre[b]) : 0.0;
-    full[4 * N + b] = hypot(ire[b], iim[b]);
+    full[4 * N + b] = (need & ANM_NEED_BUS_I) ? cabs2(ire[b], iim[b]) : 0.0;
     full[5 * N + b] = angles ? atan2(iim[b], ire[b]) : 0.0;
   }
   double* fd = full + 6 * N;
+#pragma unroll 1
   for (int d = lane; d < D; d += LPE) {
     const int t = C.dev_type[d];
     fd[d] = devp[d];
@@ -1348,15 +1376,21 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
     fd[3 * D + d] = (t == ANM_DEV_GEN || t == ANM_DEV_RENEWABLE) ? ppot[d] : 0.0;
   }
   double* fb = fd + 4 * D;
+#pragma unroll 1
   for (int l = lane; l < L; l += LPE) {
     fb[l] = brp[l];
     fb[L + l] = brq[l];
     fb[2 * L + l] = brs[l];
-    const double a = hypot(brire[l], briim[l]);
-    fb[3 * L + l] = (a == 0.0) ? 0.0 : (brire[l] / a) * a; /* simulator.py:613, NumPy>=2 sign(z) */
+    double im = 0.0;
+    if (need & ANM_NEED_BRANCH_I) {
+      const double a = cabs2(brire[l], briim[l]);
+      im = (a == 0.0) ? 0.0 : (brire[l] / a) * a; /* simulator.py:613, NumPy>=2 sign(z) */
+    }
+    fb[3 * L + l] = im;
     fb[4 * L + l] = angles ? atan2(briim[l], brire[l]) : 0.0;
   }
   double* fa = fb + 5 * L;
+#pragma unroll 1
   for (int k = lane; k < H.K; k += LPE) fa[k] = aux[k];
   gsync<FULL>(gm);
 }
@@ -1409,7 +1443,9 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
       seq_wait_for(P.seq + e, ord - 1u, P.watchdog, e); /* the previous launch is done with this instance */
       term_c = __ldcg(P.terminated + e) != 0;
       ep_c = __ldcg(P.episode + e);
+#pragma unroll 1
       for (int k = lane; k < ns; k += LPE) soc[k] = __ldcg(P.soc + e * ns + k);
+#pragma unroll 1
       for (int k = lane; k < K; k += LPE) aux[k] = __ldcg(P.aux + e * K + k);
     }
     gsync<FULL>(gm);
@@ -1436,9 +1472,16 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 
       /* ---- per-group prologue (no group collectives inside) ------------------------------------ */
       if (act == ACT_ZERO) { /* anm_env.py:365-367 */
+#pragma unroll 1
         for (int k = lane; k < O; k += LPE) P.obs[row * O + k] = 0.0;
-        if (P.state) for (int k = lane; k < S; k += LPE) P.state[row * S + k] = 0.0;
-        if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = 0.0;
+        if (P.state) {
+#pragma unroll 1
+          for (int k = lane; k < S; k += LPE) P.state[row * S + k] = 0.0;
+        }
+        if (P.full_state) {
+#pragma unroll 1
+          for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = 0.0;
+        }
         if (lane == 0) {
           P.reward[row] = 0.0;
           P.term_out[row] = 1;
@@ -1451,29 +1494,42 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
          * the new aux values wait in s0w until the step is known to be non-terminal */
         if (P.next_vars) {
           const double* nv = P.next_vars + row * NV;
+#pragma unroll 1
           for (int k = lane; k < nl; k += LPE) in_pl[k] = nv[k];
+#pragma unroll 1
           for (int k = lane; k < ng; k += LPE) in_pp[k] = nv[nl + k];
+#pragma unroll 1
           for (int k = lane; k < K; k += LPE) s0w[k] = nv[nl + ng + k];
         } else {
-          const int a = (int)fmod(aux[K - 1] + 1.0, (double)H.table_len);
+          const int a = next_slot(aux[K - 1] + 1.0, (double)H.table_len);
           const double* trow = C.table + a * (nl + ng);
+#pragma unroll 1
           for (int k = lane; k < nl; k += LPE) in_pl[k] = trow[k];
+#pragma unroll 1
           for (int k = lane; k < ng; k += LPE) in_pp[k] = trow[nl + k];
+#pragma unroll 1
           for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : aux[k];
         }
         /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410) */
         const double* av = P.action + row * A;
+#pragma unroll 1
         for (int k = lane; k < ng; k += LPE) { in_ps[k] = av[k]; in_qs[k] = av[ng + k]; }
+#pragma unroll 1
         for (int k = lane; k < ns; k += LPE) { in_ps[ng + k] = av[2 * ng + k]; in_qs[ng + k] = av[2 * ng + ns + k]; }
       } else if (act == ACT_TRANSITION) {
+#pragma unroll 1
         for (int k = lane; k < nl; k += LPE) in_pl[k] = P.p_load[e * nl + k];
+#pragma unroll 1
         for (int k = lane; k < ng; k += LPE) in_pp[k] = P.p_pot[e * ng + k];
+#pragma unroll 1
         for (int k = lane; k < nc; k += LPE) { in_ps[k] = P.p_set[e * nc + k]; in_qs[k] = P.q_set[e * nc + k]; }
       } else if (act == ACT_RESET) { /* Simulator.reset (simulator.py:225-293); s0 row kept in s0w */
+#pragma unroll 1
         for (int k = lane; k < S; k += LPE) s0w[k] = s0row[k];
       }
       gsync<FULL>(gm);
       if (act == ACT_RESET) {
+#pragma unroll 1
         for (int d = lane; d < D; d += LPE) {
           const int ty = C.dev_type[d], slot = C.dev_slot[d];
           if (ty == ANM_DEV_LOAD) {
@@ -1514,21 +1570,27 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
       const bool term = !stable;
       if (act == ACT_RESET) {
         /* SoC <- s0 (simulator.py:284-288); aux <- s0 tail (anm_env.py:587) */
+#pragma unroll 1
         for (int k = lane; k < ns; k += LPE) soc[k] = s0w[2 * D + k] / H.base_mva;
+#pragma unroll 1
         for (int k = lane; k < K; k += LPE) aux[k] = s0w[S - K + k];
       } else if (act == ACT_STEP && !term) {
+#pragma unroll 1
         for (int k = lane; k < K; k += LPE) aux[k] = s0w[k];
       }
       gsync<FULL>(gm);
       gather_full_state<LPE, FULL>(C, ws, lane, gm,
-                                   P.mode == ANM_MODE_TRANSITION || H.need_angles || P.full_state != nullptr);
+                                   (P.mode == ANM_MODE_TRANSITION || P.full_state != nullptr) ? ~0u : (unsigned)H.need_mask);
 #if ANM_DIAG
       const long long t_gather = clock64();
 #endif
 
       /* ---- per-group epilogue (no group collectives inside) ------------------------------------------- */
       if (act == ACT_TRANSITION) {
-        if (P.full_state) for (int k = lane; k < F - K; k += LPE) P.full_state[e * (F - K) + k] = full[k];
+        if (P.full_state) {
+#pragma unroll 1
+          for (int k = lane; k < F - K; k += LPE) P.full_state[e * (F - K) + k] = full[k];
+        }
         if (lane == 0) {
           if (P.reward) P.reward[e] = -(el + pe);
           if (P.e_loss) P.e_loss[e] = el;
@@ -1537,18 +1599,24 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
           if (P.n_iter) P.n_iter[e] = nit;
         }
       } else if (act == ACT_RESET || (act == ACT_STEP && !term)) {
+#pragma unroll 1
         for (int k = lane; k < O; k += LPE) {
           double v = full[C.ov_off[k]] * C.ov_mul[k];
           if (C.ov_div[k] != 1.0) v /= C.ov_div[k];
           P.obs[row * O + k] = clipd(v, C.ov_low[k], C.ov_high[k]);
         }
-        if (P.state)
+        if (P.state) {
+#pragma unroll 1
           for (int k = lane; k < S; k += LPE) {
             double v = full[C.sv_off[k]] * C.sv_mul[k];
             if (C.sv_div[k] != 1.0) v /= C.sv_div[k];
             P.state[row * S + k] = v;
           }
-        if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = full[k];
+        }
+        if (P.full_state) {
+#pragma unroll 1
+          for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = full[k];
+        }
         if (act == ACT_RESET) {
           term_c = !stable;
           if (P.mode == ANM_MODE_STEP) ++ep_c; /* auto-reset inside a step call */
@@ -1575,9 +1643,16 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
           if (P.n_iter) P.n_iter[row] = nit;
         }
       } else if (act == ACT_STEP) { /* terminal step: anm_env.py:428-432, 446-448 */
+#pragma unroll 1
         for (int k = lane; k < O; k += LPE) P.obs[row * O + k] = 0.0;
-        if (P.state) for (int k = lane; k < S; k += LPE) P.state[row * S + k] = 0.0;
-        if (P.full_state) for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = 0.0;
+        if (P.state) {
+#pragma unroll 1
+          for (int k = lane; k < S; k += LPE) P.state[row * S + k] = 0.0;
+        }
+        if (P.full_state) {
+#pragma unroll 1
+          for (int k = lane; k < F; k += LPE) P.full_state[row * F + k] = 0.0;
+        }
         term_c = true;
         if (lane == 0) {
           P.term_out[row] = 1;
@@ -1608,7 +1683,9 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
     /* ---- carried state back to global memory, then publish: the whole group's writes first (fence by every
      * lane, then the group barrier), then seq[e] ------------------------------------------------------------ */
     if (have) {
+#pragma unroll 1
       for (int k = lane; k < ns; k += LPE) P.soc[e * ns + k] = soc[k];
+#pragma unroll 1
       for (int k = lane; k < K; k += LPE) P.aux[e * K + k] = aux[k];
       if (lane == 0) {
         P.terminated[e] = term_c ? 1 : 0;

@@ -24,6 +24,7 @@ struct AnmConstHeader {
   int32_t n_action, n_state, n_obs, n_next_vars, n_full;
   int32_t table_len, y_nnz, n_jac; /* n_jac: Y entries with row, col >= 1 */
   int32_t need_angles;  /* some state/obs entry is an angle */
+  int32_t need_mask;    /* ANM_NEED_* (anm_kernels.cuh): derived quantities some state/obs entry reads */
   int32_t blob_bytes;
   int32_t ws_doubles;   /* per-env workspace size (doubles) */
   double base_mva, delta_t, lamb, gamma, clip_e, clip_pen, term_reward;

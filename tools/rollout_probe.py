@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from gym_anm_b200.anm6 import BatchedANM6Easy  # noqa: E402
 
-for B, T in ((4096, 200), (4096, 1000), (256, 200), (16384, 200)):
+for B, T in ((4096, 200), (256, 200), (16384, 100)):
     env = BatchedANM6Easy(B, validate_actions=False)
     nb = env.native
     env.reset(seed=3)
