@@ -253,6 +253,13 @@ __device__ __forceinline__ unsigned g_umax(unsigned key, unsigned gm, int grp_in
   return res;
 }
 
+/* Rarely executed library calls stay out of line: the per-step instruction stream has to fit the instruction caches
+ * (32 KB L1.5 per SM), and these expand to hundreds of instructions each. */
+__device__ __noinline__ double atan2_cold(double y, double x) { return atan2(y, x); }
+__device__ __noinline__ double fmod_cold(double v, double len) { return fmod(v, len); }
+__device__ __noinline__ void sincos_cold(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+__device__ __noinline__ double div_cold(double a, double b) { return a / b; }
+
 /* |x + jy| as sqrt(x^2 + y^2): within 1 ulp of hypot (numpy's abs of a complex) for the per-unit magnitudes of a power
  * flow, a fraction of its instructions; inf / NaN propagate (an overflowing square gives +inf like the true magnitude
  * of a diverged iterate would for all purposes here: the step is then terminal and its outputs are constants). */
@@ -277,7 +284,7 @@ __device__ __forceinline__ double pow2_inv_scale(double v) {
  * [-pi/4, pi/4].  |x| >= 2^50, inf and NaN fall back to libdevice. */
 __device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
   if (!(fabs(x) < 1.125899906842624e15)) { /* 2^50; also catches NaN / inf */
-    sincos(x, sn, cs);
+    sincos_cold(x, sn, cs);
     return;
   }
   const double k = rint(x * 0.6366197723675814);
@@ -317,7 +324,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
  * v - floor(v / len) * len is exact and a dozen instructions; anything else takes fmod. */
 __device__ __forceinline__ int next_slot(double v, double len) {
   if (v >= 0.0 && v < 4503599627370496.0 && v == floor(v)) return (int)fma(-floor(v / len), len, v);
-  return (int)fmod(v, len);
+  return (int)fmod_cold(v, len);
 }
 
 struct Cst {  // resolved pointers into the staged blob
@@ -365,11 +372,13 @@ struct Cst {  // resolved pointers into the staged blob
  * not tested against themselves. */
 template <int LPE, bool FULL>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
-                                                const double* __restrict__ rh, const double4* __restrict__ coef,
-                                                const int* __restrict__ info, int ncand, double p, double q, int lane,
-                                                unsigned gm, double& po, double& qo) {
+                                                const double* __restrict__ rh, const double* __restrict__ rhe,
+                                                const double4* __restrict__ coef, const int* __restrict__ info,
+                                                int ncand, double p, double q, int lane, unsigned gm, double& po,
+                                                double& qo) {
   constexpr int R = ANM_MAX_ROWS; /* generators: rows 7..9 carry h = +inf (never active) */
-  double a[R], b[R], h[R];
+  constexpr int U = 2;            /* candidates per lane and trip: two independent dependency chains */
+  double a[R], b[R], nh[R];
   unsigned fin = 0u;
 #pragma unroll
   for (int k = 0; k < R; ++k) {
@@ -378,40 +387,58 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
     const double hk = rh[k];
     const bool f = fabs(hk) < CUDART_INF; /* false for NaN */
     fin |= f ? (1u << k) : 0u;
-    h[k] = f ? hk : CUDART_INF; /* a x + b y - inf > tol is never true: the row is skipped */
+    nh[k] = f ? -hk : -CUDART_INF; /* a x + b y - inf > tol is never true: the row is skipped */
   }
   double best = CUDART_INF, bx = CUDART_NAN, by = CUDART_NAN;
-  int bidx = 1 << 20;
-  /* a compact loop on purpose (the body stays in the instruction cache); every lane makes the same trips */
+  /* a compact loop on purpose (the body stays in the instruction cache); every lane makes the same trips.
+   * Written stage by stage over independent values so that the FMA pipe is kept full. */
 #pragma unroll 1
-  for (int c0 = 0; c0 < ncand; c0 += LPE) {
-    const int c = c0 + lane;
-    const bool in = c < ncand;
-    const int cc = in ? c : 0;
-    const int nf = info[cc];
-    const int s1 = nf & 0xff, s2 = (nf >> 8) & 0xff;
-    const unsigned need = (unsigned)nf >> 16;
-    const double h1 = ((fin >> s1) & 1u) ? rh[s1] : 0.0, h2 = ((fin >> s2) & 1u) ? rh[s2] : 0.0;
-    const double4 kx = coef[2 * cc], ky = coef[2 * cc + 1];
-    const double x = fma(kx.x, p, fma(kx.y, q, fma(kx.z, h1, kx.w * h2)));
-    const double y = fma(ky.x, p, fma(ky.y, q, fma(ky.z, h1, ky.w * h2)));
-    /* branch-free: the R residuals are independent; viol collects the rows that the candidate breaks */
-    unsigned viol = 0u;
+  for (int c0 = 0; c0 < ncand; c0 += U * LPE) {
+    bool in[U];
+    unsigned need[U];
+    double x[U], y[U];
 #pragma unroll
-    for (int k = 0; k < R; ++k) viol |= (fma(a[k], x, fma(b[k], y, -h[k])) > ANM_FEAS_TOL) ? (1u << k) : 0u;
-    const double dx = x - p, dy = y - q;
-    const double d = fma(dx, dx, dy * dy);
-    const bool take = in & ((fin & need) == need) & ((viol & ~need) == 0u) & (d < best);
-    best = take ? d : best;
-    bx = take ? x : bx;
-    by = take ? y : by;
-    bidx = take ? c : bidx;
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * LPE + lane;
+      in[u] = c < ncand;
+      const int cc = in[u] ? c : 0;
+      const int nf = info[cc];
+      const double4 kx = coef[2 * cc], ky = coef[2 * cc + 1];
+      need[u] = (unsigned)nf >> 16;
+      /* rhe: the right-hand sides with the non-finite ones replaced by 0 (they are never used: `need`) */
+      const double h1 = rhe[nf & 0xff], h2 = rhe[(nf >> 8) & 0xff];
+      x[u] = fma(kx.x, p, fma(kx.y, q, fma(kx.z, h1, kx.w * h2)));
+      y[u] = fma(ky.x, p, fma(ky.y, q, fma(ky.z, h1, ky.w * h2)));
+    }
+    double r[U][R];
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u][k] = fma(b[k], y[u], nh[k]);
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u][k] = fma(a[k], x[u], r[u][k]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned viol = 0u; /* the rows that the candidate breaks */
+#pragma unroll
+      for (int k = 0; k < R; ++k) viol |= (r[u][k] > ANM_FEAS_TOL) ? (1u << k) : 0u;
+      const double dx = x[u] - p, dy = y[u] - q;
+      const double d = fma(dx, dx, dy * dy);
+      const bool take = in[u] & ((fin & need[u]) == need[u]) & ((viol & ~need[u]) == 0u) & (d < best);
+      best = take ? d : best;
+      bx = take ? x[u] : bx;
+      by = take ? y[u] : by;
+    }
   }
-  /* arg-min over the group (ties -> lowest candidate index, like a serial scan) */
-  double key = best;
-  int who = (bidx << 5) | (lane & 31);
-  g_argopt<LPE, FULL, false>(key, who, gm);
-  const int src = who & 31; /* lane index inside the group */
+  /* closest candidate of the group: min over the lanes, then the lowest lane that holds it (equal distances
+   * are the same point up to rounding) */
+  double mn = best;
+#pragma unroll
+  for (int o = LPE / 2; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(mk<FULL>(gm), mn, o));
+  const unsigned eq = __ballot_sync(mk<FULL>(gm), best == mn) & gm;
+  const int src = (__ffs(eq) - 1) & (LPE - 1); /* lane index inside the group */
   po = __shfl_sync(mk<FULL>(gm), bx, src, LPE);
   qo = __shfl_sync(mk<FULL>(gm), by, src, LPE);
 }
@@ -1021,12 +1048,12 @@ struct RadialNR {
       const double cr = ypbr * vr - ypbi * vi, ci = ypbr * vi + ypbi * vr;     /* Y_pb V_b, for the parent */
       ir = tbr + tpr;
       ii = tbi + tpi;
-#pragma unroll
-      for (int s = 0; s < ANM_RAD_MAXC; ++s) {
-        if (s >= maxc) break; /* warp-uniform */
+#pragma unroll 1
+      for (int s = 0; s < maxc; ++s) {
         const int cb = (int)((cpack >> (8 * s)) & 0xffu), src = (cb == 0xff) ? lane : cb;
         const double gr = __shfl_sync(ANM_FULL, cr, src, LPE), gi = __shfl_sync(ANM_FULL, ci, src, LPE);
-        if (cb != 0xff) { ir += gr; ii += gi; }
+        ir += (cb != 0xff) ? gr : 0.0;
+        ii += (cb != 0xff) ? gi : 0.0;
       }
       /* mismatch rows (:84-120): S_b = V_b conj(I_b) */
       const double f0 = (vr * ir + vi * ii) - pb, f1 = (vi * ir - vr * ii) - qb;
@@ -1076,14 +1103,13 @@ struct RadialNR {
       }
       double r0 = f0, r1 = f1;
       double rdet = 0.0;
-      /* leaves -> root: bus b (depth lev) folds U D^-1 [L | f] into its parent */
-#pragma unroll
-      for (int lev = NB - 1; lev >= 2; --lev) {
-        if (lev > maxd) continue; /* warp-uniform */
+      /* leaves -> root: bus b (depth lev) folds U D^-1 [L | f] into its parent.  Rolled loops and selects instead
+       * of branches: the body is shared by all levels / child slots and stays in the instruction cache. */
+#pragma unroll 1
+      for (int lev = maxd; lev >= 2; --lev) {
         const double det = d00 * d11 - d01 * d10;
         const double rd = fast_rcp(det);
-        const bool mine = (depth == lev);
-        if (mine) rdet = rd;
+        rdet = (depth == lev) ? rd : rdet;
         /* T = adj(D) [L | f],  C = U T / det */
         const double t00 = d11 * l00 - d01 * l10, t01 = d11 * l01 - d01 * l11;
         const double t10 = d00 * l10 - d10 * l00, t11 = d00 * l11 - d10 * l01;
@@ -1092,39 +1118,35 @@ struct RadialNR {
         const double c10 = (u10 * t00 + u11 * t10) * rd, c11 = (u10 * t01 + u11 * t11) * rd;
         const double cf0 = (u00 * tf0 + u01 * tf1) * rd, cf1 = (u10 * tf0 + u11 * tf1) * rd;
         const bool gather = active && (depth + 1 == lev);
-#pragma unroll
-        for (int s = 0; s < ANM_RAD_MAXC; ++s) {
-          if (s >= maxc) break; /* warp-uniform */
+#pragma unroll 1
+        for (int s = 0; s < maxc; ++s) {
           const int cb = (int)((cpack >> (8 * s)) & 0xffu), src = (cb == 0xff) ? lane : cb;
           const double g00 = __shfl_sync(ANM_FULL, c00, src, LPE), g01 = __shfl_sync(ANM_FULL, c01, src, LPE);
           const double g10 = __shfl_sync(ANM_FULL, c10, src, LPE), g11 = __shfl_sync(ANM_FULL, c11, src, LPE);
           const double gf0 = __shfl_sync(ANM_FULL, cf0, src, LPE), gf1 = __shfl_sync(ANM_FULL, cf1, src, LPE);
-          if (gather && cb != 0xff) {
-            d00 -= g00; d01 -= g01; d10 -= g10; d11 -= g11;
-            r0 -= gf0; r1 -= gf1;
-          }
+          const bool take = gather && cb != 0xff;
+          d00 -= take ? g00 : 0.0; d01 -= take ? g01 : 0.0; d10 -= take ? g10 : 0.0; d11 -= take ? g11 : 0.0;
+          r0 -= take ? gf0 : 0.0; r1 -= take ? gf1 : 0.0;
         }
       }
       /* root level (children of the slack): plain 2x2 solves */
       double x0 = 0.0, x1 = 0.0;
       {
         const double det = d00 * d11 - d01 * d10;
-        if (depth == 1) {
-          rdet = fast_rcp(det);
-          x0 = (d11 * r0 - d01 * r1) * rdet;
-          x1 = (d00 * r1 - d10 * r0) * rdet;
-        }
+        const double rr = fast_rcp(det);
+        const bool root = (depth == 1);
+        rdet = root ? rr : rdet;
+        x0 = root ? (d11 * r0 - d01 * r1) * rr : 0.0;
+        x1 = root ? (d00 * r1 - d10 * r0) * rr : 0.0;
       }
       /* root -> leaves: x_b = D^-1 (f - L x_p) */
-#pragma unroll
-      for (int lev = 2; lev <= NB - 1; ++lev) {
-        if (lev > maxd) break; /* warp-uniform */
+#pragma unroll 1
+      for (int lev = 2; lev <= maxd; ++lev) {
         const double xp0 = __shfl_sync(ANM_FULL, x0, psrc, LPE), xp1 = __shfl_sync(ANM_FULL, x1, psrc, LPE);
-        if (depth == lev) {
-          const double q0 = r0 - (l00 * xp0 + l01 * xp1), q1 = r1 - (l10 * xp0 + l11 * xp1);
-          x0 = (d11 * q0 - d01 * q1) * rdet;
-          x1 = (d00 * q1 - d10 * q0) * rdet;
-        }
+        const double q0 = r0 - (l00 * xp0 + l01 * xp1), q1 = r1 - (l10 * xp0 + l11 * xp1);
+        const bool mine = (depth == lev);
+        x0 = mine ? (d11 * q0 - d01 * q1) * rdet : x0;
+        x1 = mine ? (d00 * q1 - d10 * q0) * rdet : x1;
       }
       if (active && !done) { /* x <- x - J^{-1} F (:220) */
         th -= x0;
@@ -1159,6 +1181,22 @@ struct RadialNR {
   }
 };
 
+/* The step-independent right-hand sides of every polygon row (raw, and with the non-finite ones replaced by 0 for
+ * the candidate evaluation): once per pass, before the first transition. */
+template <int LPE>
+__device__ __forceinline__ void init_polygon_rows(const Cst& C, double* __restrict__ ws, int lane) {
+  const AnmConstHeader& H = *C.H;
+  double* rowh = ws + H.w_rowh;
+  double* rowhe = rowh + H.n_ctrl * ANM_MAX_ROWS;
+#pragma unroll 1
+  for (int i = lane; i < H.n_ctrl * ANM_MAX_ROWS; i += LPE) {
+    const int c = i / ANM_MAX_ROWS, r = i - c * ANM_MAX_ROWS;
+    const double h = C.ctrl_rows[c * 3 * ANM_MAX_ROWS + 2 * ANM_MAX_ROWS + r];
+    rowh[i] = h;
+    rowhe[i] = (fabs(h) < CUDART_INF) ? h : 0.0;
+  }
+}
+
 /* ---- one Simulator.transition for one environment ----------------------------------------
  * Inputs in the workspace: in_pl, in_pp, in_ps, in_qs (MW / MVAr), soc (p.u.).
  * Leaves dev_p/q, ppot, bus_p/q, V, I, branch quantities in the workspace.  Returns `stable`
@@ -1184,8 +1222,11 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   double* devq = ws + H.w_devq; double* ppot = ws + H.w_ppot; double* busp = ws + H.w_busp;
   double* busq = ws + H.w_busq; double* vre = ws + H.w_vre; double* vim = ws + H.w_vim;
   double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* rowh = ws + H.w_rowh;
+  double* rowhe = rowh + H.n_ctrl * ANM_MAX_ROWS;
 
-  /* 1. loads, p_pot, slack (devices.py:156-167, simulator.py:511, 521-523) */
+  /* 1. loads, p_pot, slack (devices.py:156-167, simulator.py:511, 521-523) and the polygon rows that depend on
+   *    this step: p <= p_pot for a generator, the two SoC rows of a storage unit.  The other right-hand sides were
+   *    written once per launch (init_polygon_rows). */
 #pragma unroll 1
   for (int d = lane; d < D; d += LPE) {
     const int t = C.dev_type[d], slot = C.dev_slot[d];
@@ -1197,28 +1238,23 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
       devq[d] = pv * P[ANM_DP_QP_RATIO];
     } else if (t == ANM_DEV_GEN || t == ANM_DEV_RENEWABLE) {
       pp = clipd(in_pp[slot] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]);
+      const int i = slot * ANM_MAX_ROWS + 2; /* p <= p_pot, devices.py:296 */
+      rowh[i] = pp;
+      rowhe[i] = (fabs(pp) < CUDART_INF) ? pp : 0.0;
+    } else if (t == ANM_DEV_STORAGE) {
+      const double sc = soc[slot], eff = P[ANM_DP_EFF];
+      const double h8 = -(sc - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
+      const double h9 = eff * (sc - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
+      const int i = (H.n_gen + slot) * ANM_MAX_ROWS + 8;
+      rowh[i] = h8;
+      rowh[i + 1] = h9;
+      rowhe[i] = (fabs(h8) < CUDART_INF) ? h8 : 0.0;
+      rowhe[i + 1] = (fabs(h9) < CUDART_INF) ? h9 : 0.0;
     } else if (t == ANM_DEV_SLACK) {
       devp[d] = 0.0;
       devq[d] = 0.0;
     }
     ppot[d] = pp;
-  }
-  /* right-hand sides of every polygon row of every controllable device (no barrier needed before: the rows that
-   * depend on this step are recomputed from the inputs) */
-#pragma unroll 1
-  for (int i = lane; i < H.n_ctrl * ANM_MAX_ROWS; i += LPE) {
-    const int c = i / ANM_MAX_ROWS, r = i - c * ANM_MAX_ROWS;
-    const int d = C.ctrl_dev[c];
-    const double* P = C.dev_param + d * ANM_DEV_NPARAM;
-    double h = C.ctrl_rows[c * 3 * ANM_MAX_ROWS + 2 * ANM_MAX_ROWS + r];
-    if (c < H.n_gen) {
-      if (r == 2) h = clipd(in_pp[c] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]); /* p <= p_pot, devices.py:296 */
-    } else {
-      const double sc = soc[c - H.n_gen], eff = P[ANM_DP_EFF];
-      if (r == 8) h = -(sc - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
-      if (r == 9) h = eff * (sc - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
-    }
-    rowh[i] = h;
   }
   gsync<FULL>(gm);
   ANM_STAMP(0);
@@ -1231,8 +1267,8 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const bool is_des = (c >= H.n_gen);
     const int c0 = C.cand_ptr[c], nc = C.cand_ptr[c + 1] - c0;
     double po, qo;
-    project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, C.cand_coef + 2 * c0,
-                               C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
+    project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, rowhe + c * ANM_MAX_ROWS,
+                               C.cand_coef + 2 * c0, C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
     if (lane == 0) {
       devp[d] = po;
       devq[d] = qo;
@@ -1362,9 +1398,9 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
     full[b] = busp[b];
     full[N + b] = busq[b];
     full[2 * N + b] = (need & ANM_NEED_BUS_V) ? cabs2(vre[b], vim[b]) : 0.0;
-    full[3 * N + b] = angles ? atan2(vim[b], vre[b]) : 0.0;
+    full[3 * N + b] = angles ? atan2_cold(vim[b], vre[b]) : 0.0;
     full[4 * N + b] = (need & ANM_NEED_BUS_I) ? cabs2(ire[b], iim[b]) : 0.0;
-    full[5 * N + b] = angles ? atan2(iim[b], ire[b]) : 0.0;
+    full[5 * N + b] = angles ? atan2_cold(iim[b], ire[b]) : 0.0;
   }
   double* fd = full + 6 * N;
 #pragma unroll 1
@@ -1387,7 +1423,7 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
       im = (a == 0.0) ? 0.0 : (brire[l] / a) * a; /* simulator.py:613, NumPy>=2 sign(z) */
     }
     fb[3 * L + l] = im;
-    fb[4 * L + l] = angles ? atan2(briim[l], brire[l]) : 0.0;
+    fb[4 * L + l] = angles ? atan2_cold(briim[l], brire[l]) : 0.0;
   }
   double* fa = fb + 5 * L;
 #pragma unroll 1
@@ -1448,6 +1484,7 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 #pragma unroll 1
       for (int k = lane; k < K; k += LPE) aux[k] = __ldcg(P.aux + e * K + k);
     }
+    init_polygon_rows<LPE>(C, ws, lane);
     gsync<FULL>(gm);
 
     for (int t = 0; t < T; ++t) {
@@ -1602,14 +1639,14 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 #pragma unroll 1
         for (int k = lane; k < O; k += LPE) {
           double v = full[C.ov_off[k]] * C.ov_mul[k];
-          if (C.ov_div[k] != 1.0) v /= C.ov_div[k];
+          if (C.ov_div[k] != 1.0) v = div_cold(v, C.ov_div[k]);
           P.obs[row * O + k] = clipd(v, C.ov_low[k], C.ov_high[k]);
         }
         if (P.state) {
 #pragma unroll 1
           for (int k = lane; k < S; k += LPE) {
             double v = full[C.sv_off[k]] * C.sv_mul[k];
-            if (C.sv_div[k] != 1.0) v /= C.sv_div[k];
+            if (C.sv_div[k] != 1.0) v = div_cold(v, C.sv_div[k]);
             P.state[row * S + k] = v;
           }
         }
