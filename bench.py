@@ -5,24 +5,25 @@
 
 Workload (BASELINE.json configs[1]): ANM6Easy-v0, B = 4096 environment instances PER GPU
 (weak scaling), uniform-random actions over the action box, fp64 Newton-Raphson.  A "step"
-is one pass of the hot path over the whole batch = one kernel launch advancing every
-instance by one timestep.  Terminated instances are re-initialised by the kernel's
-next-step auto-reset from a pool of initial states that are known to converge, so every
-instance does one full transition per step.
+is one pass of the hot path over the whole batch: every instance advances by one timestep.
+Terminated instances are re-initialised by the kernel's next-step auto-reset from a pool of
+initial states that are known to converge, so every instance does one full transition per step.
 
-* `value`      : K steps replayed from a CUDA graph, actions already resident in HBM
-                 (a 1000-slot x B x 6 fp64 ring, 197 MB > the 126 MB L2), timed with CUDA
-                 events, max over ranks.  The random agent is open-loop, so the steps are enqueued
-                 CHAINED (ANM_STEP_CHAINED, include/anm_b200.h): launch t+1 is ordered against
-                 launch t per environment instance, and the ~1 % of instances whose Newton iteration
-                 diverges (100 iterations) finish step t while the others are already in step t+1.
-                 `lockstep` reports the same loop with every launch fully ordered after the previous
-                 one (what a closed-loop policy sees).
-* `e2e`        : the same metric through the C-ABI host calls `anm_step_host_async` + `anm_host_sync`
-                 -- pinned HOST action buffer in, HOST obs / reward / terminated out, every step,
-                 H2D + D2H inside the timed region (zero-copy: the kernel reads / writes the pinned
-                 buffers over PCIe); a ring of Q output buffers, one host sync per Q steps.
-                 `e2e.sync_every_step` is the synchronous `anm_step_host` (Q = 1).
+* `value`      : K steps as open-loop rollouts: the random agent does not look at the observations, so
+                 its action sequence (a 1000-slot x B x 6 fp64 ring resident in HBM, 197 MB > the 126 MB
+                 L2) is handed to `anm_rollout` 1000 steps at a time.  One kernel launch takes every
+                 instance through its 1000 steps -- carried state on chip, every step's obs / reward /
+                 terminated row written to HBM ([T, B, .] outputs) -- so an instance whose Newton iteration
+                 diverges (100 iterations) only delays the three instances that share its warp.  Timed
+                 with CUDA events, max over ranks.
+                 `per_step_launches` reports the same workload as ONE kernel launch per step (CUDA graph):
+                 `chained` (launches ordered per instance, ANM_STEP_CHAINED) and `lockstep` (every launch
+                 fully ordered after the previous one -- what a closed-loop policy sees).
+* `e2e`        : the same metric through the C-ABI host calls `anm_rollout_host_async` + `anm_host_sync`
+                 -- pinned HOST action arrays in, HOST obs / reward / terminated arrays out, for every
+                 step, H2D + D2H inside the timed region (zero-copy: the kernel reads / writes the pinned
+                 buffers over PCIe); 100 steps per call, two calls in flight.
+                 `e2e.sync_every_step` is the synchronous one-step `anm_step_host`.
 * `roofline`   : algorithmic bytes (234 B / env-step) x B / mean kernel time
                  against the measured HBM copy bandwidth (MEASURED_PEAKS.json).  The path is NOT
                  HBM-bound (arithmetic intensity ~30 fp64 FLOP/B); the fraction is reported
@@ -270,7 +271,43 @@ def run_ours(args):
         nb.step(ring[t % RING], None, out=(obs, rew, term))
     torch.cuda.synchronize()
 
-    # ---- value: K steps replayed from a CUDA graph ------------------------------------------------------
+    # ---- value: K steps as open-loop rollouts (anm_rollout: T steps per kernel launch) ---------------------------
+    # The random agent is open-loop, so the whole action sequence is handed over at once: one launch takes every
+    # instance through T = RING consecutive steps (carried state on chip) and writes every step's obs / reward /
+    # terminated row; consecutive launches are chained per instance (ANM_STEP_CHAINED).
+    T = min(K, RING)
+    n_roll, rem = divmod(K, T)
+    obs_r, rew_r, term_r = nb.empty(T, B, 18), nb.empty(T, B), nb.empty(T, B, dtype=torch.uint8)
+    nb.rollout(ring[:T], out=(obs_r, rew_r, term_r))  # untimed: instruction cache, allocator
+    torch.cuda.synchronize()
+
+    def timed(fn):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_host0 = time.perf_counter()
+        ev0.record()
+        fn()
+        ev1.record()
+        barrier()
+        t_host1 = time.perf_counter()
+        sampler.mark(t_host0, t_host1)
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def run_rollouts():
+        for i in range(n_roll):
+            nb.rollout(ring[:T], out=(obs_r, rew_r, term_r), chained=(i > 0))
+        if rem:
+            nb.rollout(ring[:rem], out=(obs_r[:rem], rew_r[:rem], term_r[:rem]), chained=True)
+
+    launches0 = nb.launch_count
+    ms_total = timed(run_rollouts)
+    gpu_launches = nb.launch_count - launches0
+    frac_reset = float((term_r[-1] != 0).double().mean())
+
+    # ---- the same K' steps as one kernel launch per step, replayed from a CUDA graph ----------------------------
     G = min(K, RING)
     side = torch.cuda.Stream()
 
@@ -285,45 +322,27 @@ def run_ours(args):
         g.replay()  # untimed replay: graph upload + instruction cache
         return g
 
-    def timed_replays(g, n_rep, rem, chained):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        t_host0 = time.perf_counter()
-        ev0.record()
-        for _ in range(n_rep):
-            g.replay()
-        for t in range(rem):
-            nb.step(ring[t], None, out=(obs, rew, term), chained=chained)
-        ev1.record()
-        barrier()
-        t_host1 = time.perf_counter()
-        sampler.mark(t_host0, t_host1)
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
+    n_g = max(1, min(K // G, 4))
+    per_step = {}
+    for name, chained in (("chained", True), ("lockstep", False)):
+        g = capture(chained)
+        ms_g = timed(lambda: [g.replay() for _ in range(n_g)])
+        per_step[name] = {"value": world * B * n_g * G / (ms_g / 1000.0), "unit": "env-steps/s",
+                          "ms_per_step": ms_g / (n_g * G), "steps": n_g * G}
+        del g
+    per_step["chained"]["what"] = ("one kernel launch per step (CUDA graph), launches ordered per instance "
+                                   "(programmatic dependent launch + per-instance sequence numbers)")
+    per_step["lockstep"]["what"] = ("one kernel launch per step (CUDA graph), every launch fully ordered after the "
+                                    "previous one: the rate a closed-loop policy on the same stream can reach")
 
-    graph = capture(True)
-    n_rep, rem = divmod(K, G)
-    launches0 = nb.launch_count
-    ms_total = timed_replays(graph, n_rep, rem, True)
-    gpu_launches = n_rep * G + (nb.launch_count - launches0)
-    frac_reset = float((term != 0).double().mean())
-    # the same loop with every launch fully ordered after the previous one (closed-loop view)
-    graph_ls = capture(False)
-    n_ls = max(1, min(n_rep, 4))
-    ms_lockstep = timed_replays(graph_ls, n_ls, 0, False)
-    lockstep_rate = world * B * n_ls * G / (ms_lockstep / 1000.0)
-    del graph_ls
-
-    # ---- e2e: host buffers through the C ABI's host calls (H2D + kernel + D2H every step) ---------------
+    # ---- e2e: host buffers through the C ABI's host calls (H2D + kernel + D2H for every step) -------------------
     hs = nb.host_stream
-    Q = 16  # queued steps between two host synchronisations (each has its own pinned output buffers)
-    obs_q = torch.empty(Q, B, 18, dtype=torch.float64).pin_memory()
-    rew_q = torch.empty(Q, B, dtype=torch.float64).pin_memory()
-    term_q = torch.empty(Q, B, dtype=torch.uint8).pin_memory()
+    Te = 100  # steps per queued rollout call; two sets of pinned output buffers, one host sync per call
+    obs_q = torch.empty(2, Te, B, 18, dtype=torch.float64).pin_memory()
+    rew_q = torch.empty(2, Te, B, dtype=torch.float64).pin_memory()
+    term_q = torch.empty(2, Te, B, dtype=torch.uint8).pin_memory()
     act_ptr = [ring_host[t].data_ptr() for t in range(RING)]
-    out_ptr = [(obs_q[q].data_ptr(), rew_q[q].data_ptr(), term_q[q].data_ptr()) for q in range(Q)]
+    out_ptr = [(obs_q[q].data_ptr(), rew_q[q].data_ptr(), term_q[q].data_ptr()) for q in range(2)]
 
     def e2e_loop(n, queued):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,10 +350,10 @@ def run_ours(args):
         t_host0 = time.perf_counter()
         e0.record(hs)
         if queued:
-            for t in range(n):
-                o, r, d = out_ptr[t % Q]
-                nb.step_host_async(act_ptr[t % RING], None, o, r, d)
-                if t % Q == Q - 1:
+            for i in range(n // Te):
+                o, r, d = out_ptr[i % 2]
+                nb.rollout_host_async(Te, act_ptr[(i * Te) % (RING - Te + 1)], None, o, r, d)
+                if i % 2 == 1:  # two calls in flight, then the host waits (and would consume both buffer sets)
                     nb.host_sync()
             nb.host_sync()
         else:
@@ -349,8 +368,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return world * B * n / (float(ms) / 1000.0)
 
-    Ke = max(Q, min(K, 8000) // Q * Q)
-    e2e_loop(3 * Q, True)
+    Ke = max(2 * Te, min(K, 8000) // (2 * Te) * (2 * Te))
+    e2e_loop(2 * Te, True)
     e2e_rate = e2e_loop(Ke, True)
     checksum = float(obs_q.sum()) + float(rew_q.sum())
     e2e_loop(3, False)
@@ -370,7 +389,7 @@ def run_ours(args):
         barrier()
         g0.record()
         for t in range(Kg):
-            nb.step(ring[t % RING], None, out=(obs, rew, term), chained=True)
+            nb.step(ring[t % RING], None, out=(obs, rew, term))
             packed[:, :18] = obs
             packed[:, 18] = rew
             packed[:, 19] = term
@@ -409,8 +428,8 @@ def run_ours(args):
         "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src,
         "algorithmic_bytes_per_env_step": B_MIN_BYTES, "env_steps_per_launch": B,
         "kernel_us_mean": kernel_s * 1e6,
-        "kernel_time": "timed region / launches (consecutive launches overlap; an isolated launch takes longer, "
-                       "see lockstep.ms_per_step)",
+        "kernel_time": "timed region / steps (a launch covers many steps; a single-step launch: "
+                       "per_step_launches.lockstep.ms_per_step)",
         "note": "compute/latency-bound path (fp64 FMA pipe + shuffle/LDS latency), not HBM-bound; see fp64 fields",
         "fp64_pipe_pct_ncu": ncu.get("fp64_pipe_pct"), "issue_slot_pct_ncu": ncu.get("issue_active_pct"),
         "ncu_profile": ncu.get("source"),
@@ -447,20 +466,18 @@ def run_ours(args):
             "envs_per_gpu": B, "global_envs": world * B, "parallelism": "dp%d (independent env shards)" % world,
             "autoreset": "next-step, from a pool of %d convergent initial states" % pool.shape[0],
             "l2": "inputs cycle through a %d-slot action ring of %.0f MB (> 126 MB L2)" % (RING, ring.numel() * 8 / 1e6),
-            "launch": "CUDA graph of %d step kernels replayed %d times (+%d eager); one kernel launch per step, "
-                      "launches chained per instance (programmatic dependent launch + per-instance sequence "
-                      "numbers): the tail of step t overlaps step t+1" % (G, n_rep, rem),
+            "launch": "anm_rollout: %d launches x %d steps (+%d); each instance runs its steps back to back with its "
+                      "carried state on chip and writes every step's obs / reward / terminated row to HBM; launches "
+                      "chained per instance" % (n_roll, T, rem),
             "lanes_per_env": nb.sizes["lanes_per_env"], "smem_bytes_per_cta": nb.sizes["smem_bytes"],
             "frac_envs_reset_last_step": frac_reset,
         },
         "clocks": clocks,
-        "lockstep": {"value": lockstep_rate, "unit": "env-steps/s", "ms_per_step": ms_lockstep / (n_ls * G),
-                     "steps": n_ls * G, "what": "same graph loop, every launch fully ordered after the previous one "
-                     "(no cross-launch overlap): the rate a closed-loop policy on the same stream can reach"},
+        "per_step_launches": per_step,
         "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 6 * 8,
-                "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "queue_depth": Q,
-                "api": "anm_step_host_async x %d + anm_host_sync (C ABI; pinned host buffers, read / written by the "
-                       "kernel over PCIe = zero-copy; ANM_HOST_IO=copy stages through cudaMemcpyAsync instead)" % Q,
+                "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "steps_per_call": Te,
+                "api": "anm_rollout_host_async (%d steps per call) + anm_host_sync every second call (C ABI; pinned host "
+                       "buffers read / written by the kernel over PCIe = zero-copy)" % Te,
                 "sync_every_step": {"value": e2e_sync_rate, "unit": "env-steps/s", "steps": Ks,
                                     "api": "anm_step_host (synchronous)"},
                 "checksum": checksum},  # fmt: skip

@@ -489,10 +489,19 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
 #define ANM_HOST_IO_DEFAULT 2 /* zero-copy when the caller's buffers are pinned: +14 % e2e on B200 (profiles/) */
 #endif
 typedef void (*kernel_fn)(const AnmLaunch);
+/* ANM_LANES=16 (environment): 16 lanes per instance for the radial solver (two instances per warp instead of four:
+ * half the lock-step penalty of a divergent instance, half the projection trips, twice the issue slots). */
+static int radial_lanes() {
+  static const int v = [] {
+    const char* e = getenv("ANM_LANES");
+    return (e && atoi(e) == 16) ? 16 : 8;
+  }();
+  return v;
+}
 static int lanes_for(const AnmConstHeader& H) {
   const int M = H.n_unk;
   switch (solver_for(H)) {
-    case 2: return 8;
+    case 2: return (H.n_bus >= 9) ? 16 : radial_lanes(); /* the radial solver wants an idle lane: n_bus - 1 < lanes */
     case 1: return (H.n_bus <= 5) ? 8 : 16;
     case 4: return 32;
     default: return (M <= 8) ? 8 : (M <= 16 ? 16 : 32);
@@ -505,6 +514,18 @@ static int threads_for(const AnmConstHeader& H) {
 
 kernel_fn kernel_for(const AnmConstHeader& H) {
   const int solver = solver_for(H);
+  if (solver == 2 && lanes_for(H) == 16) {
+    switch (H.n_bus) {
+      case 2: return anm::anm_env_kernel<16, 2, 2>;
+      case 3: return anm::anm_env_kernel<16, 3, 2>;
+      case 4: return anm::anm_env_kernel<16, 4, 2>;
+      case 5: return anm::anm_env_kernel<16, 5, 2>;
+      case 6: return anm::anm_env_kernel<16, 6, 2>;
+      case 7: return anm::anm_env_kernel<16, 7, 2>;
+      case 8: return anm::anm_env_kernel<16, 8, 2>;
+      default: return anm::anm_env_kernel<16, 9, 2>;
+    }
+  }
   if (solver == 2) {
     switch (H.n_bus) {
       case 2: return anm::anm_env_kernel<8, 2, 2>;
@@ -513,8 +534,7 @@ kernel_fn kernel_for(const AnmConstHeader& H) {
       case 5: return anm::anm_env_kernel<8, 5, 2>;
       case 6: return anm::anm_env_kernel<8, 6, 2>;
       case 7: return anm::anm_env_kernel<8, 7, 2>;
-      case 8: return anm::anm_env_kernel<8, 8, 2>;
-      default: return anm::anm_env_kernel<8, 9, 2>;
+      default: return anm::anm_env_kernel<8, 8, 2>;
     }
   }
   if (solver == 1) {

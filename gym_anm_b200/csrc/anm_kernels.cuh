@@ -287,11 +287,13 @@ __device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
     sincos_cold(x, sn, cs);
     return;
   }
-  const double k = rint(x * 0.6366197723675814);
+  /* k = rint(x * 2/pi) by the 1.5 * 2^52 trick: the quadrant is in the low mantissa bits of the sum */
+  const double t = fma(x, 0.6366197723675814, 6755399441055744.0);
+  const int q = __double2loint(t) & 3;
+  const double k = t - 6755399441055744.0;
   double r = fma(-k, 1.5707963267948966, x);
   r = fma(-k, 6.123233995736766e-17, r);
   r = fma(-k, -1.4973849048591698e-33, r);
-  const int q = (int)(__double2ll_rn(k) & 3ll);
   const double z = r * r;
   double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
   ps = fma(z, ps, 2.75573137070700676789e-06);
@@ -374,9 +376,11 @@ template <int LPE, bool FULL>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
                                                 const double* __restrict__ rh, const double* __restrict__ rhe,
                                                 const double4* __restrict__ coef, const int* __restrict__ info,
-                                                int ncand, double p, double q, int lane, unsigned gm, double& po,
-                                                double& qo) {
-  constexpr int R = ANM_MAX_ROWS; /* generators: rows 7..9 carry h = +inf (never active) */
+                                                int ncand, int nrows, double p, double q, int lane, unsigned gm,
+                                                double& po, double& qo) {
+  constexpr int R = ANM_MAX_ROWS; /* storage units: 10 rows; generators: 7 (nrows; rows 7..9 are then skipped) */
+  constexpr int R0 = 7;
+  const bool more = nrows > R0; /* warp-uniform: every lane group works on the same device */
   constexpr int U = 2;            /* candidates per lane and trip: two independent dependency chains */
   double a[R], b[R], nh[R];
   unsigned fin = 0u;
@@ -411,22 +415,40 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
       y[u] = fma(ky.x, p, fma(ky.y, q, fma(ky.z, h1, ky.w * h2)));
     }
     double r[U][R];
+    unsigned viol[U]; /* the rows that the candidate breaks */
 #pragma unroll
-    for (int k = 0; k < R; ++k)
+    for (int k = 0; k < R0; ++k)
 #pragma unroll
       for (int u = 0; u < U; ++u) r[u][k] = fma(b[k], y[u], nh[k]);
 #pragma unroll
-    for (int k = 0; k < R; ++k)
+    for (int k = 0; k < R0; ++k)
 #pragma unroll
       for (int u = 0; u < U; ++u) r[u][k] = fma(a[k], x[u], r[u][k]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      unsigned viol = 0u; /* the rows that the candidate breaks */
+      viol[u] = 0u;
 #pragma unroll
-      for (int k = 0; k < R; ++k) viol |= (r[u][k] > ANM_FEAS_TOL) ? (1u << k) : 0u;
+      for (int k = 0; k < R0; ++k) viol[u] |= (r[u][k] > ANM_FEAS_TOL) ? (1u << k) : 0u;
+    }
+    if (more) {
+#pragma unroll
+      for (int k = R0; k < R; ++k)
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u][k] = fma(b[k], y[u], nh[k]);
+#pragma unroll
+      for (int k = R0; k < R; ++k)
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u][k] = fma(a[k], x[u], r[u][k]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = R0; k < R; ++k) viol[u] |= (r[u][k] > ANM_FEAS_TOL) ? (1u << k) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       const double dx = x[u] - p, dy = y[u] - q;
       const double d = fma(dx, dx, dy * dy);
-      const bool take = in[u] & ((fin & need[u]) == need[u]) & ((viol & ~need[u]) == 0u) & (d < best);
+      const bool take = in[u] & ((fin & need[u]) == need[u]) & ((viol[u] & ~need[u]) == 0u) & (d < best);
       best = take ? d : best;
       bx = take ? x[u] : bx;
       by = take ? y[u] : by;
@@ -999,7 +1021,7 @@ struct RadialNR {
 
   static __device__ __forceinline__ void run(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
                                              int& it_out, bool& converged_out, bool& stable_out, int& n_fb, int& n_big) {
-    static_assert(n <= LPE, "one bus per lane");
+    static_assert(n < LPE, "one bus per lane and at least one idle lane (the all-zero source of empty child slots)");
     const AnmConstHeader& H = *C.H;
     const double* busp = ws + H.w_busp; const double* busq = ws + H.w_busq;
     double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ire = ws + H.w_ire; double* iim = ws + H.w_iim;
@@ -1009,15 +1031,18 @@ struct RadialNR {
     const int pl = active ? C.rad_parent[bl] : -1; /* parent's lane, -1: the slack bus */
     const int depth = active ? C.rad_depth[bl] : 0;
     const int maxc = H.rad_maxc, maxd = H.rad_maxdepth;
-    /* children's lanes packed into one register (byte s = lane of child s, 0xff = none): no local-memory array */
-    unsigned cpack = 0xffffffffu;
-    if (active) {
-      cpack = 0u;
+    /* Source lane of every child slot.  An empty slot (and every slot of an idle lane) reads lane n, an idle lane
+     * whose admittances are zero and whose depth is 0: everything it offers is exactly 0, so the gathers below need
+     * no per-slot select. */
+    int csrc[ANM_RAD_MAXC];
 #pragma unroll
-      for (int s = 0; s < ANM_RAD_MAXC; ++s) cpack |= ((unsigned)C.rad_child[bl * ANM_RAD_MAXC + s] & 0xffu) << (8 * s);
+    for (int s = 0; s < ANM_RAD_MAXC; ++s) {
+      const int cb = active ? C.rad_child[bl * ANM_RAD_MAXC + s] : -1;
+      csrc[s] = (cb < 0) ? n : cb;
     }
     const double* yv = C.rad_y + 6 * bl;
-    const double ybbr = yv[0], ybbi = yv[1], ybpr = yv[2], ybpi = yv[3], ypbr = yv[4], ypbi = yv[5];
+    const double ybbr = active ? yv[0] : 0.0, ybbi = active ? yv[1] : 0.0, ybpr = active ? yv[2] : 0.0,
+                 ybpi = active ? yv[3] : 0.0, ypbr = active ? yv[4] : 0.0, ypbi = active ? yv[5] : 0.0;
     const double pb = busp[b], qb = busq[b];
     const int psrc = (pl < 0) ? lane : pl;
     double th = 0.0, vm = 1.0; /* flat start (solve_load_flow.py:42) */
@@ -1028,8 +1053,8 @@ struct RadialNR {
     const long long t_loop0 = clock64();
     long long t_done = 0;
 #endif
-    bool done = !live, bad = false, big = false;
-    double vr = 1.0, vi = 0.0, ir = 0.0, ii = 0.0;
+    bool done = !live, big = false;
+    double vr = 1.0, vi = 0.0, ir = 0.0, ii = 0.0, f0 = 0.0, f1 = 0.0;
     for (;;) {
       /* V_b = |V| e^{j theta}, E_b = V_b / |V_b| (:167-173, :150) */
       double sn, cs;
@@ -1048,24 +1073,26 @@ struct RadialNR {
       const double cr = ypbr * vr - ypbi * vi, ci = ypbr * vi + ypbi * vr;     /* Y_pb V_b, for the parent */
       ir = tbr + tpr;
       ii = tbi + tpi;
-#pragma unroll 1
-      for (int s = 0; s < maxc; ++s) {
-        const int cb = (int)((cpack >> (8 * s)) & 0xffu), src = (cb == 0xff) ? lane : cb;
-        const double gr = __shfl_sync(ANM_FULL, cr, src, LPE), gi = __shfl_sync(ANM_FULL, ci, src, LPE);
-        ir += (cb != 0xff) ? gr : 0.0;
-        ii += (cb != 0xff) ? gi : 0.0;
+#pragma unroll
+      for (int s = 0; s < ANM_RAD_MAXC; ++s) {
+        if (s < maxc) { /* warp-uniform */
+          ir += __shfl_sync(ANM_FULL, cr, csrc[s], LPE);
+          ii += __shfl_sync(ANM_FULL, ci, csrc[s], LPE);
+        }
       }
-      /* mismatch rows (:84-120): S_b = V_b conj(I_b) */
-      const double f0 = (vr * ir + vi * ii) - pb, f1 = (vi * ir - vr * ii) - qb;
-      const unsigned nanb = __ballot_sync(ANM_FULL, active && ((f0 != f0) || (f1 != f1)));
-      const unsigned bigb = __ballot_sync(ANM_FULL, active && (fabs(f0) > ANM_NR_TOL || fabs(f1) > ANM_NR_TOL));
+      /* mismatch rows (:84-120): S_b = V_b conj(I_b).  One vote per iteration: `notok` is set by an entry above the
+       * tolerance and by a NaN alike.  (The reference leaves its loop at the first NaN residual -- `nan > tol` is
+       * False, :218 -- where this loop runs on to the iteration cap; a NaN never goes away, so the verdict below is
+       * the same, and only n_iter of such a terminal step differs.) */
+      f0 = (vr * ir + vi * ii) - pb;
+      f1 = (vi * ir - vr * ii) - qb;
+      const unsigned notok = __ballot_sync(ANM_FULL, active && !(fabs(f0) <= ANM_NR_TOL && fabs(f1) <= ANM_NR_TOL));
       if (!done) {
-        bad = (nanb & gm) != 0u; /* numpy: norm(F, inf) is NaN, and `nan > tol` is False (:218) */
-        big = (bigb & gm) != 0u;
+        big = (notok & gm) != 0u;
 #if ANM_DIAG
-        if (bad || !big || it >= ANM_NR_MAXIT) done = true, t_done = clock64(); else ++it;
+        if (!big || it >= ANM_NR_MAXIT) done = true, t_done = clock64(); else ++it;
 #else
-        if (bad || !big || it >= ANM_NR_MAXIT) done = true; else ++it;
+        if (!big || it >= ANM_NR_MAXIT) done = true; else ++it;
 #endif
       }
       if (__all_sync(ANM_FULL, done)) break;
@@ -1109,24 +1136,25 @@ struct RadialNR {
       for (int lev = maxd; lev >= 2; --lev) {
         const double det = d00 * d11 - d01 * d10;
         const double rd = fast_rcp(det);
-        rdet = (depth == lev) ? rd : rdet;
+        const bool mine = (depth == lev);
+        rdet = mine ? rd : rdet;
+        const double rdm = mine ? rd : 0.0; /* only the buses of this level offer a non-zero contribution */
         /* T = adj(D) [L | f],  C = U T / det */
         const double t00 = d11 * l00 - d01 * l10, t01 = d11 * l01 - d01 * l11;
         const double t10 = d00 * l10 - d10 * l00, t11 = d00 * l11 - d10 * l01;
         const double tf0 = d11 * r0 - d01 * r1, tf1 = d00 * r1 - d10 * r0;
-        const double c00 = (u00 * t00 + u01 * t10) * rd, c01 = (u00 * t01 + u01 * t11) * rd;
-        const double c10 = (u10 * t00 + u11 * t10) * rd, c11 = (u10 * t01 + u11 * t11) * rd;
-        const double cf0 = (u00 * tf0 + u01 * tf1) * rd, cf1 = (u10 * tf0 + u11 * tf1) * rd;
-        const bool gather = active && (depth + 1 == lev);
-#pragma unroll 1
-        for (int s = 0; s < maxc; ++s) {
-          const int cb = (int)((cpack >> (8 * s)) & 0xffu), src = (cb == 0xff) ? lane : cb;
-          const double g00 = __shfl_sync(ANM_FULL, c00, src, LPE), g01 = __shfl_sync(ANM_FULL, c01, src, LPE);
-          const double g10 = __shfl_sync(ANM_FULL, c10, src, LPE), g11 = __shfl_sync(ANM_FULL, c11, src, LPE);
-          const double gf0 = __shfl_sync(ANM_FULL, cf0, src, LPE), gf1 = __shfl_sync(ANM_FULL, cf1, src, LPE);
-          const bool take = gather && cb != 0xff;
-          d00 -= take ? g00 : 0.0; d01 -= take ? g01 : 0.0; d10 -= take ? g10 : 0.0; d11 -= take ? g11 : 0.0;
-          r0 -= take ? gf0 : 0.0; r1 -= take ? gf1 : 0.0;
+        const double c00 = (u00 * t00 + u01 * t10) * rdm, c01 = (u00 * t01 + u01 * t11) * rdm;
+        const double c10 = (u10 * t00 + u11 * t10) * rdm, c11 = (u10 * t01 + u11 * t11) * rdm;
+        const double cf0 = (u00 * tf0 + u01 * tf1) * rdm, cf1 = (u10 * tf0 + u11 * tf1) * rdm;
+        /* a parent pulls from its children (non-zero exactly when they are at this level); an empty slot pulls
+         * zeros from the idle lane */
+#pragma unroll
+        for (int s = 0; s < ANM_RAD_MAXC; ++s) {
+          if (s < maxc) { /* warp-uniform */
+            d00 -= __shfl_sync(ANM_FULL, c00, csrc[s], LPE); d01 -= __shfl_sync(ANM_FULL, c01, csrc[s], LPE);
+            d10 -= __shfl_sync(ANM_FULL, c10, csrc[s], LPE); d11 -= __shfl_sync(ANM_FULL, c11, csrc[s], LPE);
+            r0 -= __shfl_sync(ANM_FULL, cf0, csrc[s], LPE);  r1 -= __shfl_sync(ANM_FULL, cf1, csrc[s], LPE);
+          }
         }
       }
       /* root level (children of the slack): plain 2x2 solves */
@@ -1172,9 +1200,10 @@ struct RadialNR {
       }
     }
     __syncwarp();
+    const bool bad = ((__ballot_sync(ANM_FULL, active && ((f0 != f0) || (f1 != f1))) & gm) != 0u);
     it_out = it;
-    converged_out = !bad;
-    stable_out = !bad && !big; /* solve_load_flow.py:49 */
+    converged_out = !bad;            /* numpy: norm(F, inf) is NaN <=> some entry is */
+    stable_out = !bad && !big;       /* solve_load_flow.py:49 */
 #if ANM_DIAG
     n_fb = (n_fb & 0xffff) | ((int)((t_done - t_loop0) >> 4) << 16);
 #endif
@@ -1268,7 +1297,8 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const int c0 = C.cand_ptr[c], nc = C.cand_ptr[c + 1] - c0;
     double po, qo;
     project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, rowhe + c * ANM_MAX_ROWS,
-                               C.cand_coef + 2 * c0, C.cand_info + c0, nc, in_ps[c] / m, in_qs[c] / m, lane, gm, po, qo);
+                               C.cand_coef + 2 * c0, C.cand_info + c0, nc, is_des ? 10 : 7, in_ps[c] / m, in_qs[c] / m, lane,
+                               gm, po, qo);
     if (lane == 0) {
       devp[d] = po;
       devq[d] = qo;

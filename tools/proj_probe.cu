@@ -39,7 +39,7 @@ __global__ void k(const double* ab, const double* h, const double* coef, const i
   double p = 0.45 + 0.01 * grp, q = -0.6, po = 0, qo = 0, acc = 0;
   long long t0 = clock64();
   for (int r = 0; r < reps; ++r) {
-    anm::project_polygon<8, true>(s_ab, s_ab + 10, s_h[grp], s_h[grp], reinterpret_cast<const double4*>(s_coef), s_info, ncand, p, q, lane, gm, po, qo);
+    anm::project_polygon<8, true>(s_ab, s_ab + 10, s_h[grp], s_h[grp], reinterpret_cast<const double4*>(s_coef), s_info, ncand, ncand > 30 ? 10 : 7, p, q, lane, gm, po, qo);
     p = po + 0.3; q = qo - 0.2; acc += po + qo;   // dependent calls
   }
   long long t1 = clock64();
