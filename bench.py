@@ -21,9 +21,9 @@ initial states that are known to converge, so every instance does one full trans
                  fully ordered after the previous one -- what a closed-loop policy sees).
 * `e2e`        : the same metric through the C-ABI host calls `anm_rollout_host_async` + `anm_host_sync`
                  -- pinned HOST action arrays in, HOST obs / reward / terminated arrays out, for every
-                 step, H2D + D2H inside the timed region (zero-copy: the kernel reads / writes the pinned
-                 buffers over PCIe); 100 steps per call, two calls in flight.
-                 `e2e.sync_every_step` is the synchronous one-step `anm_step_host`.
+                 step, H2D + D2H inside the timed region (copy engines, overlapped with the kernels);
+                 100 steps per call, the host waits for call i-1 after queueing call i.
+                 `e2e.sync_every_step` is the synchronous one-step `anm_step_host` (zero-copy).
 * `roofline`   : algorithmic bytes (234 B / env-step) x B / mean kernel time
                  against the measured HBM copy bandwidth (MEASURED_PEAKS.json).  The path is NOT
                  HBM-bound (arithmetic intensity ~30 fp64 FLOP/B); the fraction is reported
@@ -337,7 +337,8 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the C ABI's host calls (H2D + kernel + D2H for every step) -------------------
     hs = nb.host_stream
-    Te = 100  # steps per queued rollout call; two sets of pinned output buffers, one host sync per call
+    Te = int(os.environ.get("BENCH_E2E_STEPS_PER_CALL", "100"))  # steps per queued rollout call; two sets of pinned
+    # output buffers; after queueing call i the host waits for call i-1 (whose results it would consume meanwhile)
     obs_q = torch.empty(2, Te, B, 18, dtype=torch.float64).pin_memory()
     rew_q = torch.empty(2, Te, B, dtype=torch.float64).pin_memory()
     term_q = torch.empty(2, Te, B, dtype=torch.uint8).pin_memory()
@@ -353,8 +354,7 @@ def run_ours(args):
             for i in range(n // Te):
                 o, r, d = out_ptr[i % 2]
                 nb.rollout_host_async(Te, act_ptr[(i * Te) % (RING - Te + 1)], None, o, r, d)
-                if i % 2 == 1:  # two calls in flight, then the host waits (and would consume both buffer sets)
-                    nb.host_sync()
+                nb.host_sync_previous()
             nb.host_sync()
         else:
             for t in range(n):
@@ -476,8 +476,9 @@ def run_ours(args):
         "per_step_launches": per_step,
         "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 6 * 8,
                 "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "steps_per_call": Te,
-                "api": "anm_rollout_host_async (%d steps per call) + anm_host_sync every second call (C ABI; pinned host "
-                       "buffers read / written by the kernel over PCIe = zero-copy)" % Te,
+                "api": "anm_rollout_host_async (%d steps per call) + anm_host_sync_previous after every call (C ABI; pinned host "
+                       "arrays, uploaded / downloaded by the copy engines through device staging buffers while the "
+                       "kernels of consecutive calls run back to back)" % Te,
                 "sync_every_step": {"value": e2e_sync_rate, "unit": "env-steps/s", "steps": Ks,
                                     "api": "anm_step_host (synchronous)"},
                 "checksum": checksum},  # fmt: skip

@@ -123,6 +123,7 @@ _PROTOS = {
     "anm_reset_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "anm_step_host_async": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5),
     "anm_host_sync": (C.c_int, [C.c_void_p]),
+    "anm_host_sync_previous": (C.c_int, [C.c_void_p]),
     "anm_rollout_host_async": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5),
     "anm_host_stream": (C.c_void_p, [C.c_void_p]),
     "anm_launch_count": (C.c_int64, [C.c_void_p]),

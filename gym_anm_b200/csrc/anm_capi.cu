@@ -93,6 +93,18 @@ struct anm_handle_s {
   cudaStream_t stream = nullptr;
   double *s_action = nullptr, *s_nv = nullptr, *s_obs = nullptr, *s_reward = nullptr, *s_s0 = nullptr, *s_state = nullptr;
   uint8_t *s_term = nullptr, *s_mask = nullptr;
+  /* queued host rollouts (anm_rollout_host_async): two sets of device staging buffers, inputs uploaded and outputs
+   * downloaded by the copy engines on their own streams while the compute stream runs the kernels back to back */
+  struct HostSet {
+    double *act = nullptr, *nv = nullptr, *obs = nullptr, *rew = nullptr;
+    uint8_t* term = nullptr;
+    int64_t cap_rows = 0; /* T * B rows allocated */
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+    bool used = false;
+  } hset[2];
+  int hset_next = 0;
+  cudaStream_t st_in = nullptr, st_out = nullptr;
+  bool st_last_was_rollout = false; /* the compute stream's last operation was one of our rollout kernels */
   int64_t launches = 0;
 };
 
@@ -309,6 +321,8 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
         if (v[k].index < 0 || v[k].index >= var_limit(H, v[k].quantity)) return fail(ANM_E_INVALID, "var %d: bad index", k);
         if (v[k].quantity == ANM_Q_BUS_V_ANG || v[k].quantity == ANM_Q_BUS_I_ANG || v[k].quantity == ANM_Q_BRANCH_I_ANG)
           H.need_angles = 1, H.need_mask |= ANM_NEED_ANGLES;
+        if (v[k].quantity <= ANM_Q_BUS_I_ANG) H.need_mask |= ANM_NEED_BUS;
+        if (v[k].quantity >= ANM_Q_BRANCH_P && v[k].quantity <= ANM_Q_BRANCH_I_ANG) H.need_mask |= ANM_NEED_BRANCH;
         if (v[k].quantity == ANM_Q_BUS_V_MAGN) H.need_mask |= ANM_NEED_BUS_V;
         if (v[k].quantity == ANM_Q_BUS_I_MAGN) H.need_mask |= ANM_NEED_BUS_I;
         if (v[k].quantity == ANM_Q_BRANCH_I_MAGN) H.need_mask |= ANM_NEED_BRANCH_I;
@@ -476,7 +490,9 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_vx = take(4 * N);
     H.w_dx = take(M);
     H.w_blk = take(H.solver == 4 ? 4 * H.sp_nblk : 0);
-    H.ws_doubles = (w + 15) / 16 * 16;
+    /* stride = 32 bytes mod 128: the lane groups of a warp read the same workspace entry at the same time, and
+     * their four copies then sit in four different bank groups instead of one */
+    H.ws_doubles = (w + 15) / 16 * 16 + 4;
   }
   bb.buf.resize((bb.buf.size() + 127) / 128 * 128, 0);
   H.blob_bytes = (int)bb.buf.size();
@@ -730,6 +746,14 @@ int anm_destroy(anm_handle h) {
   if (h->wd_host) cudaFreeHost(h->wd_host);
   cudaFree(h->s_action); cudaFree(h->s_nv); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_s0);
   cudaFree(h->s_state); cudaFree(h->s_term); cudaFree(h->s_mask);
+  for (auto& hs : h->hset) {
+    cudaFree(hs.act); cudaFree(hs.nv); cudaFree(hs.obs); cudaFree(hs.rew); cudaFree(hs.term);
+    if (hs.ev_in) cudaEventDestroy(hs.ev_in);
+    if (hs.ev_k) cudaEventDestroy(hs.ev_k);
+    if (hs.ev_out) cudaEventDestroy(hs.ev_out);
+  }
+  if (h->st_in) cudaStreamDestroy(h->st_in);
+  if (h->st_out) cudaStreamDestroy(h->st_out);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return ANM_OK;
@@ -846,6 +870,7 @@ int anm_set_state(anm_handle h, const double* soc, const double* aux, const uint
 static int step_host_enqueue(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs,
                              double* reward, uint8_t* terminated, bool queued) {
   DeviceGuard guard(h->device);
+  h->st_last_was_rollout = false;
   const AnmConstHeader& H = h->H;
   const size_t B = (size_t)h->B * (size_t)T; /* rows of the [T, B, .] host arrays */
   if (T > 1 && host_io_mode() < 2)
@@ -906,25 +931,109 @@ int anm_step_host_async(anm_handle h, const double* action, const double* next_v
   return step_host_enqueue(h, 1, action, next_vars, obs, reward, terminated, true);
 }
 
+/* ANM_HOST_ROLLOUT=zc (environment): queued host rollouts read / write the caller's pinned buffers from the kernel
+ * (zero-copy) instead of staging through device memory with the copy engines (default; measured faster on B200:
+ * 144-byte observation rows make poor PCIe writes, bulk DMA of [T, B, .] arrays runs at link speed). */
+static bool host_rollout_zero_copy() {
+  static const bool v = [] {
+    const char* e = getenv("ANM_HOST_ROLLOUT");
+    return e && !strcmp(e, "zc");
+  }();
+  return v;
+}
+
+static int hostset_reserve(anm_handle h, anm_handle_s::HostSet& hs, int64_t rows, bool need_nv) {
+  const AnmConstHeader& H = h->H;
+  if (!hs.ev_in) {
+    CUDA_TRY(cudaEventCreateWithFlags(&hs.ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&hs.ev_k, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&hs.ev_out, cudaEventDisableTiming));
+  }
+  if (rows > hs.cap_rows) {
+    cudaFree(hs.act); cudaFree(hs.nv); cudaFree(hs.obs); cudaFree(hs.rew); cudaFree(hs.term);
+    hs.act = hs.nv = hs.obs = hs.rew = nullptr; hs.term = nullptr; hs.cap_rows = 0;
+    CUDA_TRY(cudaMalloc((void**)&hs.act, (size_t)rows * H.n_action * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&hs.obs, (size_t)rows * H.n_obs * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&hs.rew, (size_t)rows * sizeof(double)));
+    CUDA_TRY(cudaMalloc((void**)&hs.term, (size_t)rows));
+    hs.cap_rows = rows;
+  }
+  if (need_nv && !hs.nv) CUDA_TRY(cudaMalloc((void**)&hs.nv, (size_t)hs.cap_rows * H.n_next_vars * sizeof(double)));
+  return 0;
+}
+
 int anm_rollout_host_async(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs,
                            double* reward, uint8_t* terminated) {
   if (!h || !action || !obs || !reward || !terminated || T < 1 || T > INT32_MAX)
     return fail(ANM_E_INVALID, "anm_rollout_host_async: bad argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_rollout_host_async: next_vars is NULL but the environment has no built-in table");
-  return step_host_enqueue(h, T, action, next_vars, obs, reward, terminated, true);
+  if (host_rollout_zero_copy()) {
+    h->st_last_was_rollout = false;
+    return step_host_enqueue(h, T, action, next_vars, obs, reward, terminated, true);
+  }
+  DeviceGuard guard(h->device);
+  const AnmConstHeader& H = h->H;
+  const int64_t rows = T * h->B;
+  if (!h->st_in) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
+  }
+  anm_handle_s::HostSet& hs = h->hset[h->hset_next];
+  h->hset_next ^= 1;
+  if (hs.used) { /* the set is free once its previous kernel has read the inputs and its outputs are downloaded */
+    CUDA_TRY(cudaEventSynchronize(hs.ev_k));
+    CUDA_TRY(cudaEventSynchronize(hs.ev_out));
+  }
+  if (int rc = hostset_reserve(h, hs, rows, next_vars != nullptr)) return rc;
+  /* inputs: copy engine, own stream; the HOST waits for the upload (the kernels of the earlier calls are still
+   * running meanwhile), so that the compute stream holds nothing but kernels and consecutive rollouts stay chained */
+  CUDA_TRY(cudaMemcpyAsync(hs.act, action, (size_t)rows * H.n_action * sizeof(double), cudaMemcpyHostToDevice, h->st_in));
+  if (next_vars)
+    CUDA_TRY(cudaMemcpyAsync(hs.nv, next_vars, (size_t)rows * H.n_next_vars * sizeof(double), cudaMemcpyHostToDevice, h->st_in));
+  CUDA_TRY(cudaEventRecord(hs.ev_in, h->st_in));
+  CUDA_TRY(cudaEventSynchronize(hs.ev_in));
+  AnmLaunch p;
+  memset(&p, 0, sizeof(p));
+  p.mode = ANM_MODE_STEP;
+  p.T = (int32_t)T;
+  p.action = hs.act; p.next_vars = next_vars ? hs.nv : nullptr;
+  p.obs = hs.obs; p.reward = hs.rew; p.term_out = hs.term;
+  int rc = launch(h, p, h->stream, h->st_last_was_rollout ? ANM_LF_CHAINED : 0u);
+  if (rc) return rc;
+  h->st_last_was_rollout = true;
+  hs.used = true;
+  CUDA_TRY(cudaEventRecord(hs.ev_k, h->stream));
+  /* outputs: copy engine, own stream, after this kernel */
+  CUDA_TRY(cudaStreamWaitEvent(h->st_out, hs.ev_k, 0));
+  CUDA_TRY(cudaMemcpyAsync(obs, hs.obs, (size_t)rows * H.n_obs * sizeof(double), cudaMemcpyDeviceToHost, h->st_out));
+  CUDA_TRY(cudaMemcpyAsync(reward, hs.rew, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, h->st_out));
+  CUDA_TRY(cudaMemcpyAsync(terminated, hs.term, (size_t)rows, cudaMemcpyDeviceToHost, h->st_out));
+  CUDA_TRY(cudaEventRecord(hs.ev_out, h->st_out));
+  return ANM_OK;
 }
 
 int anm_host_sync(anm_handle h) {
   if (!h) return fail(ANM_E_INVALID, "null handle");
   DeviceGuard guard(h->device);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->st_out) CUDA_TRY(cudaStreamSynchronize(h->st_out));
+  return ANM_OK;
+}
+
+int anm_host_sync_previous(anm_handle h) {
+  if (!h) return fail(ANM_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  if (host_rollout_zero_copy() || !h->st_out) return anm_host_sync(h);
+  anm_handle_s::HostSet& prev = h->hset[h->hset_next]; /* the set of the call before the most recent one */
+  if (prev.used) CUDA_TRY(cudaEventSynchronize(prev.ev_out));
   return ANM_OK;
 }
 
 int anm_reset_host(anm_handle h, const double* s0, const uint8_t* mask, double* obs, double* state, uint8_t* converged) {
   if (!h || !s0 || !obs || !converged) return fail(ANM_E_INVALID, "anm_reset_host: null argument");
   DeviceGuard guard(h->device);
+  h->st_last_was_rollout = false;
   const AnmConstHeader& H = h->H;
   const size_t B = (size_t)h->B;
   cudaStream_t st = h->stream;

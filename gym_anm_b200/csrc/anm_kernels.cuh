@@ -1412,6 +1412,8 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
 #define ANM_NEED_BUS_I 2u    /* bus_i_magn (hypot)            */
 #define ANM_NEED_ANGLES 4u   /* the three angle groups (atan2) */
 #define ANM_NEED_BRANCH_I 8u /* branch_i_magn                  */
+#define ANM_NEED_BUS 16u     /* any bus quantity               */
+#define ANM_NEED_BRANCH 32u  /* any branch quantity            */
 template <int LPE, bool FULL>
 __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restrict__ ws, int lane, unsigned gm,
                                                   unsigned need) {
@@ -1423,14 +1425,16 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
                *ppot = ws + H.w_ppot, *soc = ws + H.w_soc, *brp = ws + H.w_brp, *brq = ws + H.w_brq,
                *brs = ws + H.w_brs, *brire = ws + H.w_brire, *briim = ws + H.w_briim, *aux = ws + H.w_aux;
   const bool angles = (need & ANM_NEED_ANGLES) != 0u;
+  if (need & ANM_NEED_BUS) {
 #pragma unroll 1
-  for (int b = lane; b < N; b += LPE) {
-    full[b] = busp[b];
-    full[N + b] = busq[b];
-    full[2 * N + b] = (need & ANM_NEED_BUS_V) ? cabs2(vre[b], vim[b]) : 0.0;
-    full[3 * N + b] = angles ? atan2_cold(vim[b], vre[b]) : 0.0;
-    full[4 * N + b] = (need & ANM_NEED_BUS_I) ? cabs2(ire[b], iim[b]) : 0.0;
-    full[5 * N + b] = angles ? atan2_cold(iim[b], ire[b]) : 0.0;
+    for (int b = lane; b < N; b += LPE) {
+      full[b] = busp[b];
+      full[N + b] = busq[b];
+      full[2 * N + b] = (need & ANM_NEED_BUS_V) ? cabs2(vre[b], vim[b]) : 0.0;
+      full[3 * N + b] = angles ? atan2_cold(vim[b], vre[b]) : 0.0;
+      full[4 * N + b] = (need & ANM_NEED_BUS_I) ? cabs2(ire[b], iim[b]) : 0.0;
+      full[5 * N + b] = angles ? atan2_cold(iim[b], ire[b]) : 0.0;
+    }
   }
   double* fd = full + 6 * N;
 #pragma unroll 1
@@ -1442,18 +1446,20 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
     fd[3 * D + d] = (t == ANM_DEV_GEN || t == ANM_DEV_RENEWABLE) ? ppot[d] : 0.0;
   }
   double* fb = fd + 4 * D;
+  if (need & ANM_NEED_BRANCH) {
 #pragma unroll 1
-  for (int l = lane; l < L; l += LPE) {
-    fb[l] = brp[l];
-    fb[L + l] = brq[l];
-    fb[2 * L + l] = brs[l];
-    double im = 0.0;
-    if (need & ANM_NEED_BRANCH_I) {
-      const double a = cabs2(brire[l], briim[l]);
-      im = (a == 0.0) ? 0.0 : (brire[l] / a) * a; /* simulator.py:613, NumPy>=2 sign(z) */
+    for (int l = lane; l < L; l += LPE) {
+      fb[l] = brp[l];
+      fb[L + l] = brq[l];
+      fb[2 * L + l] = brs[l];
+      double im = 0.0;
+      if (need & ANM_NEED_BRANCH_I) {
+        const double a = cabs2(brire[l], briim[l]);
+        im = (a == 0.0) ? 0.0 : (brire[l] / a) * a; /* simulator.py:613, NumPy>=2 sign(z) */
+      }
+      fb[3 * L + l] = im;
+      fb[4 * L + l] = angles ? atan2_cold(briim[l], brire[l]) : 0.0;
     }
-    fb[3 * L + l] = im;
-    fb[4 * L + l] = angles ? atan2_cold(briim[l], brire[l]) : 0.0;
   }
   double* fa = fb + 5 * L;
 #pragma unroll 1

@@ -181,6 +181,10 @@ class NativeBatch:
         _capi.check(self.lib.anm_rollout_host_async(self.h, C.c_int64(T), p(actions), p(next_vars), p(obs), p(reward),
                                                     p(terminated)), self.lib)  # fmt: skip
 
+    def host_sync_previous(self):
+        """Wait for every queued rollout except the most recent one (consume call i-1 while call i runs)."""
+        _capi.check(self.lib.anm_host_sync_previous(self.h), self.lib)
+
     def host_sync(self):
         _capi.check(self.lib.anm_host_sync(self.h), self.lib)
 

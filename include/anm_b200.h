@@ -242,8 +242,15 @@ int anm_reset_host(anm_handle h, const double* s0_host, const uint8_t* mask_host
 int anm_step_host_async(anm_handle h, const double* action_host, const double* next_vars_host_or_null,
                         double* obs_host, double* reward_host, uint8_t* terminated_host);
 int anm_host_sync(anm_handle h);
-/* Queued anm_rollout on host buffers: [T, B, .] arrays, all of them pinned (page-locked, mapped) host
- * memory that the kernel reads / writes directly; valid after anm_host_sync. */
+/* Queued anm_rollout on host buffers: [T, B, .] arrays (pinned memory for full speed; pageable works).
+ * The actions are uploaded and the results downloaded by the copy engines through device staging
+ * buffers of the handle while the kernels of consecutive calls run back to back; the outputs are
+ * valid after anm_host_sync.  The call returns once the upload of its inputs has completed, so the
+ * caller may reuse the action arrays at once.  (ANM_HOST_ROLLOUT=zc: the kernel reads / writes the
+ * pinned buffers directly instead.) */
+/* Wait until every queued rollout except the most recent one has delivered its outputs (the consumer
+ * works on call i-1 while call i runs: no pipeline drain). */
+int anm_host_sync_previous(anm_handle h);
 int anm_rollout_host_async(anm_handle h, int64_t T, const double* action_host,
                            const double* next_vars_host_or_null, double* obs_host, double* reward_host,
                            uint8_t* terminated_host);

@@ -625,7 +625,8 @@ def test_queued_host_steps_equal_synchronous_ones():
 
 
 def test_rollout_on_pinned_host_buffers():
-    """anm_rollout_host_async: [T, B, .] pinned host arrays read / written by the kernel == device rollout."""
+    """anm_rollout_host_async: [T, B, .] host arrays (pinned or pageable) staged by the copy engines == device
+    rollout; also with the zero-copy variant in a subprocess."""
     B, T = 512, 32
     a_env, b_env = _two_envs(B, 44)
     na, nb = a_env.native, b_env.native
@@ -641,12 +642,21 @@ def test_rollout_on_pinned_host_buffers():
     nb.host_sync()
     obs_d, rew_d, term_d = na.rollout(acts.to(na.device))
     assert torch.equal(obs_d.cpu(), obs_q) and torch.equal(rew_d.cpu(), rew_q) and torch.equal(term_d.cpu(), term_q)
-    with pytest.raises(Exception):  # pageable memory is refused loudly (no silent staging for T > 1)
-        nb.rollout_host_async(T, acts[:T], None, obs_q[:T], rew_q[:T], term_q[:T])
+    import os
+
+    if os.environ.get("ANM_HOST_ROLLOUT") == "zc":
+        return  # the zero-copy variant needs pinned buffers
+    # pageable arrays, same steps replayed from the same carried state
+    c_env = _two_envs(B, 44)[0]
+    obs_p, rew_p, term_p = np.zeros((T, B, 18)), np.zeros((T, B)), np.zeros((T, B), dtype=np.uint8)
+    c_env.native.rollout_host_async(T, acts[:T].numpy(), None, obs_p, rew_p, term_p)
+    c_env.native.host_sync()
+    assert np.array_equal(obs_p, obs_q[:T].numpy()) and np.array_equal(term_p, term_q[:T].numpy())
 
 
 def test_chaining_off_same_results_subprocess():
-    """ANM_PDL=0 (no programmatic dependent launch, every launch fully ordered) gives the same results."""
+    """ANM_PDL=0 (no programmatic dependent launch, every launch fully ordered), ANM_HOST_ROLLOUT=zc (queued host
+    rollouts through zero-copy instead of the copy engines) and ANM_LANES=16 give the same results."""
     import os
     import subprocess
     import sys
@@ -654,6 +664,7 @@ def test_chaining_off_same_results_subprocess():
     here = os.path.abspath(__file__)
     sel = ("test_rollout_equals_stepwise or test_chained_steps_graph_replay_and_oracle or test_queued_host_steps "
            "or test_rollout_on_pinned")
-    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
-                       env=dict(os.environ, ANM_PDL="0"), capture_output=True, text=True, timeout=900)  # fmt: skip
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    for var in ({"ANM_PDL": "0"}, {"ANM_HOST_ROLLOUT": "zc"}, {"ANM_LANES": "16"}):
+        r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-k", sel, "-p", "no:cacheprovider"],
+                           env=dict(os.environ, **var), capture_output=True, text=True, timeout=900)  # fmt: skip
+        assert r.returncode == 0, str(var) + "\n" + r.stdout[-3000:] + r.stderr[-2000:]
