@@ -417,22 +417,26 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = B_MIN_BYTES * B / kernel_s / 1e9
+    launch_s = (ms_total / 1000.0) / max(gpu_launches, 1)      # one anm_rollout launch = T steps of every instance
+    steps_per_launch = K / max(gpu_launches, 1)
+    achieved = B_MIN_BYTES * B * steps_per_launch / launch_s / 1e9
     ncu = {}
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
     except Exception:  # noqa: BLE001
         pass
+    per_es = ncu.get("dram_bytes_per_env_step")
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src,
-        "algorithmic_bytes_per_env_step": B_MIN_BYTES, "env_steps_per_launch": B,
-        "kernel_us_mean": kernel_s * 1e6,
-        "kernel_time": "timed region / steps (a launch covers many steps; a single-step launch: "
-                       "per_step_launches.lockstep.ms_per_step)",
-        "note": "compute/latency-bound path (fp64 FMA pipe + shuffle/LDS latency), not HBM-bound; see fp64 fields",
+        "traffic": None if per_es is None else per_es * B * steps_per_launch, "peak_source": peak_src,
+        "algorithmic_bytes_per_env_step": B_MIN_BYTES, "env_steps_per_launch": B * steps_per_launch,
+        "kernel_us_mean": launch_s * 1e6, "kernel_us_per_step": kernel_s * 1e6,
+        "traffic_note": "dram bytes per env-step of the ncu capture (a 50-step launch: the 153 B / env-step of outputs "
+                        "were still in the 126 MB L2 when it ended) x env-steps per launch",
+        "note": "compute/latency-bound path (dependent fp64 FMA chains, shuffle / shared-memory latency at 1.7 warps per "
+                "scheduler), not HBM-bound: 234 B against ~1650 warp instructions per env-step; see the fp64 / issue fields",
         "fp64_pipe_pct_ncu": ncu.get("fp64_pipe_pct"), "issue_slot_pct_ncu": ncu.get("issue_active_pct"),
-        "ncu_profile": ncu.get("source"),
+        "stall_samples_pct_ncu": ncu.get("stall_samples_pct"), "ncu_profile": ncu.get("source"),
     }  # fmt: skip
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
