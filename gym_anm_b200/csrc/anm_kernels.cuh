@@ -874,6 +874,7 @@ struct SmallNR {
       vbi = vm * sn;
       const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN); /* v/abs(v): 0/0 -> NaN */
       const double ebr = sg * cs, ebi = sg * sn;
+      __syncwarp(); /* the previous iteration's reads of xch are done (write-after-read) */
       if (active && !part) xch[b] = make_double4(vbr, vbi, ebr, ebi);
       __syncwarp();
       /* I_b = sum_j Y_bj V_j ; S_b = V_b conj(I_b) ; my mismatch entry (:84-120) */
