@@ -53,10 +53,11 @@
 #define ANM_DIAG 0 /* 1: fill anm_step_extras.solver_stats (costs ~10 %: clock64 + votes); tools/ build only */
 #endif
 #ifndef ANM_VAR_THREADS
-#define ANM_VAR_THREADS 64 /* CTA size of the small-network kernels */
+#define ANM_VAR_THREADS 32 /* CTA size of the small-network kernels: one warp (four instances); 1024 CTAs at B = 4096
+                              spread more evenly over the 148 SMs than 512 two-warp CTAs (+11 % rollout rate) */
 #endif
 #ifndef ANM_VAR_MINB
-#define ANM_VAR_MINB 5 /* CTAs per SM the small-network kernels are built for: 5 x 44 KB of shared memory per SM, <= 204 registers */
+#define ANM_VAR_MINB 7 /* CTAs per SM the small-network kernels are built for: 7 x 30 KB of shared memory per SM */
 #endif
 #ifndef ANM_VAR_YREG
 #define ANM_VAR_YREG 1 /* 1: the lane's dense Y row lives in registers; 0: re-read from shared memory */
@@ -257,7 +258,11 @@ __device__ __forceinline__ unsigned g_umax(unsigned key, unsigned gm, int grp_in
  * (32 KB L1.5 per SM), and these expand to hundreds of instructions each. */
 __device__ __noinline__ double atan2_cold(double y, double x) { return atan2(y, x); }
 __device__ __noinline__ double fmod_cold(double v, double len) { return fmod(v, len); }
-__device__ __noinline__ void sincos_cold(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+__device__ __noinline__ double2 sincos_cold(double x) {
+  double sn, cs;
+  sincos(x, &sn, &cs);
+  return make_double2(sn, cs);
+}
 __device__ __noinline__ double div_cold(double a, double b) { return a / b; }
 
 /* |x + jy| as sqrt(x^2 + y^2): within 1 ulp of hypot (numpy's abs of a complex) for the per-unit magnitudes of a power
@@ -282,34 +287,44 @@ __device__ __forceinline__ double pow2_inv_scale(double v) {
  * is what V = |V| e^{j theta} needs -- divergent Newton trajectories routinely reach |theta| > 1e5 and the
  * slow path dominated their latency).  Kernels: fdlibm's __kernel_sin/__kernel_cos minimax polynomials on
  * [-pi/4, pi/4].  |x| >= 2^50, inf and NaN fall back to libdevice. */
-__device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
+/* the constants of sincos_fast live in the constant bank: a DFMA takes them as operands, whereas a 64-bit immediate
+ * costs two extra instructions each time */
+__constant__ double ANM_SC[17] = {
+    0.6366197723675814, 6755399441055744.0, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04,
+    8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07, 2.48015872894767294178e-05,
+    -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__device__ __forceinline__ void sincos_fast(double x, double& sn, double& cs) {
   if (!(fabs(x) < 1.125899906842624e15)) { /* 2^50; also catches NaN / inf */
-    sincos_cold(x, sn, cs);
+    const double2 r = sincos_cold(x);
+    sn = r.x;
+    cs = r.y;
     return;
   }
   /* k = rint(x * 2/pi) by the 1.5 * 2^52 trick: the quadrant is in the low mantissa bits of the sum */
-  const double t = fma(x, 0.6366197723675814, 6755399441055744.0);
+  const double t = fma(x, ANM_SC[0], ANM_SC[1]);
   const int q = __double2loint(t) & 3;
-  const double k = t - 6755399441055744.0;
-  double r = fma(-k, 1.5707963267948966, x);
-  r = fma(-k, 6.123233995736766e-17, r);
-  r = fma(-k, -1.4973849048591698e-33, r);
+  const double k = t - ANM_SC[1];
+  double r = fma(-k, ANM_SC[2], x);
+  r = fma(-k, ANM_SC[3], r);
+  r = fma(-k, ANM_SC[4], r);
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
+  double ps = fma(z, ANM_SC[5], ANM_SC[6]);
+  ps = fma(z, ps, ANM_SC[7]);
+  ps = fma(z, ps, ANM_SC[8]);
+  ps = fma(z, ps, ANM_SC[9]);
+  ps = fma(z, ps, ANM_SC[10]);
   const double s = fma(z * r, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
+  double pc = fma(z, ANM_SC[11], ANM_SC[12]);
+  pc = fma(z, pc, ANM_SC[13]);
+  pc = fma(z, pc, ANM_SC[14]);
+  pc = fma(z, pc, ANM_SC[15]);
+  pc = fma(z, pc, ANM_SC[16]);
   const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
   const double s1 = (q & 1) ? c : s, c1 = (q & 1) ? s : c;
-  *sn = (q & 2) ? -s1 : s1;
-  *cs = ((q + 1) & 2) ? -c1 : c1;
+  sn = (q & 2) ? -s1 : s1;
+  cs = ((q + 1) & 2) ? -c1 : c1;
 }
 
 /* 1/x to ~1 ulp without the IEEE corner-case handling of `1.0 / x`: MUFU.RCP64H seed + two Newton steps.
@@ -641,7 +656,7 @@ __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws,
       double re = 1.0, im = 0.0, er = 1.0, ei = 0.0;
       if (b > 0) {
         double sn, cs;
-        sincos_fast(x[b - 1], &sn, &cs);
+        sincos_fast(x[b - 1], sn, cs);
         const double vm = x[n + b - 1];
         const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN);
         re = vm * cs; im = vm * sn; er = sg * cs; ei = sg * sn;
@@ -865,7 +880,7 @@ struct SmallNR {
       const double other = __shfl_sync(ANM_FULL, xr, partner, LPE);
       const double th = part ? other : xr, vm = part ? xr : other;
       double sn, cs;
-      sincos_fast(th, &sn, &cs);
+      sincos_fast(th, sn, cs);
 #if ANM_DIAG
       const bool big_angle = g_any<true>(active && fabs(th) > 1e5, gm);
       if (!done && big_angle) ++n_big;
@@ -1059,7 +1074,7 @@ struct RadialNR {
     for (;;) {
       /* V_b = |V| e^{j theta}, E_b = V_b / |V_b| (:167-173, :150) */
       double sn, cs;
-      sincos_fast(th, &sn, &cs);
+      sincos_fast(th, sn, cs);
       vr = vm * cs;
       vi = vm * sn;
       const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN);
