@@ -338,9 +338,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
 }
 
 /* int(v % len) of ANM6Easy.next_vars (anm6_easy.py:56): v is an integer-valued counter in practice, for which
- * v - floor(v / len) * len is exact and a dozen instructions; anything else takes fmod. */
+ * the integer remainder is exact and a dozen instructions; anything else takes fmod. */
 __device__ __forceinline__ int next_slot(double v, double len) {
-  if (v >= 0.0 && v < 4503599627370496.0 && v == floor(v)) return (int)fma(-floor(v / len), len, v);
+  if (v >= 0.0 && v < 2147483648.0 && v == floor(v) && len == floor(len) && len >= 1.0 && len < 2147483648.0)
+    return (int)v % (int)len;
   return (int)fmod_cold(v, len);
 }
 
@@ -1539,8 +1540,21 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
     init_polygon_rows<LPE>(C, ws, lane);
     gsync<FULL>(gm);
 
+    /* Step mode: lane j < A keeps entry j of the action row one step ahead of its use, so that the global-memory
+     * latency of the load (HBM: the action ring does not fit the L2) is hidden behind the previous step. */
+    const bool a_pre_ok = (P.mode == ANM_MODE_STEP) && (A <= LPE);
+    int aslot = 0;
+    bool aslot_q = false;
+    if (lane < ng) aslot = lane;
+    else if (lane < 2 * ng) aslot = lane - ng, aslot_q = true;
+    else if (lane < 2 * ng + ns) aslot = ng + (lane - 2 * ng);
+    else aslot = ng + (lane - 2 * ng - ns), aslot_q = true;
+    double a_pre = 0.0, a_next = 0.0;
+    if (a_pre_ok && have && lane < A) a_pre = P.action[e * A + lane];
+
     for (int t = 0; t < T; ++t) {
       const int64_t row = (int64_t)t * P.B + e; /* this step's slice of the [T, B, .] inputs / outputs */
+      if (a_pre_ok && have && lane < A && t + 1 < T) a_next = P.action[(row + P.B) * A + lane];
       int act = ACT_NONE;
       const double* s0row = nullptr;
       if (have) {
@@ -1599,12 +1613,17 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 #pragma unroll 1
           for (int k = lane; k < K; k += LPE) s0w[k] = (k == K - 1) ? (double)a : aux[k];
         }
-        /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410) */
-        const double* av = P.action + row * A;
+        /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410); entry j goes to the set-point slot aslot.
+         * With A <= LPE lane j already holds this step's entry (loaded one step ahead, see below). */
+        if (a_pre_ok) {
+          if (lane < A) (aslot_q ? in_qs : in_ps)[aslot] = a_pre;
+        } else {
+          const double* av = P.action + row * A;
 #pragma unroll 1
-        for (int k = lane; k < ng; k += LPE) { in_ps[k] = av[k]; in_qs[k] = av[ng + k]; }
+          for (int k = lane; k < ng; k += LPE) { in_ps[k] = av[k]; in_qs[k] = av[ng + k]; }
 #pragma unroll 1
-        for (int k = lane; k < ns; k += LPE) { in_ps[ng + k] = av[2 * ng + k]; in_qs[ng + k] = av[2 * ng + ns + k]; }
+          for (int k = lane; k < ns; k += LPE) { in_ps[ng + k] = av[2 * ng + k]; in_qs[ng + k] = av[2 * ng + ns + k]; }
+        }
       } else if (act == ACT_TRANSITION) {
 #pragma unroll 1
         for (int k = lane; k < nl; k += LPE) in_pl[k] = P.p_load[e * nl + k];
@@ -1766,6 +1785,7 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
         o[10] = nit;
       }
 #endif
+      a_pre = a_next;
       gsync<FULL>(gm); /* the workspace is reused by the next step */
     }
 
