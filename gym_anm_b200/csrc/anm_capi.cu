@@ -274,6 +274,17 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     }
     H.o_ctrl_dev = bb.add(ctrl);
     H.o_ctrl_rows = bb.add(rows);
+    {
+      std::vector<int> fin(H.n_ctrl, 0);
+      for (int c = 0; c < H.n_ctrl; ++c) {
+        const double* h = &rows[(size_t)c * 3 * ANM_MAX_ROWS + 2 * ANM_MAX_ROWS];
+        for (int k = 0; k < ANM_MAX_ROWS; ++k) {
+          const bool dynamic = (c < H.n_gen) ? (k == 2) : (k == 8 || k == 9); /* rewritten every step by the kernel */
+          if (!dynamic && std::isfinite(h[k])) fin[c] |= 1 << k;
+        }
+      }
+      H.o_ctrl_fin = bb.add(fin);
+    }
     /* candidate_table: every candidate of the exact projection (project_polygon, anm_kernels.cuh) as an affine map
      * of (p, q, h[s1], h[s2]) -- the point, its projection on each row's line, each pairwise intersection, in the
      * order of oracle/shims/cvxpy/_projection.py (ties go to the lowest candidate); parallel pairs are dropped. */
@@ -484,7 +495,7 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_devp = take(D); H.w_devq = take(D); H.w_ppot = take(D); H.w_busp = take(N); H.w_busq = take(N);
     H.w_x = take(M); H.w_vre = take(N); H.w_vim = take(N); H.w_ere = take(N); H.w_eim = take(N);
     H.w_ire = take(N); H.w_iim = take(N);
-    H.w_J = take(H.solver == 4 ? 0 : M * (M + 1)); H.w_rowh = take(2 * H.n_ctrl * ANM_MAX_ROWS); /* raw + sanitised */
+    H.w_J = take(H.solver == 4 ? 0 : M * (M + 1)); H.w_rowh = take(2 * H.n_ctrl * ANM_MAX_ROWS + H.n_ctrl); /* -h / -inf, h / 0, finite-row mask per device */
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
     H.w_vx = take(4 * N);

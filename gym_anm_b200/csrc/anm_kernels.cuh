@@ -354,7 +354,7 @@ struct Cst {  // resolved pointers into the staged blob
       *sp_blk_y, *sp_step, *sp_row, *sp_col, *sp_nbr, *sp_tgt;
   const double* rad_y;
   const double4* cand_coef; /* [ncand_total][2]: kx, ky of every candidate */
-  const int *cand_info, *cand_ptr;
+  const int *cand_info, *cand_ptr, *ctrl_fin;
   __device__ explicit Cst(const unsigned char* b) {
     H = reinterpret_cast<const AnmConstHeader*>(b);
 #define DP(name, off) name = reinterpret_cast<const double*>(b + H->off)
@@ -371,7 +371,7 @@ struct Cst {  // resolved pointers into the staged blob
     IP(sp_blk_i, o_sp_blk_i); IP(sp_blk_j, o_sp_blk_j); IP(sp_blk_y, o_sp_blk_y); IP(sp_step, o_sp_step);
     IP(sp_row, o_sp_row); IP(sp_col, o_sp_col); IP(sp_nbr, o_sp_nbr); IP(sp_tgt, o_sp_tgt);
     cand_coef = reinterpret_cast<const double4*>(b + H->o_cand_coef);
-    IP(cand_info, o_cand_info); IP(cand_ptr, o_cand_ptr);
+    IP(cand_info, o_cand_info); IP(cand_ptr, o_cand_ptr); IP(ctrl_fin, o_ctrl_fin);
 #undef DP
 #undef IP
   }
@@ -390,24 +390,22 @@ struct Cst {  // resolved pointers into the staged blob
  * not tested against themselves. */
 template <int LPE, bool FULL>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
-                                                const double* __restrict__ rh, const double* __restrict__ rhe,
-                                                const double4* __restrict__ coef, const int* __restrict__ info,
-                                                int ncand, int nrows, double p, double q, int lane, unsigned gm,
-                                                double& po, double& qo) {
+                                                const double* __restrict__ rnh, const double* __restrict__ rhe,
+                                                unsigned fin, const double4* __restrict__ coef,
+                                                const int* __restrict__ info, int ncand, int nrows, double p, double q,
+                                                int lane, unsigned gm, double& po, double& qo) {
   constexpr int R = ANM_MAX_ROWS; /* storage units: 10 rows; generators: 7 (nrows; rows 7..9 are then skipped) */
   constexpr int R0 = 7;
+  constexpr int U = 2;          /* candidates per lane and trip: two independent dependency chains */
   const bool more = nrows > R0; /* warp-uniform: every lane group works on the same device */
-  constexpr int U = 2;            /* candidates per lane and trip: two independent dependency chains */
+  /* rnh: minus the right-hand sides, -inf where the row is unused (a x + b y - inf > tol is never true: the row is
+   * skipped); fin: bit k set = row k has a finite right-hand side.  Both prepared by whoever wrote the rows. */
   double a[R], b[R], nh[R];
-  unsigned fin = 0u;
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     a[k] = ra[k];
     b[k] = rb[k];
-    const double hk = rh[k];
-    const bool f = fabs(hk) < CUDART_INF; /* false for NaN */
-    fin |= f ? (1u << k) : 0u;
-    nh[k] = f ? -hk : -CUDART_INF; /* a x + b y - inf > tol is never true: the row is skipped */
+    nh[k] = rnh[k];
   }
   double best = CUDART_INF, bx = CUDART_NAN, by = CUDART_NAN;
   /* a compact loop on purpose (the body stays in the instruction cache); every lane makes the same trips.
@@ -1227,24 +1225,26 @@ struct RadialNR {
   }
 };
 
-/* The step-independent right-hand sides of every polygon row (raw, and with the non-finite ones replaced by 0 for
- * the candidate evaluation): once per pass, before the first transition. */
+/* The step-independent right-hand sides of every polygon row, in the two forms project_polygon reads (negated with
+ * -inf for unused rows; plain with 0 for unused rows): once per pass, before the first transition. */
 template <int LPE>
 __device__ __forceinline__ void init_polygon_rows(const Cst& C, double* __restrict__ ws, int lane) {
   const AnmConstHeader& H = *C.H;
-  double* rowh = ws + H.w_rowh;
-  double* rowhe = rowh + H.n_ctrl * ANM_MAX_ROWS;
+  double* rownh = ws + H.w_rowh;
+  double* rowhe = rownh + H.n_ctrl * ANM_MAX_ROWS;
 #pragma unroll 1
   for (int i = lane; i < H.n_ctrl * ANM_MAX_ROWS; i += LPE) {
     const int c = i / ANM_MAX_ROWS, r = i - c * ANM_MAX_ROWS;
     const double h = C.ctrl_rows[c * 3 * ANM_MAX_ROWS + 2 * ANM_MAX_ROWS + r];
-    rowh[i] = h;
-    rowhe[i] = (fabs(h) < CUDART_INF) ? h : 0.0;
+    const bool f = fabs(h) < CUDART_INF;
+    rownh[i] = f ? -h : -CUDART_INF;
+    rowhe[i] = f ? h : 0.0;
   }
 }
 
 /* ---- one Simulator.transition for one environment ----------------------------------------
- * Inputs in the workspace: in_pl, in_pp, in_ps, in_qs (MW / MVAr), soc (p.u.).
+ * Inputs in the workspace: in_pl, in_pp (MW), in_ps, in_qs (set-points, already p.u.: the lane that unpacks an
+ * entry divides it by baseMVA, simulator.py:507-517), soc (p.u.).
  * Leaves dev_p/q, ppot, bus_p/q, V, I, branch quantities in the workspace.  Returns `stable`
  * and the (unclipped) reward terms to every lane of the group.  `live` = this group has a real
  * environment (a dead group runs along for lock-step but skips the Newton iterations). */
@@ -1267,8 +1267,9 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   double* in_qs = ws + H.w_in_qs; double* soc = ws + H.w_soc; double* devp = ws + H.w_devp;
   double* devq = ws + H.w_devq; double* ppot = ws + H.w_ppot; double* busp = ws + H.w_busp;
   double* busq = ws + H.w_busq; double* vre = ws + H.w_vre; double* vim = ws + H.w_vim;
-  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* rowh = ws + H.w_rowh;
-  double* rowhe = rowh + H.n_ctrl * ANM_MAX_ROWS;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* rownh = ws + H.w_rowh;
+  double* rowhe = rownh + H.n_ctrl * ANM_MAX_ROWS;
+  int* rowfin = reinterpret_cast<int*>(rowhe + H.n_ctrl * ANM_MAX_ROWS); /* per device: finite-row mask */
 
   /* 1. loads, p_pot, slack (devices.py:156-167, simulator.py:511, 521-523) and the polygon rows that depend on
    *    this step: p <= p_pot for a generator, the two SoC rows of a storage unit.  The other right-hand sides were
@@ -1285,17 +1286,21 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     } else if (t == ANM_DEV_GEN || t == ANM_DEV_RENEWABLE) {
       pp = clipd(in_pp[slot] / m, P[ANM_DP_PMIN], P[ANM_DP_PMAX]);
       const int i = slot * ANM_MAX_ROWS + 2; /* p <= p_pot, devices.py:296 */
-      rowh[i] = pp;
-      rowhe[i] = (fabs(pp) < CUDART_INF) ? pp : 0.0;
+      const bool f = fabs(pp) < CUDART_INF;
+      rownh[i] = f ? -pp : -CUDART_INF;
+      rowhe[i] = f ? pp : 0.0;
+      rowfin[slot] = C.ctrl_fin[slot] | (f ? 4 : 0);
     } else if (t == ANM_DEV_STORAGE) {
       const double sc = soc[slot], eff = P[ANM_DP_EFF];
       const double h8 = -(sc - P[ANM_DP_SOCMAX]) / (dt * eff); /* devices.py:511 */
       const double h9 = eff * (sc - P[ANM_DP_SOCMIN]) / dt;    /* devices.py:512 */
-      const int i = (H.n_gen + slot) * ANM_MAX_ROWS + 8;
-      rowh[i] = h8;
-      rowh[i + 1] = h9;
-      rowhe[i] = (fabs(h8) < CUDART_INF) ? h8 : 0.0;
-      rowhe[i + 1] = (fabs(h9) < CUDART_INF) ? h9 : 0.0;
+      const int c = H.n_gen + slot, i = c * ANM_MAX_ROWS + 8;
+      const bool f8 = fabs(h8) < CUDART_INF, f9 = fabs(h9) < CUDART_INF;
+      rownh[i] = f8 ? -h8 : -CUDART_INF;
+      rownh[i + 1] = f9 ? -h9 : -CUDART_INF;
+      rowhe[i] = f8 ? h8 : 0.0;
+      rowhe[i + 1] = f9 ? h9 : 0.0;
+      rowfin[c] = C.ctrl_fin[c] | (f8 ? 256 : 0) | (f9 ? 512 : 0);
     } else if (t == ANM_DEV_SLACK) {
       devp[d] = 0.0;
       devq[d] = 0.0;
@@ -1313,8 +1318,8 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const bool is_des = (c >= H.n_gen);
     const int c0 = C.cand_ptr[c], nc = C.cand_ptr[c + 1] - c0;
     double po, qo;
-    project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rowh + c * ANM_MAX_ROWS, rowhe + c * ANM_MAX_ROWS,
-                               C.cand_coef + 2 * c0, C.cand_info + c0, nc, is_des ? 10 : 7, in_ps[c] / m, in_qs[c] / m, lane,
+    project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rownh + c * ANM_MAX_ROWS, rowhe + c * ANM_MAX_ROWS,
+                               (unsigned)rowfin[c], C.cand_coef + 2 * c0, C.cand_info + c0, nc, is_des ? 10 : 7, in_ps[c], in_qs[c], lane,
                                gm, po, qo);
     if (lane == 0) {
       devp[d] = po;
@@ -1616,13 +1621,16 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
         /* action = [P_gen | Q_gen | P_des | Q_des] (anm_env.py:394-410); entry j goes to the set-point slot aslot.
          * With A <= LPE lane j already holds this step's entry (loaded one step ahead, see below). */
         if (a_pre_ok) {
-          if (lane < A) (aslot_q ? in_qs : in_ps)[aslot] = a_pre;
+          if (lane < A) (aslot_q ? in_qs : in_ps)[aslot] = a_pre / H.base_mva;
         } else {
           const double* av = P.action + row * A;
 #pragma unroll 1
-          for (int k = lane; k < ng; k += LPE) { in_ps[k] = av[k]; in_qs[k] = av[ng + k]; }
+          for (int k = lane; k < ng; k += LPE) { in_ps[k] = av[k] / H.base_mva; in_qs[k] = av[ng + k] / H.base_mva; }
 #pragma unroll 1
-          for (int k = lane; k < ns; k += LPE) { in_ps[ng + k] = av[2 * ng + k]; in_qs[ng + k] = av[2 * ng + ns + k]; }
+          for (int k = lane; k < ns; k += LPE) {
+            in_ps[ng + k] = av[2 * ng + k] / H.base_mva;
+            in_qs[ng + k] = av[2 * ng + ns + k] / H.base_mva;
+          }
         }
       } else if (act == ACT_TRANSITION) {
 #pragma unroll 1
@@ -1630,7 +1638,10 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 #pragma unroll 1
         for (int k = lane; k < ng; k += LPE) in_pp[k] = P.p_pot[e * ng + k];
 #pragma unroll 1
-        for (int k = lane; k < nc; k += LPE) { in_ps[k] = P.p_set[e * nc + k]; in_qs[k] = P.q_set[e * nc + k]; }
+        for (int k = lane; k < nc; k += LPE) {
+          in_ps[k] = P.p_set[e * nc + k] / H.base_mva;
+          in_qs[k] = P.q_set[e * nc + k] / H.base_mva;
+        }
       } else if (act == ACT_RESET) { /* Simulator.reset (simulator.py:225-293); s0 row kept in s0w */
 #pragma unroll 1
         for (int k = lane; k < S; k += LPE) s0w[k] = s0row[k];
@@ -1643,13 +1654,13 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
           if (ty == ANM_DEV_LOAD) {
             in_pl[slot] = s0w[d];
           } else if (ty == ANM_DEV_GEN || ty == ANM_DEV_RENEWABLE) {
-            in_ps[slot] = s0w[d];
-            in_qs[slot] = s0w[D + d];
+            in_ps[slot] = s0w[d] / H.base_mva;
+            in_qs[slot] = s0w[D + d] / H.base_mva;
             in_pp[slot] = s0w[2 * D + ns + slot];
           } else if (ty == ANM_DEV_STORAGE) {
             const double* Pp = C.dev_param + d * ANM_DEV_NPARAM;
-            in_ps[ng + slot] = s0w[d];
-            in_qs[ng + slot] = s0w[D + d];
+            in_ps[ng + slot] = s0w[d] / H.base_mva;
+            in_qs[ng + slot] = s0w[D + d] / H.base_mva;
             soc[slot] = (s0w[d] <= 0.0) ? Pp[ANM_DP_SOCMIN] : Pp[ANM_DP_SOCMAX]; /* :273-278 */
           }
         }

@@ -40,6 +40,7 @@ struct AnmConstHeader {
   int32_t o_jac_row, o_jac_col, o_jac_y;     /* int[n_jac] each: bus b>=1, bus j>=1, index into y_val */
   int32_t o_ctrl_dev;                        /* int[n_ctrl] device position (gens then storage) */
   int32_t o_ctrl_rows;                       /* double[n_ctrl][3][ANM_MAX_ROWS]: a[], b[], h[]  */
+  int32_t o_ctrl_fin;                        /* int[n_ctrl]: bit k = static row k has a finite h (dynamic rows: 0) */
   int32_t o_sv_off, o_sv_mul, o_sv_div;      /* state vars: int[], double[], double[]          */
   int32_t o_ov_off, o_ov_mul, o_ov_div, o_ov_low, o_ov_high; /* obs vars                       */
   int32_t o_table;                           /* double[table_len][n_load+n_gen]                */

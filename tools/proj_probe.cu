@@ -26,11 +26,11 @@ static Tab make(const std::vector<std::array<double, 3>>& rows) {
   return t;
 }
 __global__ void k(const double* ab, const double* h, const double* coef, const int* info, int ncand, double* out, long long* cyc, int reps) {
-  __shared__ double s_ab[20], s_h[4][10];
+  __shared__ double s_ab[20], s_h[4][10], s_nh[4][10];
   __shared__ __align__(16) double s_coef[56 * 8];
   __shared__ int s_info[56];
   for (int i = threadIdx.x; i < 20; i += 32) s_ab[i] = ab[i];
-  for (int i = threadIdx.x; i < 40; i += 32) s_h[i / 10][i % 10] = h[i % 10];
+  for (int i = threadIdx.x; i < 40; i += 32) s_h[i / 10][i % 10] = h[i % 10], s_nh[i / 10][i % 10] = -h[i % 10];
   for (int i = threadIdx.x; i < ncand * 8; i += 32) s_coef[i] = coef[i];
   for (int i = threadIdx.x; i < ncand; i += 32) s_info[i] = info[i];
   __syncwarp();
@@ -39,7 +39,7 @@ __global__ void k(const double* ab, const double* h, const double* coef, const i
   double p = 0.45 + 0.01 * grp, q = -0.6, po = 0, qo = 0, acc = 0;
   long long t0 = clock64();
   for (int r = 0; r < reps; ++r) {
-    anm::project_polygon<8, true>(s_ab, s_ab + 10, s_h[grp], s_h[grp], reinterpret_cast<const double4*>(s_coef), s_info, ncand, ncand > 30 ? 10 : 7, p, q, lane, gm, po, qo);
+    anm::project_polygon<8, true>(s_ab, s_ab + 10, s_nh[grp], s_h[grp], 0x3ffu, reinterpret_cast<const double4*>(s_coef), s_info, ncand, ncand > 30 ? 10 : 7, p, q, lane, gm, po, qo);
     p = po + 0.3; q = qo - 0.2; acc += po + qo;   // dependent calls
   }
   long long t1 = clock64();
