@@ -66,3 +66,14 @@ ms = e0.elapsed_time(e1) / (5 * R)
 n = nit.cpu().numpy()
 print("synth30: B=%d  %.3f ms/step  %.3g env-steps/s   last step: %d terminated, n_iter hist %s" % (
     B, ms, B / ms * 1e3, int(t.sum()), np.bincount(np.minimum(n, 101), minlength=102)[[0, 1, 2, 3, 4, 5, 100]]))
+# the same as one rollout launch (R steps per instance, carried state on chip)
+ro = (nb.empty(R, B, nb.O), nb.empty(R, B), nb.empty(R, B, dtype=torch.uint8))
+nb.rollout(acts, nvs, out=ro)
+torch.cuda.synchronize()
+e0.record()
+for k in range(5):
+    nb.rollout(acts, nvs, out=ro, chained=(k > 0))
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / (5 * R)
+print("synth30 rollout: B=%d  %.3f ms/step  %.3g env-steps/s" % (B, ms, B / ms * 1e3))
