@@ -104,6 +104,7 @@ struct anm_handle_s {
   } hset[2];
   int hset_next = 0;
   cudaStream_t st_in = nullptr, st_out = nullptr;
+  int64_t last_T = 1; /* steps per instance of the most recent launch (watchdog limit of the next one) */
   bool st_last_was_rollout = false; /* the compute stream's last operation was one of our rollout kernels */
   int64_t launches = 0;
 };
@@ -629,6 +630,11 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
   /* launch chaining: wait for the previous launch per instance, publish this one (anm_kernels.cuh) */
   p.seq = h->d_seq;
   p.ticket = h->d_seq + h->B + 32; /* its own 128-byte line */
+  {
+    const int64_t passes = (h->B + (int64_t)h->grid * h->gpb - 1) / ((int64_t)h->grid * h->gpb);
+    p.wd_limit_ns = 2000000000ull + 2000000ull * (uint64_t)(h->last_T * passes);
+    h->last_T = p.T > 1 ? p.T : 1;
+  }
   p.watchdog = h->wd_dev;
   const bool pdl = pdl_enabled();
   p.flags = pdl ? flags : (flags & ~ANM_LF_CHAINED);

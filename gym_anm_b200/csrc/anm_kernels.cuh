@@ -103,6 +103,7 @@ struct AnmLaunch {
   uint32_t flags;        /* ANM_LF_* */
   int32_t* phase_stats;  /* [B, 16] diagnostic builds only: SM cycles at the end of each phase -- or NULL */
   int32_t T;             /* step mode: consecutive steps in this launch; inputs / outputs are [T, B, .] (anm_rollout) */
+  uint64_t wd_limit_ns;  /* chaining watchdog: longest legitimate wait for the previous launch */
 };
 #define ANM_WD_WORDS 8
 #define ANM_LF_CHAINED 1u /* inputs do not depend on earlier work in the stream: skip griddepcontrol.wait */
@@ -128,8 +129,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
  * every CTA of its predecessor has started (and drawn), k = ticket / gridDim.x + 1 in every CTA of the launch.
  * seq[e] is published with a release store after a fence that covers the whole lane group's writes and consumed
  * with an acquire load; the carried state is read with ld.global.cg (L2), never from a possibly stale L1 line.
- * No deadlock: by the same induction every CTA that is being waited for is already running.  A wait that lasts
- * longer than 2 s writes a record to the handle's watchdog words (mapped host memory) and traps. */
+ * No deadlock: by the same induction every CTA that is being waited for is already running.  A wait that outlasts
+ * the most the previous launch can take (2 s + 2 ms per step and pass) writes a record to the handle's watchdog
+ * words (mapped host memory) and traps. */
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint64_t global_ns() {
@@ -144,7 +146,10 @@ __device__ __noinline__ void chain_timeout(uint32_t* wd, int64_t e, uint32_t wan
   }
   __trap(); /* fail loudly: the launch that owns this instance never finished with it */
 }
-__device__ __forceinline__ void seq_wait_for(const uint32_t* p, uint32_t want, uint32_t* wd, int64_t e) {
+/* `limit_ns`: 2 s plus 2 ms for every step the previous launch takes an instance through (the host knows): a chained
+ * launch may legitimately wait for the whole of a long rollout. */
+__device__ __forceinline__ void seq_wait_for(const uint32_t* p, uint32_t want, uint32_t* wd, int64_t e,
+                                             uint64_t limit_ns) {
   uint32_t v;
   uint32_t spins = 0;
   uint64_t t0 = 0;
@@ -155,7 +160,7 @@ __device__ __forceinline__ void seq_wait_for(const uint32_t* p, uint32_t want, u
     if ((++spins & 1023u) == 0u) {
       const uint64_t now = global_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) chain_timeout(wd, e, want, v);
+      else if (now - t0 > limit_ns) chain_timeout(wd, e, want, v);
     }
   }
 }
@@ -1534,7 +1539,7 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
     bool term_c = true;  /* carried: ANMEnv.terminated */
     uint32_t ep_c = 0;   /* carried: auto-reset counter */
     if (have) {
-      seq_wait_for(P.seq + e, ord - 1u, P.watchdog, e); /* the previous launch is done with this instance */
+      seq_wait_for(P.seq + e, ord - 1u, P.watchdog, e, P.wd_limit_ns); /* the previous launch is done with it */
       term_c = __ldcg(P.terminated + e) != 0;
       ep_c = __ldcg(P.episode + e);
 #pragma unroll 1

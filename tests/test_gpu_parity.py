@@ -654,6 +654,32 @@ def test_rollout_on_pinned_host_buffers():
     assert np.array_equal(obs_p, obs_q[:T].numpy()) and np.array_equal(term_p, term_q[:T].numpy())
 
 
+def test_chained_launch_may_wait_longer_than_the_watchdog_window():
+    """A chained launch waits (per instance) for the previous one; the 2 s watchdog must only fire when nothing
+    moves any more, not when the predecessor is simply long: two chained rollouts of ~2.5 s each."""
+    from gym_anm_b200.anm6 import BatchedANM6Easy
+
+    B, T = 8, 150_000
+    env = BatchedANM6Easy(B, validate_actions=False)
+    nb = env.native
+    env.reset(seed=1)
+    nb.set_autoreset_pool(env.state.clone())
+    gen = torch.Generator(device=nb.device)
+    gen.manual_seed(3)
+    lo, hi = (torch.as_tensor(x, device=nb.device) for x in (env.spec.action_low, env.spec.action_high))
+    acts = torch.rand((T, B, 6), dtype=torch.float64, device=nb.device, generator=gen) * (hi - lo) + lo
+    out = (nb.empty(T, B, 18), nb.empty(T, B), nb.empty(T, B, dtype=torch.uint8))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    nb.rollout(acts, out=out)
+    nb.rollout(acts, out=out, chained=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    assert nb.watchdog()[0] == 0
+    assert ev0.elapsed_time(ev1) > 2500.0  # the second launch did have to wait beyond the window
+    assert float(out[0].abs().sum()) > 0.0
+
+
 def test_chaining_off_same_results_subprocess():
     """ANM_PDL=0 (no programmatic dependent launch, every launch fully ordered), ANM_HOST_ROLLOUT=zc (queued host
     rollouts through zero-copy instead of the copy engines) and ANM_LANES=16 give the same results."""
