@@ -1064,7 +1064,9 @@ struct RadialNR {
     const double ybbr = active ? yv[0] : 0.0, ybbi = active ? yv[1] : 0.0, ybpr = active ? yv[2] : 0.0,
                  ybpi = active ? yv[3] : 0.0, ypbr = active ? yv[4] : 0.0, ypbi = active ? yv[5] : 0.0;
     const double pb = busp[b], qb = busq[b];
-    const int psrc = (pl < 0) ? lane : pl;
+    /* the slack bus is played by the idle lane n: it never leaves the flat start, so its V and E are exactly 1+0j
+     * (solve_load_flow.py:171) -- the children of the slack need no special case */
+    const int psrc = (pl < 0) ? n : pl;
     double th = 0.0, vm = 1.0; /* flat start (solve_load_flow.py:42) */
     int it = 0;
     n_fb = 0;
@@ -1073,7 +1075,7 @@ struct RadialNR {
     const long long t_loop0 = clock64();
     long long t_done = 0;
 #endif
-    bool done = !live, big = false;
+    int done = live ? 0 : 1, big = 0;
     double vr = 1.0, vi = 0.0, ir = 0.0, ii = 0.0, f0 = 0.0, f1 = 0.0;
     for (;;) {
       /* V_b = |V| e^{j theta}, E_b = V_b / |V_b| (:167-173, :150) */
@@ -1084,9 +1086,8 @@ struct RadialNR {
       const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN);
       const double er = sg * cs, ei = sg * sn;
       /* the parent's V, E (slack: 1+0j) */
-      double pvr = __shfl_sync(ANM_FULL, vr, psrc, LPE), pvi = __shfl_sync(ANM_FULL, vi, psrc, LPE);
-      double per = __shfl_sync(ANM_FULL, er, psrc, LPE), pei = __shfl_sync(ANM_FULL, ei, psrc, LPE);
-      if (pl < 0) { pvr = 1.0; pvi = 0.0; per = 1.0; pei = 0.0; }
+      const double pvr = __shfl_sync(ANM_FULL, vr, psrc, LPE), pvi = __shfl_sync(ANM_FULL, vi, psrc, LPE);
+      const double per = __shfl_sync(ANM_FULL, er, psrc, LPE), pei = __shfl_sync(ANM_FULL, ei, psrc, LPE);
       /* I_b = Y_bb V_b + Y_bp V_p + sum_children Y_bc V_c ; the child computes its own term Y_pc V_c */
       const double tbr = ybbr * vr - ybbi * vi, tbi = ybbr * vi + ybbi * vr; /* Y_bb V_b */
       const double tpr = ybpr * pvr - ybpi * pvi, tpi = ybpr * pvi + ybpi * pvr; /* Y_bp V_p */
@@ -1107,15 +1108,17 @@ struct RadialNR {
       f0 = (vr * ir + vi * ii) - pb;
       f1 = (vi * ir - vr * ii) - qb;
       const unsigned notok = __ballot_sync(ANM_FULL, active && !(fabs(f0) <= ANM_NR_TOL && fabs(f1) <= ANM_NR_TOL));
-      if (!done) {
-        big = (notok & gm) != 0u;
+      {
+        const int nb = ((notok & gm) != 0u) ? 1 : 0;
+        const int stop = (!nb || it >= ANM_NR_MAXIT) ? 1 : 0;
+        big = done ? big : nb;
+        it += (done | stop) ? 0 : 1;
 #if ANM_DIAG
-        if (!big || it >= ANM_NR_MAXIT) done = true, t_done = clock64(); else ++it;
-#else
-        if (!big || it >= ANM_NR_MAXIT) done = true; else ++it;
+        if (!done && stop) t_done = clock64();
 #endif
+        done |= stop;
       }
-      if (__all_sync(ANM_FULL, done)) break;
+      if (__all_sync(ANM_FULL, done != 0)) break;
 
       /* Jacobian blocks, rows (dP, dQ) x columns (dtheta, d|V|) */
       const double jr = -vi, ji = vr; /* j V_b */
