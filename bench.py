@@ -262,9 +262,6 @@ def run_ours(args):
     ring = torch.rand((RING, B, 6), dtype=torch.float64, device=dev, generator=gen) * (hi - lo) + lo
     ring_host = ring.cpu().pin_memory()  # e2e leg: the agent's actions live in pinned host memory
     obs, rew, term = nb.empty(B, 18), nb.empty(B), nb.empty(B, dtype=torch.uint8)
-    obs_h = torch.empty(B, 18, dtype=torch.float64).pin_memory()
-    rew_h = torch.empty(B, dtype=torch.float64).pin_memory()
-    term_h = torch.empty(B, dtype=torch.uint8).pin_memory()
 
     # ---- warm-up (eager launches) ---------------------------------------------------------------------
     for t in range(W):
