@@ -113,6 +113,9 @@ _PROTOS = {
     "anm_destroy": (C.c_int, [C.c_void_p]),
     "anm_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     "anm_reset": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "anm_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "anm_reset_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 3 + [C.c_void_p]),
+    "anm_debug_rng": (C.c_int, [C.c_uint64, C.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p]),
     "anm_step": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(StepExtras), C.c_void_p]),
     "anm_rollout": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p]),
     "anm_set_autoreset_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),

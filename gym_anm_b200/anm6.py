@@ -10,15 +10,24 @@ uniform(soc_min, soc_max) (anm6_easy.py:25-52), and a successful reset then cons
 integers(1, 365) draw (ANM6.reset -> random_date, anm6.py:138, anm6_env/utils.py:22), so
 the per-env PCG64 streams stay aligned with the reference's.
 """
+import os
+
 import numpy as np
 import torch
 
-from .anm_env import BatchedANMEnv
+from .anm_env import N_INIT_STATES_MAX, BatchedANMEnv
+from .errors import EnvInitializationError
 from .networks import anm6_network, anm6easy_tables
 
 
 class BatchedANM6Easy(BatchedANMEnv):
-    def __init__(self, num_envs=1, device=None, seed=None, validate_actions=True, env_offset=0):
+    """`device_init=True`: `reset()` draws the initial states on the GPU (anm_seed / anm_reset_seeded) from per-instance
+    PCG64 streams that are bit-identical to the NumPy Generators of the default path -- same observations for the
+    same seeds, no host round trip per retry; `np_random` then no longer reflects the streams' positions."""
+
+    def __init__(self, num_envs=1, device=None, seed=None, validate_actions=True, env_offset=0, device_init=False):
+        self.device_init = bool(device_init)
+        self._device_seeded = False
         self.P_loads, self.P_maxs = anm6easy_tables()
         delta_t = 0.25
         table = np.ascontiguousarray(np.vstack((self.P_loads, self.P_maxs)).T)
@@ -47,7 +56,35 @@ class BatchedANM6Easy(BatchedANMEnv):
         aux = int((s_t[-1] + 1) % (24 / self.delta_t))
         return np.array([p[aux] for p in self.P_loads] + [p[aux] for p in self.P_maxs] + [aux], dtype=np.float64)
 
+    def _reset_on_device(self, seed, options, mask):
+        """ANMEnv.reset (anm_env.py:235-311) + ANM6.reset's date draw (anm6.py:138) without leaving the GPU."""
+        if seed is not None:
+            self.native.seed(int(seed) + self.env_offset)
+            self._device_seeded = True
+        elif not self._device_seeded:
+            self.native.seed(int.from_bytes(os.urandom(7), "little"))
+            self._device_seeded = True
+        date_draw = not (options is not None and "date_init" in options)
+        conv = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        m = None if mask is None else torch.as_tensor(np.asarray(torch.as_tensor(mask).cpu(), dtype=bool), device=self.device)
+        self.native.reset_seeded(m, N_INIT_STATES_MAX, date_draw, obs=self._obs, state=self.state, converged=conv)
+        ok = conv.bool() if m is None else (conv.bool() | ~m)
+        if not bool(ok.all()):
+            raise EnvInitializationError(
+                "No non-terminal state found out of %d initial states for %d environment(s) of %s"
+                % (N_INIT_STATES_MAX, int((~ok).sum()), type(self).__name__)
+            )
+        sel = slice(None) if m is None else m
+        if mask is None:
+            self.timestep = 0
+        self._term_u8[sel] = 0
+        self.e_loss[sel] = 0.0
+        self.penalty[sel] = 0.0
+        return self._observe(), {}
+
     def reset(self, *, seed=None, options=None, mask=None):
+        if self.device_init:
+            return self._reset_on_device(seed, options, mask)
         obs, info = super().reset(seed=seed, options=options, mask=mask)
         # ANM6.reset draws the rendering start date from the same stream (anm6.py:138).
         idx = range(self.num_envs) if mask is None else np.flatnonzero(np.asarray(torch.as_tensor(mask).cpu(), dtype=bool))

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "anm_kernels.cuh"
+#include "anm_seeded_reset.cuh"
 
 namespace {
 
@@ -83,6 +84,10 @@ struct anm_handle_s {
   uint32_t* d_episode = nullptr;
   uint32_t* d_seq = nullptr; /* [B + 64] per-instance launch ordinals, then the ticket counter (launch chaining,
                                 anm_kernels.cuh) */
+  AnmPcg64* d_rng = nullptr; /* [B] per-instance random streams (anm_seed / anm_reset_seeded) */
+  bool seeded = false;
+  uint8_t *d_need = nullptr, *d_conv_tmp = nullptr; /* seeded reset: still looking for an initial state / last attempt */
+  int *d_remaining = nullptr, *h_remaining = nullptr;
   uint32_t* wd_host = nullptr; /* [ANM_WD_WORDS] mapped host memory: chaining watchdog record */
   uint32_t* wd_dev = nullptr;
   const double* pool = nullptr;
@@ -760,6 +765,8 @@ int anm_destroy(anm_handle h) {
   DeviceGuard guard(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_soc); cudaFree(h->d_aux); cudaFree(h->d_term); cudaFree(h->d_episode);
   cudaFree(h->d_seq);
+  cudaFree(h->d_rng); cudaFree(h->d_need); cudaFree(h->d_conv_tmp); cudaFree(h->d_remaining);
+  if (h->h_remaining) cudaFreeHost(h->h_remaining);
   if (h->wd_host) cudaFreeHost(h->wd_host);
   cudaFree(h->s_action); cudaFree(h->s_nv); cudaFree(h->s_obs); cudaFree(h->s_reward); cudaFree(h->s_s0);
   cudaFree(h->s_state); cudaFree(h->s_term); cudaFree(h->s_mask);
@@ -837,6 +844,62 @@ int anm_rollout(anm_handle h, int64_t T, const double* action, const double* nex
   p.T = (int32_t)T;
   p.action = action; p.next_vars = next_vars; p.obs = obs; p.reward = reward; p.term_out = terminated;
   return launch(h, p, (cudaStream_t)stream, (flags & ANM_STEP_CHAINED) ? ANM_LF_CHAINED : 0u);
+}
+
+int anm_seed(anm_handle h, uint64_t seed_first) {
+  if (!h) return fail(ANM_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  std::vector<AnmPcg64> host((size_t)h->B);
+  for (int64_t e = 0; e < h->B; ++e) anm_pcg_seed(host[(size_t)e], seed_first + (uint64_t)e);
+  if (!h->d_rng) CUDA_TRY(cudaMalloc((void**)&h->d_rng, (size_t)h->B * sizeof(AnmPcg64)));
+  CUDA_TRY(cudaDeviceSynchronize()); /* setup-time call: no launch of this handle may still be using the streams */
+  CUDA_TRY(cudaMemcpy(h->d_rng, host.data(), (size_t)h->B * sizeof(AnmPcg64), cudaMemcpyHostToDevice));
+  h->seeded = true;
+  return ANM_OK;
+}
+
+int anm_reset_seeded(anm_handle h, const uint8_t* mask, int32_t max_tries, int32_t date_draw, double* obs, double* state,
+                     uint8_t* converged, void* stream) {
+  if (!h || !obs || !converged) return fail(ANM_E_INVALID, "anm_reset_seeded: null argument");
+  if (!h->seeded) return fail(ANM_E_INVALID, "anm_reset_seeded: call anm_seed first");
+  if (h->H.table_len == 0 || h->H.K < 1)
+    return fail(ANM_E_UNSUPPORTED, "anm_reset_seeded: needs the built-in next_vars table (ANM6Easy-style init_state)");
+  if (max_tries < 1) return fail(ANM_E_INVALID, "anm_reset_seeded: max_tries must be >= 1");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = (size_t)h->B;
+  if (!h->d_need) {
+    CUDA_TRY(cudaMalloc((void**)&h->d_need, B));
+    CUDA_TRY(cudaMalloc((void**)&h->d_conv_tmp, B));
+    CUDA_TRY(cudaMalloc((void**)&h->d_remaining, sizeof(int)));
+    CUDA_TRY(cudaHostAlloc((void**)&h->h_remaining, sizeof(int), cudaHostAllocDefault));
+  }
+  const int threads = 128, blocks = (int)((B + threads - 1) / threads);
+  /* Round k: instances whose previous attempt converged are finished (date draw), the others draw a new initial
+   * state; the host looks at the number of draws (one stream synchronisation per round, typically two or three
+   * rounds) and stops when nobody drew; then the ordinary reset launch applies the drawn states. */
+  for (int round = 0; round <= max_tries; ++round) {
+    CUDA_TRY(cudaMemsetAsync(h->d_remaining, 0, sizeof(int), st));
+    anm::seeded_draw_kernel<<<blocks, threads, 0, st>>>(h->d_blob, h->B, h->d_rng, h->d_need, mask, round == 0,
+                                                        round == max_tries, h->d_conv_tmp, converged, date_draw, h->s_s0,
+                                                        h->d_remaining);
+    CUDA_TRY(cudaPeekAtLastError());
+    CUDA_TRY(cudaMemcpyAsync(h->h_remaining, h->d_remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (*h->h_remaining == 0) break;
+    int rc = anm_reset(h, h->s_s0, h->d_need, obs, state, h->d_conv_tmp, stream);
+    if (rc) return rc;
+  }
+  return ANM_OK;
+}
+
+int anm_debug_rng(uint64_t seed, int32_t n, const int32_t* kind, const double* lo, const double* hi, double* out) {
+  if (n < 0 || (n > 0 && (!kind || !lo || !hi || !out))) return fail(ANM_E_INVALID, "anm_debug_rng: bad argument");
+  AnmPcg64 r;
+  anm_pcg_seed(r, seed);
+  for (int32_t i = 0; i < n; ++i)
+    out[i] = kind[i] ? anm_rng_uniform(r, lo[i], hi[i]) : (double)anm_rng_integers(r, (int64_t)lo[i], (int64_t)hi[i]);
+  return ANM_OK;
 }
 
 int anm_set_autoreset_pool(anm_handle h, const double* pool, int64_t pool_size) {

@@ -85,6 +85,21 @@ class NativeBatch:
                                        self._stream()), self.lib)  # fmt: skip
         return obs, state, converged
 
+    def seed(self, seed_first):
+        """Instance e gets the stream Generator(PCG64(SeedSequence(seed_first + e))), kept on the device."""
+        _capi.check(self.lib.anm_seed(self.h, C.c_uint64(int(seed_first))), self.lib)
+
+    def reset_seeded(self, mask=None, max_tries=100, date_draw=True, obs=None, state=None, converged=None):
+        """ANMEnv.reset with ANM6Easy's init_state drawn on the device from the instances' own streams."""
+        obs = self.empty(self.B, self.O) if obs is None else obs
+        state = self.empty(self.B, self.S) if state is None else state
+        converged = torch.zeros(self.B, dtype=torch.uint8, device=self.device) if converged is None else converged
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        _capi.check(self.lib.anm_reset_seeded(self.h, _ptr(mask), int(max_tries), 1 if date_draw else 0, _ptr(obs),
+                                              _ptr(state), _ptr(converged), self._stream()), self.lib)  # fmt: skip
+        return obs, state, converged
+
     def step(self, action, next_vars=None, out=None, extras=None, chained=False):
         """out = (obs, reward, terminated) preallocated tensors or None; extras = dict of
         optional preallocated tensors among state / e_loss / penalty / n_iter / full_state.

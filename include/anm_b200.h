@@ -183,6 +183,23 @@ int anm_get_sizes(anm_handle h, anm_sizes* out);
 int anm_reset(anm_handle h, const double* s0_dev, const uint8_t* mask_dev, double* obs_dev,
               double* state_dev_or_null, uint8_t* converged_dev, void* stream);
 
+/* Device-side seeded reset.  anm_seed gives instance e the random stream
+ * np.random.Generator(PCG64(SeedSequence(seed_first + e))) -- what Gymnasium's Env.reset(seed=) creates
+ * (anm_env.py:116, 257) -- kept in device memory.  anm_reset_seeded is the whole ANMEnv.reset loop
+ * (anm_env.py:266-289) for the selected instances of an environment whose init_state() is
+ * ANM6Easy's (anm6_easy.py:25-52: needs the built-in table): draw an initial state from the instance's
+ * stream, apply it, retry up to max_tries times until the power flow converges; date_draw != 0
+ * then consumes the integers(1, 365) of ANM6.reset (anm6.py:138).  converged[b] = 0 for a selected
+ * instance that found no convergent state.  Bit-identical to the host-drawn path (anm_reset with s0
+ * from NumPy) for the same seeds. */
+int anm_seed(anm_handle h, uint64_t seed_first);
+int anm_reset_seeded(anm_handle h, const uint8_t* mask_dev_or_null, int32_t max_tries, int32_t date_draw,
+                     double* obs_dev, double* state_dev_or_null, uint8_t* converged_dev, void* stream);
+/* Host-only check of the stream restatement (no device needed): the first n draws of
+ * PCG64(SeedSequence(seed)); kind[i] = 0: integers(lo[i], hi[i]), 1: uniform(lo[i], hi[i]). */
+int anm_debug_rng(uint64_t seed, int32_t n, const int32_t* kind, const double* lo, const double* hi,
+                  double* out);
+
 /* ANMEnv.step body for a batch (anm_env.py:333-453).  action [B, n_action] (MW / MVAr,
  * layout [P_gen.. | Q_gen.. | P_des.. | Q_des..]); next_vars [B, n_next_vars] or NULL to
  * use the built-in table.  Already-terminated envs return zeros / 0.0 / 1. */

@@ -654,6 +654,38 @@ def test_rollout_on_pinned_host_buffers():
     assert np.array_equal(obs_p, obs_q[:T].numpy()) and np.array_equal(term_p, term_q[:T].numpy())
 
 
+def test_device_side_seeded_reset_matches_host_rng_path():
+    """anm_seed + anm_reset_seeded (init_state drawn on the GPU from per-instance PCG64(SeedSequence(seed + i))
+    streams, retry loop and ANM6.reset's date draw included) == the default path that draws with NumPy Generators on
+    the host: bit-identical observations / states, also for later partial resets, and equal to the reference's
+    reset(seed=i) goldens."""
+    from gym_anm_b200.anm6 import BatchedANM6Easy
+
+    B = 1024
+    host_env = BatchedANM6Easy(B, validate_actions=False)
+    dev_env = BatchedANM6Easy(B, validate_actions=False, device_init=True)
+    obs_h, _ = host_env.reset(seed=0)
+    obs_d, _ = dev_env.reset(seed=0)
+    bad = (obs_h != obs_d).any(dim=1).nonzero().flatten().tolist()
+    assert not bad, (len(bad), bad[:5], obs_h[bad[0]].tolist(), obs_d[bad[0]].tolist())
+    assert torch.equal(host_env.state, dev_env.state)
+    for i in range(3):
+        assert rel_err(obs_d[i].cpu().numpy(), load("anm6easy_traj_seed%d.npz" % i)["reset_obs"][0]) < RTOL
+    rng = np.random.default_rng(4)
+    for rnd in range(3):
+        for t in range(12):
+            a = rng.uniform(host_env.spec.action_low, host_env.spec.action_high, size=(B, 6))
+            oh, rh, th, _, _ = host_env.step(a)
+            od, rd, td, _, _ = dev_env.step(a)
+        assert torch.equal(oh, od) and torch.equal(th, td)
+        mask = th.clone()
+        mask[rnd::7] = True  # the terminated ones and a few others
+        oh, _ = host_env.reset(mask=mask)
+        od, _ = dev_env.reset(mask=mask)
+        assert torch.equal(oh, od) and torch.equal(host_env.state, dev_env.state), rnd
+    assert int(th.sum()) >= 0
+
+
 def test_chained_launch_may_wait_longer_than_the_watchdog_window():
     """A chained launch waits (per instance) for the previous one; the 2 s watchdog must only fire when nothing
     moves any more, not when the predecessor is simply long: two chained rollouts of ~2.5 s each."""

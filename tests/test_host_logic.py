@@ -130,6 +130,24 @@ def test_capi_library_exports_every_declared_symbol():
     assert rc != 0 and lib.anm_last_error()
 
 
+def test_rng_streams_match_numpy():
+    """csrc/anm_rng.h (SeedSequence -> PCG64 -> integers / uniform, the draws of ANM6Easy.init_state and ANM6.reset)
+    against NumPy itself, bit for bit, through the host-only entry point anm_debug_rng."""
+    lib = _capi.load_library()
+    kinds = np.array([0, 1, 1, 1, 0, 1, 1, 1, 0, 0, 1, 0], dtype=np.int32)
+    lo = np.array([0, -0.3, -0.5, 0, 0, -0.3, -0.5, 0, 1, 0, 2.0, 5])
+    hi = np.array([96, 0.3, 0.5, 1, 96, 0.3, 0.5, 1, 365, 1 << 20, 7.5, 6])
+    for seed in list(range(300)) + [2020 + 4095, 2**32 - 1, 2**32, 2**32 + 7, 2**63 + 1]:
+        out = np.zeros(len(kinds))
+        rc = lib.anm_debug_rng(ctypes.c_uint64(seed), len(kinds), kinds.ctypes.data_as(_capi.c_int32_p),
+                               lo.ctypes.data_as(_capi.c_double_p), hi.ctypes.data_as(_capi.c_double_p),
+                               out.ctypes.data_as(_capi.c_double_p))  # fmt: skip
+        assert rc == 0
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        want = [float(g.integers(int(a), int(b))) if k == 0 else g.uniform(a, b) for k, a, b in zip(kinds, lo, hi)]
+        assert np.array_equal(out, np.array(want)), seed
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "gym_anm_b200")
     for dirpath, _, files in os.walk(pkg):
