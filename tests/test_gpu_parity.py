@@ -448,6 +448,57 @@ def test_radial_tree_vs_oracle(stress):
     assert (n_div > 0) == (stress > 1.0)
 
 
+def test_rollout_custom_next_vars_wide_action_vs_oracle():
+    """Rollout and step on a custom radial network with caller-supplied next_vars and an action row wider than the
+    lane group (12 entries on 8 lanes: the non-prefetched unpack path), against the C oracle and against each other."""
+    import anm_oracle
+    from gym_anm_b200.env_spec import HostEnvSpec
+    from gym_anm_b200.native import NativeBatch
+
+    N_ = None
+    net = _tree_network()
+    extra = np.array([
+        [9, 4, 2, N_, 12, 0, 12, -12, 8, N_, 6, -6, N_, N_, N_],
+        [10, 2, 3, N_, 8, -8, 8, -8, 5, -5, 4, -4, 30, 0, 0.92],
+    ], dtype=object)
+    net["device"] = np.vstack([net["device"], extra])
+    spec = HostEnvSpec(net, "state", 1, 0.25, 0.9, 100, np.array([[0, 1000]]), (1, 100))
+    cn = spec.cn
+    B, T = 512, 24
+    A = len(spec.action_low)
+    assert A == 12
+    nb, nb2, cpu = NativeBatch(spec, B), NativeBatch(spec, B), anm_oracle.OracleEnv(spec, B)
+    assert nb.sizes["lanes_per_env"] == 8
+    rng = np.random.default_rng(12)
+    D, ns = cn.N_device, cn.N_des
+    pos = {d: k for k, d in enumerate(cn.devices)}
+    s0 = np.zeros((B, spec.state_N))
+    for i in cn.load_ids:
+        s0[:, pos[i]] = rng.uniform(cn.devices[i].p_min * 100, 0, B)
+    for k, i in enumerate(cn.gen_ids):
+        s0[:, pos[i]] = rng.uniform(0, cn.devices[i].p_max * 100, B)
+        s0[:, 2 * D + ns + k] = rng.uniform(0, cn.devices[i].p_max * 100, B)
+    for k, i in enumerate(cn.des_ids):
+        s0[:, 2 * D + k] = rng.uniform(0, cn.devices[i].soc_max * 100, B)
+    _, _, conv_c = cpu.reset(s0)
+    for n in (nb, nb2):
+        _, _, conv_g = n.reset(s0)
+        assert np.array_equal(conv_g.cpu().numpy().astype(bool), conv_c)
+    acts = rng.uniform(spec.action_low, spec.action_high, size=(T, B, A))
+    nvs = np.concatenate([rng.uniform([cn.devices[i].p_min * 100 for i in cn.load_ids], 0, (T, B, cn.N_load)),
+                          rng.uniform(0, [cn.devices[i].p_max * 100 for i in cn.gen_ids], (T, B, cn.N_non_slack_gen)),
+                          np.broadcast_to(np.arange(1, T + 1, dtype=np.float64)[:, None, None], (T, B, 1))], axis=2)  # fmt: skip
+    obs_r, rew_r, term_r = nb.rollout(acts, nvs)
+    n_term = 0
+    for t in range(T):
+        obs_s, rew_s, term_s = nb2.step(acts[t], nvs[t])
+        obs_c, r_c, term_c, _ = cpu.step(acts[t], nvs[t])
+        assert torch.equal(obs_s, obs_r[t]) and torch.equal(rew_s, rew_r[t]) and torch.equal(term_s, term_r[t]), t
+        assert np.array_equal(term_s.cpu().numpy().astype(bool), term_c), t
+        assert rel_err(obs_s.cpu().numpy(), obs_c) < RTOL and rel_err(rew_s.cpu().numpy(), r_c) < RTOL, t
+        n_term += int(term_c.sum())
+
+
 def test_mpc_constant_agent_drives_batched_env_config5():
     """BASELINE config 5 in small: MPCAgentConstant(planning_steps=10, safety_margin=0.96)
     (examples/mpc_constant.py:21) picks the actions from the batched env's own state; the same action
