@@ -1060,6 +1060,7 @@ struct RadialNR {
       const int cb = active ? C.rad_child[bl * ANM_RAD_MAXC + s] : -1;
       csrc[s] = (cb < 0) ? n : cb;
     }
+    double2* xbuf = reinterpret_cast<double2*>(ws + H.w_J); /* [LPE][3] exchange slots of the tree levels */
     const double* yv = C.rad_y + 6 * bl;
     const double ybbr = active ? yv[0] : 0.0, ybbi = active ? yv[1] : 0.0, ybpr = active ? yv[2] : 0.0,
                  ybpi = active ? yv[3] : 0.0, ypbr = active ? yv[4] : 0.0, ypbi = active ? yv[5] : 0.0;
@@ -1170,15 +1171,25 @@ struct RadialNR {
         const double c10 = (u10 * t00 + u11 * t10) * rdm, c11 = (u10 * t01 + u11 * t11) * rdm;
         const double cf0 = (u00 * tf0 + u01 * tf1) * rdm, cf1 = (u10 * tf0 + u11 * tf1) * rdm;
         /* a parent pulls from its children (non-zero exactly when they are at this level); an empty slot pulls
-         * zeros from the idle lane */
+         * zeros from the idle lane.  Six doubles per child: through shared memory (three 16-byte stores, three
+         * 16-byte loads per slot) instead of twelve shuffles per slot. */
+        {
+          double2* mine2 = xbuf + 3 * lane;
+          mine2[0] = make_double2(c00, c01);
+          mine2[1] = make_double2(c10, c11);
+          mine2[2] = make_double2(cf0, cf1);
+        }
+        __syncwarp();
 #pragma unroll
         for (int s = 0; s < ANM_RAD_MAXC; ++s) {
           if (s < maxc) { /* warp-uniform */
-            d00 -= __shfl_sync(ANM_FULL, c00, csrc[s], LPE); d01 -= __shfl_sync(ANM_FULL, c01, csrc[s], LPE);
-            d10 -= __shfl_sync(ANM_FULL, c10, csrc[s], LPE); d11 -= __shfl_sync(ANM_FULL, c11, csrc[s], LPE);
-            r0 -= __shfl_sync(ANM_FULL, cf0, csrc[s], LPE);  r1 -= __shfl_sync(ANM_FULL, cf1, csrc[s], LPE);
+            const double2* ch = xbuf + 3 * csrc[s];
+            const double2 a0 = ch[0], a1 = ch[1], a2 = ch[2];
+            d00 -= a0.x; d01 -= a0.y; d10 -= a1.x; d11 -= a1.y;
+            r0 -= a2.x;  r1 -= a2.y;
           }
         }
+        __syncwarp(); /* the next level overwrites the exchange slots */
       }
       /* root level (children of the slack): plain 2x2 solves */
       double x0 = 0.0, x1 = 0.0;

@@ -31,14 +31,15 @@ oA = rng.uniform(env.spec.action_low, env.spec.action_high, size=(B, 6))[ok]
 def probe(label, soc, aux, act):
     n = len(soc)
     e = BatchedANM6Easy(n, validate_actions=False)
-    stats = torch.zeros(n, 4, dtype=torch.int32, device="cuda")
+    stats_all = torch.zeros(n * 20, dtype=torch.int32, device="cuda")  # diagnostic builds: [n, 4] + [n, 16] phase stamps
+    stats = stats_all[: 4 * n].view(n, 4)
     nit = torch.zeros(n, dtype=torch.int32, device="cuda")
     obs, rew, term = e.native.empty(n, 18), e.native.empty(n), e.native.empty(n, dtype=torch.uint8)
     z = torch.zeros(n, dtype=torch.uint8, device="cuda")
     soc, aux, act = (torch.as_tensor(v, device="cuda").contiguous() for v in (soc, aux, act))
     for rep in range(3):
         e.native.set_state(soc, aux, z)
-        e.native.step(act, None, out=(obs, rew, term), extras={"solver_stats": stats, "n_iter": nit})
+        e.native.step(act, None, out=(obs, rew, term), extras={"solver_stats": stats_all, "n_iter": nit})
     torch.cuda.synchronize()
     st, ni = stats.cpu().numpy().astype(np.int64), nit.cpu().numpy()
     d = ni >= 100
