@@ -146,6 +146,8 @@ static int choose_solver(int n_bus, bool is_radial) {
 }
 static int solver_for(const AnmConstHeader& H) { return H.solver; }
 
+static int lanes_for(const AnmConstHeader& H); /* below, with the kernel table */
+
 int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHeader& H, std::vector<unsigned char>& out) {
   const int N = net->n_bus, D = net->n_dev, L = net->n_branch, K = env->K;
   if (N < 2 || N > 64) return fail(ANM_E_UNSUPPORTED, "n_bus=%d not in [2, 64]", N);
@@ -501,7 +503,7 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_devp = take(D); H.w_devq = take(D); H.w_ppot = take(D); H.w_busp = take(N); H.w_busq = take(N);
     H.w_x = take(M); H.w_vre = take(N); H.w_vim = take(N); H.w_ere = take(N); H.w_eim = take(N);
     H.w_ire = take(N); H.w_iim = take(N);
-    H.w_J = take(H.solver == 4 ? 0 : (H.solver == 2 ? 6 * 16 /* RadialNR: exchange slots, 6 doubles x <= 16 lanes */
+    H.w_J = take(H.solver == 4 ? 0 : (H.solver == 2 ? 2 * 6 * lanes_for(H) /* RadialNR: two sets of exchange slots */
                                                                  : M * (M + 1))); H.w_rowh = take(2 * H.n_ctrl * ANM_MAX_ROWS + H.n_ctrl); /* -h / -inf, h / 0, finite-row mask per device */
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);

@@ -1061,6 +1061,7 @@ struct RadialNR {
       csrc[s] = (cb < 0) ? n : cb;
     }
     double2* xbuf = reinterpret_cast<double2*>(ws + H.w_J); /* [LPE][3] exchange slots of the tree levels */
+    double2* vbuf = xbuf + 3 * LPE;                         /* [LPE][3] exchange slots of the residual evaluation */
     const double* yv = C.rad_y + 6 * bl;
     const double ybbr = active ? yv[0] : 0.0, ybbi = active ? yv[1] : 0.0, ybpr = active ? yv[2] : 0.0,
                  ybpi = active ? yv[3] : 0.0, ypbr = active ? yv[4] : 0.0, ypbi = active ? yv[5] : 0.0;
@@ -1086,20 +1087,29 @@ struct RadialNR {
       vi = vm * sn;
       const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN);
       const double er = sg * cs, ei = sg * sn;
-      /* the parent's V, E (slack: 1+0j) */
-      const double pvr = __shfl_sync(ANM_FULL, vr, psrc, LPE), pvi = __shfl_sync(ANM_FULL, vi, psrc, LPE);
-      const double per = __shfl_sync(ANM_FULL, er, psrc, LPE), pei = __shfl_sync(ANM_FULL, ei, psrc, LPE);
-      /* I_b = Y_bb V_b + Y_bp V_p + sum_children Y_bc V_c ; the child computes its own term Y_pc V_c */
+      /* Every bus publishes (V, E) and its term Y_pb V_b of the parent's current in its exchange slot; then it
+       * reads its parent's V, E (slack: the idle lane, 1+0j) and its children's terms.
+       * I_b = Y_bb V_b + Y_bp V_p + sum_children Y_bc V_c */
       const double tbr = ybbr * vr - ybbi * vi, tbi = ybbr * vi + ybbi * vr; /* Y_bb V_b */
-      const double tpr = ybpr * pvr - ybpi * pvi, tpi = ybpr * pvi + ybpi * pvr; /* Y_bp V_p */
       const double cr = ypbr * vr - ypbi * vi, ci = ypbr * vi + ypbi * vr;     /* Y_pb V_b, for the parent */
+      {
+        double2* mine2 = vbuf + 3 * lane;
+        mine2[0] = make_double2(vr, vi);
+        mine2[1] = make_double2(er, ei);
+        mine2[2] = make_double2(cr, ci);
+      }
+      __syncwarp();
+      const double2 pv = vbuf[3 * psrc], pe2 = vbuf[3 * psrc + 1];
+      const double pvr = pv.x, pvi = pv.y, per = pe2.x, pei = pe2.y;
+      const double tpr = ybpr * pvr - ybpi * pvi, tpi = ybpr * pvi + ybpi * pvr; /* Y_bp V_p */
       ir = tbr + tpr;
       ii = tbi + tpi;
 #pragma unroll
       for (int s = 0; s < ANM_RAD_MAXC; ++s) {
         if (s < maxc) { /* warp-uniform */
-          ir += __shfl_sync(ANM_FULL, cr, csrc[s], LPE);
-          ii += __shfl_sync(ANM_FULL, ci, csrc[s], LPE);
+          const double2 cc = vbuf[3 * csrc[s] + 2];
+          ir += cc.x;
+          ii += cc.y;
         }
       }
       /* mismatch rows (:84-120): S_b = V_b conj(I_b).  One vote per iteration: `notok` is set by an entry above the
@@ -1210,6 +1220,7 @@ struct RadialNR {
         x0 = mine ? (d11 * q0 - d01 * q1) * rdet : x0;
         x1 = mine ? (d00 * q1 - d10 * q0) * rdet : x1;
       }
+      __syncwarp(); /* this iteration's reads of the exchange slots are done */
       if (active && !done) { /* x <- x - J^{-1} F (:220) */
         th -= x0;
         vm -= x1;
