@@ -262,15 +262,16 @@ int anm_host_sync(anm_handle h);
 /* Queued anm_rollout on host buffers: [T, B, .] arrays (pinned memory for full speed; pageable works).
  * The actions are uploaded and the results downloaded by the copy engines through device staging
  * buffers of the handle while the kernels of consecutive calls run back to back; the outputs are
- * valid after anm_host_sync.  The call returns once the upload of its inputs has completed, so the
+ * valid after anm_host_sync (or, for every call but the most recent one, after
+ * anm_host_sync_previous).  The call returns once the upload of its inputs has completed, so the
  * caller may reuse the action arrays at once.  (ANM_HOST_ROLLOUT=zc: the kernel reads / writes the
- * pinned buffers directly instead.) */
-/* Wait until every queued rollout except the most recent one has delivered its outputs (the consumer
- * works on call i-1 while call i runs: no pipeline drain). */
-int anm_host_sync_previous(anm_handle h);
+ * pinned buffers directly instead; all of them must then be pinned.) */
 int anm_rollout_host_async(anm_handle h, int64_t T, const double* action_host,
                            const double* next_vars_host_or_null, double* obs_host, double* reward_host,
                            uint8_t* terminated_host);
+/* Wait until every queued rollout except the most recent one has delivered its outputs (the consumer
+ * works on call i-1 while call i runs: no pipeline drain). */
+int anm_host_sync_previous(anm_handle h);
 
 /* The handle's own cudaStream_t (the one the *_host calls run on), e.g. to record events. */
 void* anm_host_stream(anm_handle h);
@@ -278,7 +279,8 @@ void* anm_host_stream(anm_handle h);
 /* Number of kernels this library has launched on behalf of `h` (for bench accounting). */
 int64_t anm_launch_count(anm_handle h);
 
-/* Diagnostic: a chained launch that waited more than 2 s for an instance records
+/* Diagnostic: a chained launch that waited for an instance longer than the previous launch can
+ * possibly take (2 s + 2 ms per step and pass) records
  * [1, instance, ordinal waited for, ordinal seen, CTA, grid, thread, 0] here (host memory, readable
  * even after the CUDA context reported the launch failure) and traps; all zeros otherwise. */
 int anm_watchdog(anm_handle h, uint32_t* out8);
