@@ -206,6 +206,9 @@ class BatchedANMEnv:
 
     # ---- checkpoint / resume of the carried state ------------------------------
     def state_dict(self):
+        """The carried state of every instance (SoC, aux, terminated, state vector, timestep).  The random streams
+        are not part of it: the host Generators (`np_random`) can be pickled by the caller; the device-side streams of
+        `device_init=True` environments are re-created by `reset(seed=...)`."""
         soc, aux, term = self.native.get_state()
         return {"soc": soc, "aux": aux, "terminated": term, "state": self.state.clone(), "timestep": self.timestep}
 
