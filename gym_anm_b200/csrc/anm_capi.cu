@@ -8,6 +8,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdarg>
@@ -147,6 +148,37 @@ static int choose_solver(int n_bus, bool is_radial) {
 static int solver_for(const AnmConstHeader& H) { return H.solver; }
 
 static int lanes_for(const AnmConstHeader& H); /* below, with the kernel table */
+
+/* The candidates of the exact projection on the polygon {a_k x + b_k y <= h_k, k < R} (project_polygon,
+ * anm_kernels.cuh) as affine maps of (p, q, h[s1], h[s2]): the point itself, its projection on each row's line, each
+ * pairwise intersection, in the order of oracle/shims/cvxpy/_projection.py; parallel pairs are dropped.  Appends
+ * info = s1 | s2 << 8 | need << 16 and the eight coefficients kx[4], ky[4] of every candidate. */
+static void build_candidates(const double* a, const double* b, int R, std::vector<int>& cinfo, std::vector<double>& ccoef) {
+  auto push = [&](int s1, int s2, unsigned need, const double (&kx)[4], const double (&ky)[4]) {
+    cinfo.push_back(s1 | (s2 << 8) | (int)(need << 16));
+    ccoef.insert(ccoef.end(), kx, kx + 4);
+    ccoef.insert(ccoef.end(), ky, ky + 4);
+  };
+  push(0, 0, 0u, {1, 0, 0, 0}, {0, 1, 0, 0});
+  for (int k = 0; k < R; ++k) {
+    if (a[k] == 0.0 && b[k] == 0.0) continue;
+    if (b[k] == 0.0) {
+      push(k, k, 1u << k, {0, 0, 1.0 / a[k], 0}, {0, 1, 0, 0});
+    } else if (a[k] == 0.0) {
+      push(k, k, 1u << k, {1, 0, 0, 0}, {0, 0, 1.0 / b[k], 0});
+    } else {
+      const double w = 1.0 / (a[k] * a[k] + b[k] * b[k]);
+      push(k, k, 1u << k, {1.0 - a[k] * a[k] * w, -a[k] * b[k] * w, a[k] * w, 0},
+           {-a[k] * b[k] * w, 1.0 - b[k] * b[k] * w, b[k] * w, 0});
+    }
+  }
+  for (int j = 1; j < R; ++j)
+    for (int i = 0; i < j; ++i) {
+      const double det = a[i] * b[j] - a[j] * b[i];
+      if (det == 0.0) continue;
+      push(i, j, (1u << i) | (1u << j), {0, 0, b[j] / det, -b[i] / det}, {0, 0, -a[j] / det, a[i] / det});
+    }
+}
 
 int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHeader& H, std::vector<unsigned char>& out) {
   const int N = net->n_bus, D = net->n_dev, L = net->n_branch, K = env->K;
@@ -293,39 +325,12 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
       }
       H.o_ctrl_fin = bb.add(fin);
     }
-    /* candidate_table: every candidate of the exact projection (project_polygon, anm_kernels.cuh) as an affine map
-     * of (p, q, h[s1], h[s2]) -- the point, its projection on each row's line, each pairwise intersection, in the
-     * order of oracle/shims/cvxpy/_projection.py (ties go to the lowest candidate); parallel pairs are dropped. */
+    /* candidate_table: build_candidates() for every controllable device */
     std::vector<int> cptr(1, 0), cinfo;
     std::vector<double> ccoef;
     for (int c = 0; c < H.n_ctrl; ++c) {
       const double* a = &rows[(size_t)c * 3 * ANM_MAX_ROWS];
-      const double* b = a + ANM_MAX_ROWS;
-      const int R = (c < H.n_gen) ? 7 : 10;
-      auto push = [&](int s1, int s2, unsigned need, const double (&kx)[4], const double (&ky)[4]) {
-        cinfo.push_back(s1 | (s2 << 8) | (int)(need << 16));
-        ccoef.insert(ccoef.end(), kx, kx + 4);
-        ccoef.insert(ccoef.end(), ky, ky + 4);
-      };
-      push(0, 0, 0u, {1, 0, 0, 0}, {0, 1, 0, 0});
-      for (int k = 0; k < R; ++k) {
-        if (a[k] == 0.0 && b[k] == 0.0) continue;
-        if (b[k] == 0.0) {
-          push(k, k, 1u << k, {0, 0, 1.0 / a[k], 0}, {0, 1, 0, 0});
-        } else if (a[k] == 0.0) {
-          push(k, k, 1u << k, {1, 0, 0, 0}, {0, 0, 1.0 / b[k], 0});
-        } else {
-          const double w = 1.0 / (a[k] * a[k] + b[k] * b[k]);
-          push(k, k, 1u << k, {1.0 - a[k] * a[k] * w, -a[k] * b[k] * w, a[k] * w, 0},
-               {-a[k] * b[k] * w, 1.0 - b[k] * b[k] * w, b[k] * w, 0});
-        }
-      }
-      for (int j = 1; j < R; ++j)
-        for (int i = 0; i < j; ++i) {
-          const double det = a[i] * b[j] - a[j] * b[i];
-          if (det == 0.0) continue;
-          push(i, j, (1u << i) | (1u << j), {0, 0, b[j] / det, -b[i] / det}, {0, 0, -a[j] / det, a[i] / det});
-        }
+      build_candidates(a, a + ANM_MAX_ROWS, (c < H.n_gen) ? 7 : 10, cinfo, ccoef);
       cptr.push_back((int)cinfo.size());
     }
     H.o_cand_ptr = bb.add(cptr);
@@ -894,6 +899,51 @@ int anm_reset_seeded(anm_handle h, const uint8_t* mask, int32_t max_tries, int32
     if (rc) return rc;
   }
   return ANM_OK;
+}
+
+int anm_debug_project(const double* a, const double* b, const double* h, int32_t R, double p, double q, double* out2) {
+  if (!a || !b || !h || !out2 || R < 1 || R > ANM_MAX_ROWS) return fail(ANM_E_INVALID, "anm_debug_project: bad argument");
+  std::vector<int> cinfo;
+  std::vector<double> ccoef;
+  build_candidates(a, b, R, cinfo, ccoef);
+  /* the evaluation of project_polygon (anm_kernels.cuh), one candidate after the other */
+  const double inf = std::numeric_limits<double>::infinity();
+  unsigned fin = 0u;
+  double nh[ANM_MAX_ROWS], he[ANM_MAX_ROWS];
+  for (int k = 0; k < R; ++k) {
+    const bool f = std::fabs(h[k]) < inf;
+    fin |= f ? (1u << k) : 0u;
+    nh[k] = f ? -h[k] : -inf;
+    he[k] = f ? h[k] : 0.0;
+  }
+  double best = inf, bx = std::nan(""), by = std::nan("");
+  for (size_t c = 0; c < cinfo.size(); ++c) {
+    const int nf = cinfo[c];
+    const unsigned need = (unsigned)nf >> 16;
+    const double h1 = he[nf & 0xff], h2 = he[(nf >> 8) & 0xff];
+    const double* kx = &ccoef[8 * c];
+    const double* ky = kx + 4;
+    const double x = std::fma(kx[0], p, std::fma(kx[1], q, std::fma(kx[2], h1, kx[3] * h2)));
+    const double y = std::fma(ky[0], p, std::fma(ky[1], q, std::fma(ky[2], h1, ky[3] * h2)));
+    unsigned viol = 0u;
+    for (int k = 0; k < R; ++k) viol |= (std::fma(a[k], x, std::fma(b[k], y, nh[k])) > ANM_FEAS_TOL) ? (1u << k) : 0u;
+    const double dx = x - p, dy = y - q;
+    const double d = std::fma(dx, dx, dy * dy);
+    if (((fin & need) == need) && ((viol & ~need) == 0u) && d < best) best = d, bx = x, by = y;
+  }
+  out2[0] = bx;
+  out2[1] = by;
+  return ANM_OK;
+}
+
+int64_t anm_debug_blob(const anm_network_desc* net, const anm_env_desc* env, unsigned char* out, int64_t cap) {
+  if (!net || !env) return fail(ANM_E_INVALID, "null argument");
+  AnmConstHeader H;
+  std::vector<unsigned char> blob;
+  int rc = build_blob(net, env, H, blob);
+  if (rc) return rc;
+  if (out && cap > 0) memcpy(out, blob.data(), (size_t)std::min<int64_t>(cap, (int64_t)blob.size()));
+  return (int64_t)blob.size();
 }
 
 int anm_debug_rng(uint64_t seed, int32_t n, const int32_t* kind, const double* lo, const double* hi, double* out) {

@@ -195,6 +195,14 @@ int anm_reset(anm_handle h, const double* s0_dev, const uint8_t* mask_dev, doubl
 int anm_seed(anm_handle h, uint64_t seed_first);
 int anm_reset_seeded(anm_handle h, const uint8_t* mask_dev_or_null, int32_t max_tries, int32_t date_draw,
                      double* obs_dev, double* state_dev_or_null, uint8_t* converged_dev, void* stream);
+/* Host-only (no device needed): the exact projection of (p, q) on {a_k x + b_k y <= h_k, k < R <= 10}
+ * (Generator / StorageUnit.map_pq, devices.py:280-304, 472-522) through the same candidate table that
+ * anm_create builds for the kernel, evaluated like the kernel does; out2 = (x, y), NaN if infeasible. */
+int anm_debug_project(const double* a, const double* b, const double* h, int32_t R, double p, double q,
+                      double* out2);
+/* Host-only (no device needed): the constant blob anm_create would upload for this network / environment
+ * (layout: csrc/anm_layout.h); returns its size in bytes and copies at most `cap` bytes to `out`. */
+int64_t anm_debug_blob(const anm_network_desc* net, const anm_env_desc* env, unsigned char* out, int64_t cap);
 /* Host-only check of the stream restatement (no device needed): the first n draws of
  * PCG64(SeedSequence(seed)); kind[i] = 0: integers(lo[i], hi[i]), 1: uniform(lo[i], hi[i]). */
 int anm_debug_rng(uint64_t seed, int32_t n, const int32_t* kind, const double* lo, const double* hi,

@@ -130,6 +130,86 @@ def test_capi_library_exports_every_declared_symbol():
     assert rc != 0 and lib.anm_last_error()
 
 
+def _project_host(lib, rows, h, p, q):
+    a = np.ascontiguousarray(rows[:, 0], dtype=np.float64)
+    b = np.ascontiguousarray(rows[:, 1], dtype=np.float64)
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    out = np.zeros(2)
+    rc = lib.anm_debug_project(a.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                               h.ctypes.data_as(_capi.c_double_p), len(h), float(p), float(q),
+                               out.ctypes.data_as(_capi.c_double_p))  # fmt: skip
+    assert rc == 0
+    return out
+
+
+def test_projection_candidate_table_matches_the_exact_projection():
+    """The candidate table that anm_create builds for the kernel (host code, anm_capi.cu: build_candidates), evaluated
+    like the kernel evaluates it (anm_debug_project), against the definition of the exact projection
+    (oracle/shims/cvxpy/_projection.py, the stand-in that passes the reference's own map_pq tests): ANM6Easy's
+    generator / storage polygons with random and degenerate right-hand sides (p_pot = p_min, SoC at a bound, unused
+    rows), random polygons, box clipping bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims", "cvxpy"))
+    from _projection import project_onto_polygon
+
+    lib = _capi.load_library()
+    spec = anm6easy_spec()
+    dp = np.asarray(spec.cn.flat()["dev_param"]).reshape(-1, 16)
+    QP, PMIN, PMAX, QMIN, QMAX, T1, T2, T3, T4, R1, R2, R3, R4, SMIN, SMAX, EFF = range(16)
+
+    def rows_gen(P):
+        return np.array([[-1, 0, -P[PMIN]], [1, 0, P[PMAX]], [1, 0, P[PMAX]], [0, -1, -P[QMIN]], [0, 1, P[QMAX]],
+                         [-P[T1], 1, P[R1]], [P[T2], -1, -P[R2]]], float)  # fmt: skip
+
+    def rows_des(P):
+        return np.array([[-1, 0, -P[PMIN]], [1, 0, P[PMAX]], [0, -1, -P[QMIN]], [0, 1, P[QMAX]], [-P[T1], 1, P[R1]],
+                         [P[T2], -1, -P[R2]], [P[T3], -1, -P[R3]], [-P[T4], 1, P[R4]], [-1, 0, 0], [1, 0, 0]], float)  # fmt: skip
+
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for d, kind in ((2, "g"), (4, "g"), (6, "s")):
+        P = dp[d]
+        rows = rows_gen(P) if kind == "g" else rows_des(P)
+        for it in range(1500):
+            h = rows[:, 2].copy()
+            if kind == "g":
+                h[2] = rng.uniform(P[PMIN], P[PMAX]) if it % 7 else P[PMIN]  # p_pot, sometimes = p_min (a segment)
+            else:
+                soc = rng.uniform(P[SMIN], P[SMAX]) if it % 5 else rng.choice([P[SMIN], P[SMAX]])
+                h[8] = -(soc - P[SMAX]) / (0.25 * P[EFF])
+                h[9] = P[EFF] * (soc - P[SMIN]) / 0.25
+            if it % 13 == 0:
+                h[rng.integers(3, len(h))] = np.inf  # an unused row
+            p, q = rng.uniform(-0.7, 0.7, 2)
+            if it % 11 == 0:
+                p, q = rng.uniform(-0.05, 0.2, 2)  # often inside
+            want = project_onto_polygon(rows[:, :2], h, (p, q))
+            got = _project_host(lib, rows, h, p, q)
+            worst = max(worst, float(np.abs(want - got).max()))
+    assert worst < 1e-14, worst
+    # box clipping is exact (the reference's assertEqual tests, tests/simulator/test_devices.py:541-549)
+    rows = rows_gen(dp[2])
+    h = rows[:, 2].copy()
+    for p, q in ((0.9, 0.0), (-0.3, 0.1), (0.1, 0.9), (0.05, -0.7)):
+        want = project_onto_polygon(rows[:, :2], h, (p, q))
+        assert np.array_equal(_project_host(lib, rows, h, p, q), want), (p, q)
+    # random polygons around the origin, 3..10 rows
+    for it in range(1500):
+        R = int(rng.integers(3, 11))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, R))
+        rows = np.stack([np.cos(ang), np.sin(ang), rng.uniform(0.1, 1.0, R)], axis=1)
+        if it % 3 == 0:  # some axis-aligned rows
+            rows[0, :2], rows[1, :2] = (1.0, 0.0), (0.0, -1.0)
+        p, q = rng.uniform(-2, 2, 2)
+        try:
+            want = project_onto_polygon(rows[:, :2], rows[:, 2], (p, q))
+        except ValueError:
+            continue  # unbounded directions can make the candidate set empty only if the polygon is empty
+        got = _project_host(lib, rows, rows[:, 2], p, q)
+        assert np.abs(want - got).max() < 1e-13, (it, want, got)
+    # NaN set-points stay NaN (no candidate is selected)
+    assert np.isnan(_project_host(lib, rows_gen(dp[2]), rows_gen(dp[2])[:, 2], np.nan, 0.0)).all()
+
+
 def test_rng_streams_match_numpy():
     """csrc/anm_rng.h (SeedSequence -> PCG64 -> integers / uniform, the draws of ANM6Easy.init_state and ANM6.reset)
     against NumPy itself, bit for bit, through the host-only entry point anm_debug_rng."""
