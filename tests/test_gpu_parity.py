@@ -739,10 +739,10 @@ def test_device_side_seeded_reset_matches_host_rng_path():
 
 def test_chained_launch_may_wait_longer_than_the_watchdog_window():
     """A chained launch waits (per instance) for the previous one; the 2 s watchdog must only fire when nothing
-    moves any more, not when the predecessor is simply long: two chained rollouts of ~2.5 s each."""
+    moves any more, not when the predecessor is simply long: two chained rollouts of ~2.7 s each."""
     from gym_anm_b200.anm6 import BatchedANM6Easy
 
-    B, T = 8, 150_000
+    B, T = 8, 200_000
     env = BatchedANM6Easy(B, validate_actions=False)
     nb = env.native
     env.reset(seed=1)
@@ -759,7 +759,7 @@ def test_chained_launch_may_wait_longer_than_the_watchdog_window():
     ev1.record()
     torch.cuda.synchronize()
     assert nb.watchdog()[0] == 0
-    assert ev0.elapsed_time(ev1) > 2500.0  # the second launch did have to wait beyond the window
+    assert ev0.elapsed_time(ev1) > 3000.0  # ~2.7 s per launch today: the second one waited beyond the 2 s window
     assert float(out[0].abs().sum()) > 0.0
 
 
