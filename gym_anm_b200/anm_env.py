@@ -17,7 +17,7 @@ from .env_spec import HostEnvSpec
 from .errors import EnvInitializationError, EnvNextVarsError
 from .native import NativeBatch
 from .simulator import BatchedSimulator
-from .spaces import Box
+from .spaces import Box, EnvBase
 
 N_INIT_STATES_MAX = 100  # anm_env.py:268
 
@@ -27,11 +27,12 @@ def _make_rng(seed):
     return np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
 
 
-class BatchedANMEnv:
+class BatchedANMEnv(EnvBase):
     metadata = {"render_modes": []}
 
     def __init__(self, network, observation, K, delta_t, gamma, lamb, aux_bounds=None, costs_clipping=None, seed=None,
-                 *, num_envs=1, device=None, table=None, validate_actions=True, env_offset=0):  # fmt: skip
+                 *, num_envs=1, device=None, table=None, validate_actions=True, env_offset=0,
+                 track_full_state=False):  # fmt: skip
         self.spec = HostEnvSpec(network, observation, K, delta_t, gamma, lamb, aux_bounds, costs_clipping, table=table)
         self.num_envs = int(num_envs)
         self.env_offset = int(env_offset)  # global index of local env 0 (multi-GPU sharding)
@@ -61,6 +62,14 @@ class BatchedANMEnv:
         self.penalty = torch.zeros(B, dtype=torch.float64, device=self.device)
         self.n_iter = torch.zeros(B, dtype=torch.int32, device=self.device)
         self._extras = {"state": self.state, "e_loss": self.e_loss, "penalty": self.penalty, "n_iter": self.n_iter}
+        # `simulator.state` (the nested dict the reference's renderer and MPC agents read, anm6.py:101-109, mpc.py:419)
+        # needs every electrical quantity of the step: an extra [B, F] output row per instance, off by default
+        self.track_full_state = bool(track_full_state)
+        if self.track_full_state:
+            self._full = torch.zeros(B, nb.F, dtype=torch.float64, device=self.device)
+            self._extras["full_state"] = self._full
+            self.native.set_reset_full_state(self._full)
+            self.simulator._env = self
         self.timestep = 0
         self.render_mode = None
         self._seed = seed
@@ -206,14 +215,30 @@ class BatchedANMEnv:
 
     # ---- checkpoint / resume of the carried state ------------------------------
     def state_dict(self):
-        """The carried state of every instance (SoC, aux, terminated, state vector, timestep).  The random streams
-        are not part of it: the host Generators (`np_random`) can be pickled by the caller; the device-side streams of
-        `device_init=True` environments are re-created by `reset(seed=...)`."""
+        """Everything a resumed run needs to continue bit-identically: the carried state of every instance (SoC, aux,
+        terminated), the state / observation / cost tensors of the last step, the timestep, the host random streams
+        (`np_random`, one PCG64 per instance) and -- for `device_init=True` environments -- the device-side streams."""
         soc, aux, term = self.native.get_state()
-        return {"soc": soc, "aux": aux, "terminated": term, "state": self.state.clone(), "timestep": self.timestep}
+        d = {"soc": soc, "aux": aux, "terminated": term, "state": self.state.clone(), "obs": self._obs.clone(),
+             "reward": self.reward.clone(), "e_loss": self.e_loss.clone(), "penalty": self.penalty.clone(),
+             "timestep": self.timestep,
+             "host_rng": None if self._rngs is None else [r.bit_generator.state for r in self._rngs]}  # fmt: skip
+        if getattr(self, "_device_seeded", False):
+            d["device_rng"] = self.native.get_rng()
+        return d
 
     def load_state_dict(self, d):
         self.native.set_state(d["soc"], d["aux"], d["terminated"])
         self.state.copy_(d["state"])
         self._term_u8.copy_(d["terminated"])
+        for name, buf in (("obs", self._obs), ("reward", self.reward), ("e_loss", self.e_loss), ("penalty", self.penalty)):
+            if d.get(name) is not None:
+                buf.copy_(d[name])
         self.timestep = int(d["timestep"])
+        if d.get("host_rng") is not None:
+            self._rngs = [_make_rng(0) for _ in d["host_rng"]]
+            for r, st in zip(self._rngs, d["host_rng"]):
+                r.bit_generator.state = st
+        if d.get("device_rng") is not None:
+            self.native.set_rng(d["device_rng"])
+            self._device_seeded = True

@@ -73,6 +73,25 @@ int var_limit(const AnmConstHeader& H, int quantity) {
 
 }  // namespace
 
+namespace anm {
+/* test hook (anm_debug_math): the kernel's own fast math routines evaluated element-wise */
+__global__ void debug_math_kernel(int kind, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                                  double* __restrict__ a, double* __restrict__ b) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (kind == 0) {
+    double sn, cs;
+    sincos_fast(x[i], sn, cs);
+    a[i] = sn;
+    b[i] = cs;
+  } else if (kind == 1) {
+    a[i] = cabs2(x[i], y[i]);
+  } else {
+    a[i] = fast_rcp(x[i]);
+  }
+}
+}  // namespace anm
+
 struct anm_handle_s {
   int device = 0;
   int64_t B = 0;
@@ -83,8 +102,8 @@ struct anm_handle_s {
   double* d_aux = nullptr;
   uint8_t* d_term = nullptr;
   uint32_t* d_episode = nullptr;
-  uint32_t* d_seq = nullptr; /* [B + 64] per-instance launch ordinals, then the ticket counter (launch chaining,
-                                anm_kernels.cuh) */
+  uint32_t* d_seq = nullptr; /* [B] per-instance launch ordinals (launch chaining, anm_kernels.cuh) */
+  unsigned long long* d_ticket = nullptr; /* [16] (its own 128-byte line) CTAs started so far on this handle */
   AnmPcg64* d_rng = nullptr; /* [B] per-instance random streams (anm_seed / anm_reset_seeded) */
   bool seeded = false;
   uint8_t *d_need = nullptr, *d_conv_tmp = nullptr; /* seeded reset: still looking for an initial state / last attempt */
@@ -93,6 +112,7 @@ struct anm_handle_s {
   uint32_t* wd_dev = nullptr;
   const double* pool = nullptr;
   int64_t pool_size = 0;
+  double* reset_full = nullptr; /* optional [B, n_full] output of every reset launch (anm_set_reset_full_state) */
   /* launch geometry */
   int lpe = 32, gpb = 4, grid = 1, smem = 0, num_sms = 1;
   /* host-buffer path */
@@ -110,7 +130,9 @@ struct anm_handle_s {
   } hset[2];
   int hset_next = 0;
   cudaStream_t st_in = nullptr, st_out = nullptr;
-  int64_t last_T = 1; /* steps per instance of the most recent launch (watchdog limit of the next one) */
+  int64_t wd_last = 0;  /* the most recent launch's own share of wd_steps */
+  int64_t wd_steps = 0; /* steps x passes of every launch since the last fully ordered one: a chained launch may have
+                           to wait for all of them (chained waits are transitive) -- the watchdog limit of the next */
   bool st_last_was_rollout = false; /* the compute stream's last operation was one of our rollout kernels */
   int64_t launches = 0;
 };
@@ -192,6 +214,11 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
   H.base_mva = net->base_mva; H.delta_t = net->delta_t; H.lamb = net->lamb; H.gamma = env->gamma;
   H.clip_e = env->clip_e_loss; H.clip_pen = env->clip_penalty;
   H.term_reward = -env->clip_penalty / (1.0 - env->gamma); /* anm_env.py:430 */
+  H.nr_maxit = ANM_NR_MAXIT;
+  if (const char* e = getenv("ANM_DEBUG_NR_MAXIT")) { /* single-iteration tests of the solvers; never set in production */
+    const int v = atoi(e);
+    if (v >= 0 && v < ANM_NR_MAXIT) H.nr_maxit = v;
+  }
 
   std::vector<int> dev_bus(D), dev_type(D), dev_slot(D);
   std::vector<int> gens, dess;
@@ -508,8 +535,8 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_devp = take(D); H.w_devq = take(D); H.w_ppot = take(D); H.w_busp = take(N); H.w_busq = take(N);
     H.w_x = take(M); H.w_vre = take(N); H.w_vim = take(N); H.w_ere = take(N); H.w_eim = take(N);
     H.w_ire = take(N); H.w_iim = take(N);
-    H.w_J = take(H.solver == 4 ? 0 : (H.solver == 2 ? 2 * 6 * lanes_for(H) /* RadialNR: two sets of exchange slots */
-                                                                 : M * (M + 1))); H.w_rowh = take(2 * H.n_ctrl * ANM_MAX_ROWS + H.n_ctrl); /* -h / -inf, h / 0, finite-row mask per device */
+    /* RadialNR: two sets of exchange slots; its singular-block guard redoes an iteration on the dense M x (M+1) system */
+    H.w_J = take(H.solver == 4 ? 0 : (H.solver == 2 ? std::max(2 * 6 * lanes_for(H), M * (M + 1)) : M * (M + 1))); H.w_rowh = take(2 * H.n_ctrl * ANM_MAX_ROWS + H.n_ctrl); /* -h / -inf, h / 0, finite-row mask per device */
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
     H.w_vx = take(4 * N);
@@ -642,11 +669,17 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
   p.pool = h->pool; p.pool_size = h->pool_size;
   /* launch chaining: wait for the previous launch per instance, publish this one (anm_kernels.cuh) */
   p.seq = h->d_seq;
-  p.ticket = h->d_seq + h->B + 32; /* its own 128-byte line */
+  p.ticket = h->d_ticket;
   {
+    /* Watchdog limit: 2 s plus 2 ms for every step x pass of the launches this one may (transitively) have to wait
+     * for.  A launch that is not chained executes griddepcontrol.wait, i.e. runs after everything earlier has
+     * completed: the sum starts again with it. */
     const int64_t passes = (h->B + (int64_t)h->grid * h->gpb - 1) / ((int64_t)h->grid * h->gpb);
-    p.wd_limit_ns = 2000000000ull + 2000000ull * (uint64_t)(h->last_T * passes);
-    h->last_T = p.T > 1 ? p.T : 1;
+    const bool chained = pdl_enabled() && (flags & ANM_LF_CHAINED);
+    if (!chained) h->wd_steps = 0;
+    p.wd_limit_ns = 2000000000ull + 2000000ull * (uint64_t)h->wd_steps;
+    h->wd_last = (int64_t)(p.T > 1 ? p.T : 1) * passes;
+    h->wd_steps += h->wd_last;
   }
   p.watchdog = h->wd_dev;
   const bool pdl = pdl_enabled();
@@ -738,7 +771,8 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   ALLOC(h->d_aux, B * H.K * sizeof(double));
   ALLOC(h->d_term, B);
   ALLOC(h->d_episode, B * sizeof(uint32_t));
-  ALLOC(h->d_seq, (B + 64) * sizeof(uint32_t));
+  ALLOC(h->d_seq, B * sizeof(uint32_t));
+  ALLOC(h->d_ticket, 16 * sizeof(unsigned long long));
   ALLOC(h->s_action, B * H.n_action * sizeof(double));
   ALLOC(h->s_nv, B * H.n_next_vars * sizeof(double));
   ALLOC(h->s_obs, B * H.n_obs * sizeof(double));
@@ -753,7 +787,8 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, B * H.K * sizeof(double) + (H.K ? 0 : 16));
   if (e == cudaSuccess) e = cudaMemset(h->d_term, 1, B); /* nothing is runnable before the first reset */
   if (e == cudaSuccess) e = cudaMemset(h->d_episode, 0, B * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(h->d_seq, 0, (B + 64) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->d_seq, 0, B * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, 16 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->wd_host, ANM_WD_WORDS * sizeof(uint32_t), cudaHostAllocMapped);
   if (e == cudaSuccess) {
     memset(h->wd_host, 0, ANM_WD_WORDS * sizeof(uint32_t));
@@ -772,7 +807,7 @@ int anm_destroy(anm_handle h) {
   if (!h) return ANM_OK;
   DeviceGuard guard(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_soc); cudaFree(h->d_aux); cudaFree(h->d_term); cudaFree(h->d_episode);
-  cudaFree(h->d_seq);
+  cudaFree(h->d_seq); cudaFree(h->d_ticket);
   cudaFree(h->d_rng); cudaFree(h->d_need); cudaFree(h->d_conv_tmp); cudaFree(h->d_remaining);
   if (h->h_remaining) cudaFreeHost(h->h_remaining);
   if (h->wd_host) cudaFreeHost(h->wd_host);
@@ -811,6 +846,7 @@ int anm_reset(anm_handle h, const double* s0, const uint8_t* mask, double* obs, 
   memset(&p, 0, sizeof(p));
   p.mode = ANM_MODE_RESET;
   p.s0 = s0; p.mask = mask; p.obs = obs; p.state = state; p.converged = converged;
+  p.full_state = h->reset_full;
   return launch(h, p, (cudaStream_t)stream);
 }
 
@@ -952,6 +988,51 @@ int anm_debug_rng(uint64_t seed, int32_t n, const int32_t* kind, const double* l
   anm_pcg_seed(r, seed);
   for (int32_t i = 0; i < n; ++i)
     out[i] = kind[i] ? anm_rng_uniform(r, lo[i], hi[i]) : (double)anm_rng_integers(r, (int64_t)lo[i], (int64_t)hi[i]);
+  return ANM_OK;
+}
+
+int anm_debug_set_launch_ordinal(anm_handle h, uint64_t k) {
+  if (!h) return fail(ANM_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  const unsigned long long t = (unsigned long long)k * (unsigned long long)h->grid;
+  std::vector<uint32_t> seq((size_t)h->B, (uint32_t)k);
+  CUDA_TRY(cudaMemcpy(h->d_ticket, &t, sizeof(t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_seq, seq.data(), seq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return ANM_OK;
+}
+
+int64_t anm_rng_state_bytes(anm_handle h) { return h ? (int64_t)h->B * (int64_t)sizeof(AnmPcg64) : 0; }
+
+int anm_get_rng(anm_handle h, void* out, void* stream) {
+  if (!h || !out) return fail(ANM_E_INVALID, "anm_get_rng: null argument");
+  if (!h->seeded) return fail(ANM_E_INVALID, "anm_get_rng: call anm_seed first");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(out, h->d_rng, (size_t)h->B * sizeof(AnmPcg64), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return ANM_OK;
+}
+
+int anm_set_rng(anm_handle h, const void* in, void* stream) {
+  if (!h || !in) return fail(ANM_E_INVALID, "anm_set_rng: null argument");
+  DeviceGuard guard(h->device);
+  if (!h->d_rng) CUDA_TRY(cudaMalloc((void**)&h->d_rng, (size_t)h->B * sizeof(AnmPcg64)));
+  CUDA_TRY(cudaMemcpyAsync(h->d_rng, in, (size_t)h->B * sizeof(AnmPcg64), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  h->seeded = true;
+  return ANM_OK;
+}
+
+int anm_debug_math(int32_t kind, int64_t n, const double* x, const double* y, double* a, double* b, void* stream) {
+  if (kind < 0 || kind > 2 || n < 0 || !x || !a || (kind == 0 && !b) || (kind == 1 && !y))
+    return fail(ANM_E_INVALID, "anm_debug_math: bad argument");
+  if (n == 0) return ANM_OK;
+  anm::debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, n, x, y, a, b);
+  CUDA_TRY(cudaPeekAtLastError());
+  return ANM_OK;
+}
+
+int anm_set_reset_full_state(anm_handle h, double* full_state) {
+  if (!h) return fail(ANM_E_INVALID, "null handle");
+  h->reset_full = full_state;
   return ANM_OK;
 }
 
@@ -1117,6 +1198,7 @@ int anm_rollout_host_async(anm_handle h, int64_t T, const double* action, const 
   if (hs.used) { /* the set is free once its previous kernel has read the inputs and its outputs are downloaded */
     CUDA_TRY(cudaEventSynchronize(hs.ev_k));
     CUDA_TRY(cudaEventSynchronize(hs.ev_out));
+    h->wd_steps = h->wd_last; /* everything but the most recent launch is known to be complete */
   }
   if (int rc = hostset_reserve(h, hs, rows, next_vars != nullptr)) return rc;
   /* inputs: copy engine, own stream; the HOST waits for the upload (the kernels of the earlier calls are still

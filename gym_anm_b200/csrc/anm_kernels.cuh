@@ -98,7 +98,8 @@ struct AnmLaunch {
                             Newton loop, SM cycles of the whole pass -- or NULL */
   /* cross-launch ordering (see "launch chaining" below) */
   uint32_t* seq;         /* [B] ordinal of the last launch that finished with this instance          */
-  uint32_t* ticket;      /* [1] CTAs started so far on this handle: ordinal of a launch = ticket / grid + 1 */
+  unsigned long long* ticket; /* [1] CTAs started so far on this handle (64-bit: never wraps); ordinal of a launch =
+                                 (uint32)(ticket / grid + 1), compared modulo 2^32 with seq[e] */
   uint32_t* watchdog;    /* [ANM_WD_WORDS] mapped host memory: record of a chaining time-out, or zeros */
   uint32_t flags;        /* ANM_LF_* */
   int32_t* phase_stats;  /* [B, 16] diagnostic builds only: SM cycles at the end of each phase -- or NULL */
@@ -126,7 +127,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
  * Launch k (k = 1, 2, ...) may touch instance e once seq[e] == k-1 and publishes seq[e] = k when it is done with it.
  * k is not a kernel argument (a CUDA graph replays its arguments): every CTA draws a ticket from a device counter
  * when it starts, and because all launches of a handle have the same grid and a launch only becomes resident after
- * every CTA of its predecessor has started (and drawn), k = ticket / gridDim.x + 1 in every CTA of the launch.
+ * every CTA of its predecessor has started (and drawn), k = ticket / gridDim.x + 1 in every CTA of the launch (the
+ * ticket counter is 64 bits wide, so it never wraps; k itself is used modulo 2^32, like seq[e]).
  * seq[e] is published with a release store after a fence that covers the whole lane group's writes and consumed
  * with an acquire load; the carried state is read with ld.global.cg (L2), never from a possibly stale L1 line.
  * No deadlock: by the same induction every CTA that is being waited for is already running.  A wait that outlasts
@@ -172,7 +174,7 @@ __device__ __forceinline__ void seq_publish(uint32_t* p, uint32_t v) {
 /* Also draws the CTA's ticket (launch ordinal, see "launch chaining") while the copy is in flight and signals
  * launch_dependents once the ticket is drawn; returns the ordinal of this launch. */
 __device__ __forceinline__ uint32_t stage_constants(unsigned char* smem, const unsigned char* gblob, int bytes,
-                                                    uint32_t* ticket) {
+                                                    unsigned long long* ticket) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* ord = reinterpret_cast<uint32_t*>(smem + 16);
   const uint32_t bar_a = smem_u32(bar);
@@ -190,7 +192,7 @@ __device__ __forceinline__ uint32_t stage_constants(unsigned char* smem, const u
           : "memory");
       done += chunk;
     }
-    *ord = atomicAdd(ticket, 1u) / gridDim.x + 1u;
+    *ord = (uint32_t)(atomicAdd(ticket, 1ull) / (unsigned long long)gridDim.x) + 1u;
   }
   __syncthreads();         /* the ticket is drawn (its value has come back) before ...                        */
   pdl_launch_dependents(); /* ... this CTA lets the next launch of the stream become resident                 */
@@ -589,7 +591,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
     lmax = g_max<LPE, FULL>(lmax, gm);
     bad = g_any<FULL>(bad, gm);
     diff = bad ? CUDART_NAN : lmax; /* numpy.linalg.norm(F, inf) propagates NaN */
-    if (!(diff > ANM_NR_TOL) || it >= ANM_NR_MAXIT) break;
+    if (!(diff > ANM_NR_TOL) || it >= H.nr_maxit) break;
     ++it;
     gsync<FULL>(gm);
 
@@ -691,7 +693,7 @@ __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws,
     lmax = g_max<LPE, FULL>(lmax, gm);
     bad = g_any<FULL>(bad, gm);
     diff = bad ? CUDART_NAN : lmax;
-    if (!(diff > ANM_NR_TOL) || it >= ANM_NR_MAXIT) break;
+    if (!(diff > ANM_NR_TOL) || it >= H.nr_maxit) break;
     ++it;
     gsync<FULL>(gm);
 
@@ -852,6 +854,7 @@ struct SmallNR {
     const int b = active ? (lane - part * n + 1) : 1; /* bus of my row / unknown */
     const int partner = active ? (part ? lane - n : lane + n) : lane;
     const int giw = (threadIdx.x & 31) / LPE; /* my group's index inside the warp */
+    const int maxit = H.nr_maxit;
     const double2* Yd = reinterpret_cast<const double2*>(C.y_dense) + (size_t)b * NB;
 #if ANM_VAR_YREG
     double yre[NB], yim[NB];
@@ -917,9 +920,9 @@ struct SmallNR {
         bad = (nanb & gm) != 0u; /* numpy: norm(F, inf) is NaN, and `nan > tol` is False (:218) */
         big = (bigb & gm) != 0u;
 #if ANM_DIAG
-        if (bad || !big || it >= ANM_NR_MAXIT) done = true, t_done = clock64(); else ++it;
+        if (bad || !big || it >= maxit) done = true, t_done = clock64(); else ++it;
 #else
-        if (bad || !big || it >= ANM_NR_MAXIT) done = true; else ++it;
+        if (bad || !big || it >= maxit) done = true; else ++it;
 #endif
       }
       if (__all_sync(ANM_FULL, done)) break;
@@ -1023,6 +1026,75 @@ struct SmallNR {
   }
 };
 
+/* ---- one Newton step by the dense, partially pivoted solver: the cold path of RadialNR's singular-block guard ----
+ * The tree elimination of RadialNR inverts 2x2 (Schur) blocks without pivoting across blocks; the reference's
+ * SuperLU pivots.  When a block's determinant has cancelled to less than ANM_SING_TAU of its products while the
+ * Jacobian itself may be perfectly regular, the step of that iteration is recomputed here the way nr_generic does
+ * it: dense Jacobian (solve_load_flow.py:123-164) of the iterate (theta, |V|) in shared memory, Gauss-Jordan with
+ * partial pivoting.  Lock-step: every lane group of the warp runs along on its own iterate, only the groups that
+ * tripped use the result (so an instance's arithmetic never depends on the company it keeps in its warp). */
+#ifndef ANM_SING_TAU
+#define ANM_SING_TAU 1e-7
+#endif
+template <int LPE>
+__device__ __noinline__ double2 dense_step_cold(const unsigned char* blob, double* __restrict__ ws, double th, double vm,
+                                                double f0, double f1, int lane, unsigned gm) {
+  const Cst C(blob); /* resolved here, not passed: the caller's copy stays in registers */
+  const AnmConstHeader& H = *C.H;
+  const int N = H.n_bus, n = N - 1, M = H.n_unk, LD = M + 1;
+  double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* J = ws + H.w_J; double* dxs = ws + H.w_dx;
+  __syncwarp();
+  if (lane < n) {
+    double sn, cs;
+    sincos_fast(th, sn, cs);
+    const double sg = (vm > 0.0) ? 1.0 : ((vm < 0.0) ? -1.0 : CUDART_NAN);
+    vre[lane + 1] = vm * cs; vim[lane + 1] = vm * sn; ere[lane + 1] = sg * cs; eim[lane + 1] = sg * sn;
+    J[lane * LD + M] = f0;
+    J[(n + lane) * LD + M] = f1;
+  }
+  if (lane == 0) { vre[0] = 1.0; vim[0] = 0.0; ere[0] = 1.0; eim[0] = 0.0; }
+  __syncwarp();
+  for (int b = lane; b < N; b += LPE) {
+    double sr = 0.0, si = 0.0;
+    for (int k = C.y_ptr[b]; k < C.y_ptr[b + 1]; ++k) {
+      const int j = C.y_col[k];
+      const double yr = C.y_val[2 * k], yi = C.y_val[2 * k + 1];
+      sr += yr * vre[j] - yi * vim[j];
+      si += yr * vim[j] + yi * vre[j];
+    }
+    ire[b] = sr; iim[b] = si;
+  }
+  for (int r = 0; r < M; ++r)
+    for (int c = lane; c < M; c += LPE) J[r * LD + c] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < H.n_jac; e += LPE) {
+    const int b = C.jac_row[e], j = C.jac_col[e], yk = C.jac_y[e];
+    const double yr = C.y_val[2 * yk], yi = C.y_val[2 * yk + 1];
+    const bool dg = (b == j);
+    const double tr = yr * vre[j] - yi * vim[j], ti = yr * vim[j] + yi * vre[j];
+    const double inr = (dg ? ire[b] : 0.0) - tr, ini = (dg ? iim[b] : 0.0) - ti;
+    const double jr = -vim[b], ji = vre[b];
+    const double wr = jr * inr + ji * ini, wi = ji * inr - jr * ini;
+    const double gr = yr * ere[j] - yi * eim[j], gi = yr * eim[j] + yi * ere[j];
+    double ur = vre[b] * gr + vim[b] * gi, ui = vim[b] * gr - vre[b] * gi;
+    if (dg) {
+      ur += ere[b] * ire[b] + eim[b] * iim[b];
+      ui += eim[b] * ire[b] - ere[b] * iim[b];
+    }
+    J[(b - 1) * LD + (j - 1)] = wr;
+    J[(b - 1) * LD + (n + j - 1)] = ur;
+    J[(n + b - 1) * LD + (j - 1)] = wi;
+    J[(n + b - 1) * LD + (n + j - 1)] = ui;
+  }
+  __syncwarp();
+  gj_pivot_smem<LPE, true>(J, M, dxs, lane, gm);
+  const int bl = lane < n ? lane : 0;
+  const double2 r = make_double2(dxs[bl], dxs[n + bl]);
+  __syncwarp();
+  return r;
+}
+
 /* ---- Newton-Raphson for RADIAL networks (the bus graph is a tree rooted at the slack bus) --------
  * Lane b-1 owns non-slack bus b: its two unknowns (theta_b, |V|_b), its two mismatch rows and the three
  * non-zero 2x2 Jacobian blocks of a tree: D = J[b][b], L = J[b][parent], U = J[parent][b]
@@ -1030,10 +1102,10 @@ struct SmallNR {
  * along the tree: leaves first, every bus folds  U D^-1 [L | f]  into its parent's (D, f) (one shuffle
  * round per tree level), then the step is back-substituted from the root down -- the critical path is the
  * tree depth instead of 2(N-1) pivots, and an environment needs only N-1 lanes.  2x2 diagonal blocks are
- * inverted by the adjugate.  No pivoting across blocks: a (near-)singular Schur block while the Jacobian itself
- * is regular is non-generic (never observed in 5e5 instance-steps against the pivoting oracle, divergent
- * instances included); ANM_SOLVER=generic selects the dense partial-pivoting solver.  Lock-step lane groups,
- * full-mask intrinsics, like SmallNR. */
+ * inverted by the adjugate.  No pivoting across blocks; instead every inverted block is watched (singular-block
+ * guard: |det| <= ANM_SING_TAU (|d00 d11| + |d01 d10|)) and the rare iteration in which a Schur block has all but
+ * cancelled while the Jacobian itself is regular is redone by the dense partially pivoted solver (dense_step_cold),
+ * which is what the reference's SuperLU does.  Lock-step lane groups, full-mask intrinsics, like SmallNR. */
 #define ANM_RAD_MAXC 4
 template <int LPE, int NB>
 struct RadialNR {
@@ -1050,7 +1122,7 @@ struct RadialNR {
     const int b = bl + 1;
     const int pl = active ? C.rad_parent[bl] : -1; /* parent's lane, -1: the slack bus */
     const int depth = active ? C.rad_depth[bl] : 0;
-    const int maxc = H.rad_maxc, maxd = H.rad_maxdepth;
+    const int maxc = H.rad_maxc, maxd = H.rad_maxdepth, maxit = H.nr_maxit;
     /* Source lane of every child slot.  An empty slot (and every slot of an idle lane) reads lane n, an idle lane
      * whose admittances are zero and whose depth is 0: everything it offers is exactly 0, so the gathers below need
      * no per-slot select. */
@@ -1121,7 +1193,7 @@ struct RadialNR {
       const unsigned notok = __ballot_sync(ANM_FULL, active && !(fabs(f0) <= ANM_NR_TOL && fabs(f1) <= ANM_NR_TOL));
       {
         const int nb = ((notok & gm) != 0u) ? 1 : 0;
-        const int stop = (!nb || it >= ANM_NR_MAXIT) ? 1 : 0;
+        const int stop = (!nb || it >= maxit) ? 1 : 0;
         big = done ? big : nb;
         it += (done | stop) ? 0 : 1;
 #if ANM_DIAG
@@ -1164,13 +1236,16 @@ struct RadialNR {
       }
       double r0 = f0, r1 = f1;
       double rdet = 0.0;
+      bool sing = false; /* singular-block guard: some 2x2 block this lane inverts has all but cancelled */
       /* leaves -> root: bus b (depth lev) folds U D^-1 [L | f] into its parent.  Rolled loops and selects instead
        * of branches: the body is shared by all levels / child slots and stays in the instruction cache. */
 #pragma unroll 1
       for (int lev = maxd; lev >= 2; --lev) {
-        const double det = d00 * d11 - d01 * d10;
+        const double pa = d00 * d11, pb2 = d01 * d10;
+        const double det = pa - pb2;
         const double rd = fast_rcp(det);
         const bool mine = (depth == lev);
+        sing |= mine & (fabs(det) <= ANM_SING_TAU * (fabs(pa) + fabs(pb2)));
         rdet = mine ? rd : rdet;
         const double rdm = mine ? rd : 0.0; /* only the buses of this level offer a non-zero contribution */
         /* T = adj(D) [L | f],  C = U T / det */
@@ -1204,9 +1279,11 @@ struct RadialNR {
       /* root level (children of the slack): plain 2x2 solves */
       double x0 = 0.0, x1 = 0.0;
       {
-        const double det = d00 * d11 - d01 * d10;
+        const double pa = d00 * d11, pb2 = d01 * d10;
+        const double det = pa - pb2;
         const double rr = fast_rcp(det);
         const bool root = (depth == 1);
+        sing |= root & (fabs(det) <= ANM_SING_TAU * (fabs(pa) + fabs(pb2)));
         rdet = root ? rr : rdet;
         x0 = root ? (d11 * r0 - d01 * r1) * rr : 0.0;
         x1 = root ? (d00 * r1 - d10 * r0) * rr : 0.0;
@@ -1221,6 +1298,19 @@ struct RadialNR {
         x1 = mine ? (d00 * q1 - d10 * q0) * rdet : x1;
       }
       __syncwarp(); /* this iteration's reads of the exchange slots are done */
+      {
+        /* singular-block guard (cold): the groups in which a block all but cancelled redo this step with the dense,
+         * partially pivoted solver -- what the reference's SuperLU would have done */
+        const unsigned trip = __ballot_sync(ANM_FULL, sing && active && !done);
+        if (trip != 0u) {
+          const double2 xd = dense_step_cold<LPE>(reinterpret_cast<const unsigned char*>(C.H), ws, th, vm, f0, f1, lane, gm);
+          if ((trip & gm) != 0u) {
+            x0 = xd.x;
+            x1 = xd.y;
+            ++n_fb;
+          }
+        }
+      }
       if (active && !done) { /* x <- x - J^{-1} F (:220) */
         th -= x0;
         vm -= x1;

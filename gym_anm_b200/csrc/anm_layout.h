@@ -27,6 +27,9 @@ struct AnmConstHeader {
   int32_t need_mask;    /* ANM_NEED_* (anm_kernels.cuh): derived quantities some state/obs entry reads */
   int32_t blob_bytes;
   int32_t ws_doubles;   /* per-env workspace size (doubles) */
+  int32_t nr_maxit;     /* Newton-Raphson iteration cap: 100 (solve_load_flow.py:176); ANM_DEBUG_NR_MAXIT (environment,
+                           read by anm_create) lowers it for single-iteration tests */
+  int32_t pad0;
   double base_mva, delta_t, lamb, gamma, clip_e, clip_pen, term_reward;
   /* blob offsets (bytes) */
   int32_t o_vmin, o_vmax;                    /* double[n_bus]                                  */

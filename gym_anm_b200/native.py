@@ -36,10 +36,12 @@ class NativeBatch:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise NativeLibraryError("device must be a CUDA device, got %s" % self.device)
+        if self.device.index is None:  # "cuda" means the CURRENT device (not GPU 0): the handle and every tensor live there
+            self.device = torch.device("cuda", torch.cuda.current_device())
         net, env, keep = spec.descs()
         self._keep = keep
         h = C.c_void_p()
-        _capi.check(self.lib.anm_create(C.byref(net), C.byref(env), C.c_int64(self.B), self.device.index or 0, C.byref(h)),
+        _capi.check(self.lib.anm_create(C.byref(net), C.byref(env), C.c_int64(self.B), int(self.device.index), C.byref(h)),
                     self.lib)  # fmt: skip
         self.h = h
         sz = _capi.Sizes()
@@ -65,7 +67,13 @@ class NativeBatch:
     def empty(self, *shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    def _on_device(self, t):
+        if t is not None and isinstance(t, torch.Tensor) and t.is_cuda and t.device != self.device:
+            raise ValueError("tensor on %s, but the handle lives on %s" % (t.device, self.device))
+        return t
+
     def _f64(self, t, cols):
+        self._on_device(t)
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
             t = torch.as_tensor(np.asarray(t, dtype=np.float64) if not isinstance(t, torch.Tensor) else t,
                                 dtype=torch.float64, device=self.device).contiguous()  # fmt: skip
@@ -84,6 +92,11 @@ class NativeBatch:
         _capi.check(self.lib.anm_reset(self.h, _ptr(s0), _ptr(mask), _ptr(obs), _ptr(state), _ptr(converged),
                                        self._stream()), self.lib)  # fmt: skip
         return obs, state, converged
+
+    def set_reset_full_state(self, full):
+        """Every later reset also writes the [B, F] full electrical state of the instances it resets (or None: off)."""
+        self._reset_full = None if full is None else self._on_device(full)
+        _capi.check(self.lib.anm_set_reset_full_state(self.h, _ptr(self._reset_full)), self.lib)
 
     def seed(self, seed_first):
         """Instance e gets the stream Generator(PCG64(SeedSequence(seed_first + e))), kept on the device."""
@@ -167,6 +180,19 @@ class NativeBatch:
         if terminated is not None:
             terminated = torch.as_tensor(terminated, device=self.device).to(torch.uint8).contiguous()
         _capi.check(self.lib.anm_set_state(self.h, _ptr(soc), _ptr(aux), _ptr(terminated), self._stream()), self.lib)
+
+    def get_rng(self):
+        """Opaque uint8 tensor holding the device-side PCG64 streams (after seed()); see set_rng."""
+        n = int(self.lib.anm_rng_state_bytes(self.h))
+        out = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _capi.check(self.lib.anm_get_rng(self.h, _ptr(out), self._stream()), self.lib)
+        return out
+
+    def set_rng(self, blob):
+        blob = torch.as_tensor(blob, dtype=torch.uint8, device=self.device).contiguous()
+        if blob.numel() != int(self.lib.anm_rng_state_bytes(self.h)):
+            raise ValueError("rng state of %d bytes, expected %d" % (blob.numel(), self.lib.anm_rng_state_bytes(self.h)))
+        _capi.check(self.lib.anm_set_rng(self.h, _ptr(blob), self._stream()), self.lib)
 
     def set_autoreset_pool(self, pool):
         if pool is None:

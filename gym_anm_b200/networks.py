@@ -68,13 +68,15 @@ def anm6easy_tables():
     return np.vstack((p1, p3, p5)), np.vstack((p2, p4))
 
 
-def synth_feeder_network(n_bus=30, n_load=10, n_ren=6, n_des=3, n_loops=2, seed=30):
+def synth_feeder_network(n_bus=30, n_load=10, n_ren=6, n_des=3, n_loops=2, seed=30, impedance_scale=1.0):
     """A deterministic synthetic distribution feeder that passes the network validators.
 
     Bus 0 is the 132 kV slack, bus 1 the 33 kV substation bus fed through one branch;
     the other buses hang in a shallow random tree below bus 1, plus ``n_loops`` extra
     loop-closing branches.  Branch impedances / ratings and device ratings are drawn in
     the range of the ANM6 grid, scaled so that the network solves from a flat start.
+    ``impedance_scale`` > 1 multiplies every 33 kV branch's r and x: a weaker grid whose power flow needs more Newton
+    iterations and, under random set-points, has no solution for a few per cent of the draws (stress fixture).
     """
     rng = np.random.default_rng(seed)
     net = {"baseMVA": 100.0}
@@ -103,6 +105,8 @@ def synth_feeder_network(n_bus=30, n_load=10, n_ren=6, n_des=3, n_loops=2, seed=
                          round(float(rng.uniform(0.0, 0.02)), 4), 30.0, 1, 0])  # fmt: skip
         n_loops -= 1
     net["branch"] = np.array(branches, dtype=np.float64)
+    if impedance_scale != 1.0:
+        net["branch"][1:, 2:4] *= impedance_scale
 
     leaves = list(rng.permutation(np.arange(2, n_bus)))
     devices = [[0, 0, 0, N, 400, -400, 400, -400, N, N, N, N, N, N, N]]

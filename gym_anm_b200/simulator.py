@@ -18,6 +18,8 @@ class BatchedSimulator:
         self.state_bounds = cn.state_bounds
         self.pfe_converged = None
         self._last_full = None
+        self._env = None  # set by BatchedANMEnv(track_full_state=True): `state` then follows the env's steps / resets
+        self.env_index = 0  # which instance the reference-shaped single-env views (`state`) show
 
     @property
     def Y_bus(self):
@@ -36,6 +38,32 @@ class BatchedSimulator:
 
     def get_state_space(self):
         return self.state_bounds
+
+    def get_rendering_specs(self):
+        """Operating limits of the network for the renderer (simulator.py:295-338)."""
+        cn, m = self.cn, self.baseMVA
+        return {
+            "bus_p": self.state_bounds["bus_p"], "bus_q": self.state_bounds["bus_q"],
+            "dev_p": self.state_bounds["dev_p"], "dev_q": self.state_bounds["dev_q"],
+            "bus_v": {i: {"pu": (b.v_min, b.v_max), "kV": (b.v_min * b.baseKV, b.v_max * b.baseKV)} for i, b in cn.buses.items()},
+            "dev_type": {i: d.type for i, d in cn.devices.items()},
+            "des_soc": self.state_bounds["des_soc"],
+            "branch_s": {k: {"MVA": (0, br.rate * m), "pu": (0, br.rate)} for k, br in cn.branches.items()},
+        }  # fmt: skip
+
+    @property
+    def state(self):
+        """`Simulator.state` of instance `env_index` (simulator.py:551-636): the nested {quantity: {unit: {id: value}}}
+        dict the reference's renderer (anm6.py:101-109) and MPC agents (mpc.py:419, mpc_constant.py:23-29) read.
+        Follows the environment's resets / steps when it was built with `track_full_state=True`, else the last
+        `transition()` call."""
+        if self._env is not None:
+            if bool(self._env._term_u8[self.env_index]):
+                return None  # anm_env.py:446-448: no valid electrical state after a terminal step
+            return self.state_dict(self.env_index, full=self._env._full)
+        if self._last_full is None:
+            raise AttributeError("no state yet: call transition() or build the environment with track_full_state=True")
+        return self.state_dict(self.env_index)
 
     def _stack(self, d, ids):
         B = self.native.B

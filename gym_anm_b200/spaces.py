@@ -1,5 +1,10 @@
-"""`Box` space: gymnasium's if it is installed, else a minimal equivalent."""
+"""`Box` space and the `Env` base class: gymnasium's if it is installed, else minimal equivalents."""
 import numpy as np
+
+try:  # the registered classes are real gymnasium.Env subclasses when Gymnasium is there (its wrappers assert that)
+    from gymnasium import Env as EnvBase  # noqa: F401
+except Exception:  # noqa: BLE001
+    EnvBase = object
 
 try:  # pragma: no cover - gymnasium is optional
     from gymnasium.spaces import Box  # noqa: F401

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ANM_ABI_VERSION 2
+#define ANM_ABI_VERSION 3
 
 /* error codes */
 #define ANM_OK 0
@@ -183,6 +183,12 @@ int anm_get_sizes(anm_handle h, anm_sizes* out);
 int anm_reset(anm_handle h, const double* s0_dev, const uint8_t* mask_dev, double* obs_dev,
               double* state_dev_or_null, uint8_t* converged_dev, void* stream);
 
+/* Optional: every later reset launch of this handle (anm_reset, anm_reset_host, anm_reset_seeded) also writes the
+ * full electrical state [B, n_full_state] (p.u., layout above) of the instances it resets -- Simulator.state after
+ * Simulator.reset (simulator.py:281-293), which the reference's renderer and MPC agents read.  NULL turns it off.
+ * The caller owns the buffer and keeps it alive. */
+int anm_set_reset_full_state(anm_handle h, double* full_state_dev_or_null);
+
 /* Device-side seeded reset.  anm_seed gives instance e the random stream
  * np.random.Generator(PCG64(SeedSequence(seed_first + e))) -- what Gymnasium's Env.reset(seed=) creates
  * (anm_env.py:116, 257) -- kept in device memory.  anm_reset_seeded is the whole ANMEnv.reset loop
@@ -195,6 +201,19 @@ int anm_reset(anm_handle h, const double* s0_dev, const uint8_t* mask_dev, doubl
 int anm_seed(anm_handle h, uint64_t seed_first);
 int anm_reset_seeded(anm_handle h, const uint8_t* mask_dev_or_null, int32_t max_tries, int32_t date_draw,
                      double* obs_dev, double* state_dev_or_null, uint8_t* converged_dev, void* stream);
+/* Checkpointing of the device-side random streams: anm_rng_state_bytes(h) bytes of opaque device memory
+ * (one 48-byte PCG64 record per instance) copied out of / into the handle, asynchronous on `stream`. */
+int64_t anm_rng_state_bytes(anm_handle h);
+int anm_get_rng(anm_handle h, void* out_dev, void* stream);
+int anm_set_rng(anm_handle h, const void* in_dev, void* stream);
+/* Test hook: pretend that k launches have already run on this handle (launch chaining: sets the 64-bit ticket
+ * counter to k * grid and every instance's ordinal to (uint32) k).  Synchronises the device. */
+int anm_debug_set_launch_ordinal(anm_handle h, uint64_t k);
+/* Test hook: the kernel's own fast math routines element-wise on device arrays of n doubles (current device).
+ * kind 0: (a, b) = sincos_fast(x) (RadialNR / SmallNR: V = |V| e^{j theta});  1: a = sqrt(x^2 + y^2) as the kernel
+ * computes magnitudes;  2: a = the MUFU.RCP64H + 2 Newton steps reciprocal of the 2x2 block inversions. */
+int anm_debug_math(int32_t kind, int64_t n, const double* x_dev, const double* y_dev_or_null, double* a_dev,
+                   double* b_dev_or_null, void* stream);
 /* Host-only (no device needed): the exact projection of (p, q) on {a_k x + b_k y <= h_k, k < R <= 10}
  * (Generator / StorageUnit.map_pq, devices.py:280-304, 472-522) through the same candidate table that
  * anm_create builds for the kernel, evaluated like the kernel does; out2 = (x, y), NaN if infeasible. */

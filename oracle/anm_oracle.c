@@ -23,6 +23,15 @@
 #define MAXUNK (2 * (MAXBUS - 1))
 #define NR_TOL 1e-5 /* simulator.py:529 xtol=1e-5 */
 #define NR_MAXIT 100 /* solve_load_flow.py:176 lim_iter=100 */
+/* ANM_DEBUG_NR_MAXIT (environment) lowers the cap: single-iteration comparisons with the CUDA solvers (tests only) */
+static int nr_maxit(void) {
+  const char* e = getenv("ANM_DEBUG_NR_MAXIT");
+  if (e) {
+    const int v = atoi(e);
+    if (v >= 0 && v < NR_MAXIT) return v;
+  }
+  return NR_MAXIT;
+}
 #define FEAS_TOL 1e-12
 
 typedef struct {
@@ -257,7 +266,7 @@ static int power_flow(const anm_network_desc* net, work_t* w) {
   for (int j = 0; j < n; ++j) x[j] = 0.0, x[n + j] = 1.0; /* flat start, :42 */
   int n_iter = 0;
   double diff = nr_residual(net, x, w->bus_p, w->bus_q, F);
-  while (diff > NR_TOL && n_iter < NR_MAXIT) {
+  while (diff > NR_TOL && n_iter < nr_maxit()) {
     ++n_iter;
     nr_jacobian(net, x, J);
     lu_solve(M, J, F);

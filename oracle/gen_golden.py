@@ -16,6 +16,10 @@ path.  Fixtures:
                              3-bus loop, 3-bus with off-nominal transformer, the
                              test_reset network, a 2-bus net with flexible devices, the
                              synthetic 30-bus feeder) incl. Simulator.reset cases.
+  listobs_{net}.npz          ANMEnv subclasses with LIST-style observation specs in every unit (kV / kA / degree /
+                             MVA / MWh ..., anm_env.py:497-549, constants.py:31-48; the reference's
+                             tests/envs/custom_obs_space.py:33-72 pattern), K = 1, random init_state / next_vars /
+                             actions: reset and step observations, bounds of the observation space.
   tables.npz                 ANM6Easy's 96-slot tables and the known-answer tables of the
                              reference's own device tests (tests/simulator/test_devices.py:
                              290-291, 556-557).
@@ -296,6 +300,88 @@ def flex_forced():
     return forced, np.array(gen_pts, dtype=np.float64), np.array(des_pts, dtype=np.float64)
 
 
+LIST_OBS = [("bus_v_magn", "all", "kV"), ("bus_i_magn", [1, 2], "kA"), ("bus_v_ang", "all", "degree"),
+            ("branch_i_magn", "all", "pu"), ("branch_s", "all", "MVA"), ("bus_i_ang", [1], "degree"),
+            ("branch_i_ang", "all", "rad"), ("bus_p", "all", "MW"), ("bus_q", [0, 2], "pu"), ("dev_q", "all", "MVAr"),
+            ("des_soc", "all", "MWh"), ("gen_p_max", "all", "pu"), ("branch_p", "all", "MW"), ("branch_q", "all", "pu"),
+            ("bus_v_magn", [1], "pu"), ("bus_i_magn", "all", "pu"), ("aux", "all")]  # fmt: skip
+
+
+def gen_listobs(name, net, delta_t, T, seed, load_scale=1.0):
+    """A reference ANMEnv with a list-style observation in every supported unit; the hooks draw from a recorded
+    stream so that the batched engine can be fed the same s0 / next_vars / actions."""
+    from gym_anm.envs import ANMEnv
+
+    rng = np.random.default_rng(seed)
+    rec = {k: [] for k in ("s0", "reset_obs", "reset_state", "reset_before_step", "next_vars", "actions", "obs", "state",
+                           "reward", "terminated")}  # fmt: skip
+
+    class ListObsEnv(ANMEnv):
+        def __init__(self):
+            super().__init__(net, list(LIST_OBS), 1, delta_t, 0.9, 50, np.array([[0.0, 10.0]]), (1, 100), None)
+            self.loads, self.gens, self.des = _dev_groups(self.simulator)
+
+        def _draw(self):
+            sim, m = self.simulator, self.simulator.baseMVA
+            pl = [rng.uniform(max(sim.devices[i].p_min, -1.0) * load_scale, 0.0) * m for i in self.loads]
+            pp = [rng.uniform(0.0, min(sim.devices[i].p_max, 1.0)) * m for i in self.gens]
+            return pl, pp
+
+        def init_state(self):
+            sim, m = self.simulator, self.simulator.baseMVA
+            n_dev, n_des, n_gen = sim.N_device, sim.N_des, sim.N_non_slack_gen
+            s0 = np.zeros(2 * n_dev + n_des + n_gen + 1)
+            pl, pp = self._draw()
+            ids = list(sim.devices.keys())
+            for i, v in zip(self.loads, pl):
+                s0[ids.index(i)] = v
+                s0[n_dev + ids.index(i)] = v * sim.devices[i].qp_ratio
+            for k, (i, v) in enumerate(zip(self.gens, pp)):
+                s0[ids.index(i)] = v * rng.uniform(0, 1)
+                s0[n_dev + ids.index(i)] = rng.uniform(max(sim.devices[i].q_min, -1.0), min(sim.devices[i].q_max, 1.0)) * m
+                s0[2 * n_dev + n_des + k] = v
+            for k, i in enumerate(self.des):
+                d = sim.devices[i]
+                s0[ids.index(i)] = rng.uniform(max(d.p_min, -1.0), min(d.p_max, 1.0)) * m
+                s0[n_dev + ids.index(i)] = rng.uniform(max(d.q_min, -1.0), min(d.q_max, 1.0)) * m
+                s0[2 * n_dev + k] = rng.uniform(d.soc_min, d.soc_max) * m
+            s0[-1] = float(rng.integers(0, 10))
+            rec["s0"].append(s0.copy())
+            return s0
+
+        def next_vars(self, s_t):
+            pl, pp = self._draw()
+            v = np.array(pl + pp + [float((s_t[-1] + 1) % 10)])
+            rec["next_vars"].append(v.copy())
+            return v
+
+    env = ListObsEnv()
+    obs, _ = env.reset(seed=seed)
+    rec["reset_obs"].append(obs), rec["reset_state"].append(env.state.copy()), rec["reset_before_step"].append(0)
+    rec["s0"] = rec["s0"][-1:]  # only the s0 that converged is replayed
+    lo, hi = env.action_space.low, env.action_space.high
+    lo_c, hi_c = np.maximum(lo, -1.5 * env.simulator.baseMVA), np.minimum(hi, 1.5 * env.simulator.baseMVA)
+    for t in range(T):
+        a = rng.uniform(lo_c, hi_c)
+        o, r, term, _, _ = env.step(a)
+        rec["actions"].append(a), rec["obs"].append(o), rec["state"].append(env.state.copy())
+        rec["reward"].append(r), rec["terminated"].append(term)
+        if term:
+            n0 = len(rec["s0"])
+            obs, _ = env.reset()
+            rec["s0"] = rec["s0"][:n0] + rec["s0"][-1:]
+            rec["reset_obs"].append(obs), rec["reset_state"].append(env.state.copy())
+            rec["reset_before_step"].append(t + 1)
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["obs_low"], out["obs_high"] = env.observation_space.low, env.observation_space.high
+    out["action_low"], out["action_high"] = lo, hi
+    out["delta_t"] = np.array(delta_t)
+    for k, v in net_to_float(net).items():
+        out["net_" + k] = np.array(v)
+    np.savez_compressed(os.path.join(OUT, "listobs_%s.npz" % name), **out)
+    print("listobs", name, "T=%d terminations=%d obs dim %d" % (T, int(out["terminated"].sum()), out["obs"].shape[1]))
+
+
 def gen_tables():
     from gym_anm.envs.anm6_env.anm6_easy import _get_gen_time_series, _get_load_time_series
 
@@ -324,4 +410,8 @@ if __name__ == "__main__":
     gen_transitions("anm6", __import__("gym_anm_b200.networks", fromlist=["x"]).anm6_network(), 0.25, 100, T=120,
                     seed=11, scale=1.2, resets=10)  # fmt: skip
     gen_transitions("synth30", synth_feeder_network(), 0.25, 100, T=60, seed=30, scale=1.1, resets=6)
+    # the same feeder with four times the branch impedances: divergent draws and 5-7 iteration solves at 30 buses
+    gen_transitions("synth30s", synth_feeder_network(impedance_scale=4.0), 0.25, 100, T=120, seed=31, scale=1.1, resets=6)
     gen_tables()
+    gen_listobs("anm6", __import__("gym_anm_b200.networks", fromlist=["x"]).anm6_network(), 0.25, T=150, seed=41, load_scale=1.0)
+    gen_listobs("3bus_xfmr", nets["3bus_xfmr"][0], 0.5, T=150, seed=42)

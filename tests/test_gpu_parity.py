@@ -97,7 +97,7 @@ def test_single_env_facade_reference_shapes():
         env.step(np.array([1e3, 0, 0, 0, 0, 0.0]))
 
 
-@pytest.mark.parametrize("name", ["2bus", "3bus_loop", "3bus_xfmr", "3bus_reset", "2bus_flex", "anm6", "synth30"])
+@pytest.mark.parametrize("name", ["2bus", "3bus_loop", "3bus_xfmr", "3bus_reset", "2bus_flex", "anm6", "synth30", "synth30s"])
 def test_transition_goldens(name):
     """Simulator.transition sequences recorded from the reference (8/16/32-lane kernels)."""
     from gym_anm_b200.native import NativeBatch
@@ -132,16 +132,68 @@ def test_transition_goldens(name):
             np.testing.assert_allclose(row[sl["dev_q"]][2] * 100, dm[1], rtol=0, atol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["3bus_reset", "anm6", "synth30", "2bus"])
+@pytest.mark.parametrize("name", ["3bus_reset", "anm6", "synth30", "synth30s", "2bus", "3bus_loop", "3bus_xfmr", "2bus_flex"])
 def test_reset_goldens(name):
+    """Simulator.reset cases recorded from the reference (simulator.py:225-293): the converged flags, and for the
+    converged cases the whole electrical state after the reset plus the state / observation vectors derived from it."""
     from gym_anm_b200.native import NativeBatch
 
     g = load("transitions_%s.npz" % name)
     spec = transition_spec(g)
     n = len(g["reset_s0"])
     nb = NativeBatch(spec, n)
+    full = nb.empty(n, nb.F)
+    nb.set_reset_full_state(full)
     obs, state, conv = nb.reset(g["reset_s0"])
-    assert np.array_equal(conv.cpu().numpy().astype(bool), g["reset_converged"])
+    conv = conv.cpu().numpy().astype(bool)
+    assert np.array_equal(conv, g["reset_converged"])
+    assert conv.any()
+    full, obs, state = full.cpu().numpy(), obs.cpu().numpy(), state.cpu().numpy()
+    sl, cn, m = spec.full_state_slices(), spec.cn, spec.cn.baseMVA
+    pos = {d: k for k, d in enumerate(cn.devices)}
+    for k in np.flatnonzero(conv):
+        want = g["reset_full_state"][k]
+        compare_full(spec, full[k], np.concatenate([want, np.zeros(spec.K)]), where=(name, k))
+        # the state vector (anm_env.py:562-592): dev_p MW, dev_q MVAr, des_soc MWh, gen_p_max MW
+        vec = np.concatenate([want[sl["dev_p"]] * m, want[sl["dev_q"]] * m,
+                              [want[sl["des_soc"]][pos[i]] * m for i in cn.des_ids],
+                              [want[sl["gen_p_max"]][pos[i]] * m for i in cn.gen_ids]])  # fmt: skip
+        assert rel_err(state[k], vec) < RTOL, (name, k)
+        assert rel_err(obs[k], np.clip(vec, spec.obs_low, spec.obs_high)) < RTOL, (name, k)
+
+
+@pytest.mark.parametrize("name", ["anm6", "3bus_xfmr"])
+def test_list_observation_goldens(name):
+    """List-style observation specs in every unit (kV / kA / degree / MVA / MWh / rad / p.u.; anm_env.py:497-549,
+    constants.py:31-48; the pattern of the reference's tests/envs/custom_obs_space.py:33-72) through the kernel's
+    observation map (unit divisors, angle gathers, magnitudes): the reference's reset and step observations for the
+    recorded s0 / next_vars / actions.  Four identical instances: every lane group must give the same row."""
+    from golden_util import listobs_noise_mask, listobs_spec
+    from gym_anm_b200.native import NativeBatch
+
+    g = load("listobs_%s.npz" % name)
+    spec = listobs_spec(g)
+    ok = ~listobs_noise_mask(spec)
+    B = 4
+    nb = NativeBatch(spec, B)
+    rep = lambda a: np.repeat(np.asarray(a)[None], B, axis=0)  # noqa: E731
+    resets = {int(t): k for k, t in enumerate(g["reset_before_step"])}
+    state = nb.empty(B, nb.S)
+    for t in range(len(g["actions"])):
+        if t in resets:
+            k = resets[t]
+            obs, st, conv = nb.reset(rep(g["s0"][k]))
+            assert bool(conv.all())
+            assert rel_err(obs.cpu().numpy()[:, ok], rep(g["reset_obs"][k])[:, ok]) < RTOL, (name, t, "reset")
+            assert rel_err(st.cpu().numpy(), rep(g["reset_state"][k])) < RTOL
+        obs, r, term = nb.step(rep(g["actions"][t]), rep(g["next_vars"][t]), extras={"state": state})
+        assert np.array_equal(term.cpu().numpy().astype(bool), rep(bool(g["terminated"][t]))), (name, t)
+        o = obs.cpu().numpy()
+        assert np.array_equal(o, rep(o[0]))
+        bad = np.abs(o[0] - g["obs"][t])
+        assert rel_err(o[:, ok], rep(g["obs"][t])[:, ok]) < RTOL, (name, t, int(np.argmax(bad * ok)))
+        assert rel_err(r.cpu().numpy(), rep(g["reward"][t])) < RTOL
+        assert rel_err(state.cpu().numpy(), rep(g["state"][t])) < RTOL
 
 
 @pytest.mark.parametrize("B,steps", [(4096, 120)])
@@ -185,41 +237,208 @@ def test_batch_vs_oracle(B, steps):
     assert n_term > 0  # the divergent cases were exercised
 
 
-def test_synth30_env_vs_oracle():
-    """BASELINE config 4 (30-bus, 32-lane kernel, caller-supplied next_vars)."""
+def _synth30_setup(B, impedance_scale, seed):
     import anm_oracle
     from gym_anm_b200.env_spec import HostEnvSpec
     from gym_anm_b200.native import NativeBatch
     from gym_anm_b200.networks import synth_feeder_network
 
-    B = 256
-    spec = HostEnvSpec(synth_feeder_network(), "state", 1, 0.25, 0.99, 100, np.array([[0, 95]]), (1, 100))
+    spec = HostEnvSpec(synth_feeder_network(impedance_scale=impedance_scale), "state", 1, 0.25, 0.99, 100,
+                       np.array([[0, 95]]), (1, 100))  # fmt: skip
     cn = spec.cn
-    rng = np.random.default_rng(30)
+    rng = np.random.default_rng(seed)
     nb, cpu = NativeBatch(spec, B), anm_oracle.OracleEnv(spec, B)
-    D, ns, ng = cn.N_device, cn.N_des, cn.N_non_slack_gen
+    D, ns = cn.N_device, cn.N_des
     s0 = np.zeros((B, spec.state_N))
     pos = {d: k for k, d in enumerate(cn.devices)}
+    f = 1.0 if impedance_scale == 1.0 else 0.3  # a weak grid needs a light initial state to start from
     for i in cn.load_ids:
-        s0[:, pos[i]] = rng.uniform(cn.devices[i].p_min * 100, 0, B)
+        s0[:, pos[i]] = rng.uniform(cn.devices[i].p_min * 100 * f, 0, B)
     for k, i in enumerate(cn.gen_ids):
-        s0[:, pos[i]] = rng.uniform(0, cn.devices[i].p_max * 100, B)
-        s0[:, 2 * D + ns + k] = rng.uniform(0, cn.devices[i].p_max * 100, B)
+        s0[:, pos[i]] = rng.uniform(0, cn.devices[i].p_max * 100 * f, B)
+        s0[:, 2 * D + ns + k] = rng.uniform(cn.devices[i].p_max * 100 * f, cn.devices[i].p_max * 100, B)
     for k, i in enumerate(cn.des_ids):
         s0[:, 2 * D + k] = rng.uniform(0, cn.devices[i].soc_max * 100, B)
+    return spec, cn, rng, nb, cpu, s0
+
+
+def _synth30_inputs(spec, cn, rng, B, t):
+    a = rng.uniform(spec.action_low, spec.action_high, size=(B, len(spec.action_low)))
+    nv = np.concatenate([rng.uniform([cn.devices[i].p_min * 100 for i in cn.load_ids], 0, (B, cn.N_load)),
+                         rng.uniform(0, [cn.devices[i].p_max * 100 for i in cn.gen_ids], (B, cn.N_non_slack_gen)),
+                         np.full((B, 1), float(t))], axis=1)  # fmt: skip
+    return a, nv
+
+
+def test_synth30_env_vs_oracle():
+    """BASELINE config 4 (30-bus, 32-lane kernel, caller-supplied next_vars)."""
+    B = 256
+    spec, cn, rng, nb, cpu, s0 = _synth30_setup(B, 1.0, 30)
     obs_c, state_c, conv_c = cpu.reset(s0)
     obs_g, state_g, conv_g = nb.reset(s0)
     assert np.array_equal(conv_g.cpu().numpy().astype(bool), conv_c) and conv_c.all()
     assert rel_err(obs_g.cpu().numpy(), obs_c) < RTOL
     for t in range(10):
-        a = rng.uniform(spec.action_low, spec.action_high, size=(B, len(spec.action_low)))
-        nv = np.concatenate([rng.uniform([cn.devices[i].p_min * 100 for i in cn.load_ids], 0, (B, cn.N_load)),
-                             rng.uniform(0, [cn.devices[i].p_max * 100 for i in cn.gen_ids], (B, ng)),
-                             np.full((B, 1), float(t))], axis=1)  # fmt: skip
+        a, nv = _synth30_inputs(spec, cn, rng, B, t)
         obs_g, r_g, term_g = nb.step(a, nv)
         obs_c, r_c, term_c, info = cpu.step(a, nv)
         assert np.array_equal(term_g.cpu().numpy().astype(bool), term_c)
         assert rel_err(obs_g.cpu().numpy(), obs_c) < RTOL and rel_err(r_g.cpu().numpy(), r_c) < RTOL
+
+
+def test_synth30_stressed_full_size_vs_oracle():
+    """BASELINE config 4 at its full size (8192 instances) on the stressed 30-bus feeder (four times the branch
+    impedances; the reference's own numbers for it are in transitions_synth30s.npz): a few per cent of the solves
+    diverge (100 iterations through the block-sparse solver), others need 5-7 iterations.  `terminated` and the
+    Newton iteration counts of every converged solve are bit-exact against the pivoting C oracle."""
+    B = 8192
+    spec, cn, rng, nb, cpu, s0 = _synth30_setup(B, 4.0, 31)
+    obs_c, state_c, conv_c = cpu.reset(s0)
+    obs_g, state_g, conv_g = nb.reset(s0)
+    assert np.array_equal(conv_g.cpu().numpy().astype(bool), conv_c) and conv_c.mean() > 0.99
+    n_term, hist = 0, np.zeros(102, dtype=np.int64)
+    nit = nb.empty(B, dtype=torch.int32)
+    for t in range(3):
+        a, nv = _synth30_inputs(spec, cn, rng, B, t)
+        obs_g, r_g, term_g = nb.step(a, nv, extras={"n_iter": nit})
+        obs_c, r_c, term_c, info = cpu.step(a, nv)
+        tg = term_g.cpu().numpy().astype(bool)
+        assert np.array_equal(tg, term_c), (t, int((tg != term_c).sum()))
+        live = ~term_c
+        assert rel_err(obs_g.cpu().numpy()[live], obs_c[live]) < RTOL and rel_err(r_g.cpu().numpy(), r_c) < RTOL
+        ran = live & (info["n_iter"] > 0)  # instances that were already terminal report 0 iterations
+        assert np.array_equal(nit.cpu().numpy()[ran], info["n_iter"][ran])
+        hist += np.bincount(np.minimum(info["n_iter"][ran], 101), minlength=102)
+        n_term += int(term_c.sum())
+        if t == 0:
+            assert term_c.mean() > 0.01, "the stress fixture must contain divergent instances"
+    assert hist[5:9].sum() > 0, "the stress fixture must contain 5-8 iteration solves"
+
+
+def _singular_leaf_network(bsh):
+    """0 - 1 - 2 chain whose leaf line (r = x = 0.5 p.u.) carries the line charging `bsh`: with bsh = 2.0 the leaf's
+    2x2 Jacobian block at the flat start is [[1, 1], [-1, -1]] -- exactly singular -- while the whole Jacobian is
+    regular and well conditioned (cond ~ 54)."""
+    N_ = None
+    slack = [0, 0, 0, N_, 200, -200, 200, -200, N_, N_, N_, N_, N_, N_, N_]
+    return {"baseMVA": 1,
+            "bus": np.array([[0, 0, 50, 1.0, 1.0], [1, 1, 50, 1.5, 0.5], [2, 1, 50, 1.5, 0.5]]),
+            "branch": np.array([[0, 1, 0.01, 0.1, 0.0, 30, 1, 0], [1, 2, 0.5, 0.5, bsh, 30, 1, 0]]),
+            "device": np.array([slack, [1, 1, -1, 0.2, 0, -10, N_, N_, N_, N_, N_, N_, N_, N_, N_],
+                                [2, 2, -1, 0.2, 0, -10, N_, N_, N_, N_, N_, N_, N_, N_, N_]], dtype=object)}  # fmt: skip
+
+
+_SINGULAR_SCRIPT = r"""
+import os, sys, json
+import numpy as np
+sys.path[:0] = [%(root)r, os.path.join(%(root)r, "oracle"), os.path.join(%(root)r, "tests")]
+os.environ["ANM_DEBUG_NR_MAXIT"] = "%(maxit)d"
+import anm_oracle
+from gym_anm_b200.env_spec import HostEnvSpec
+from gym_anm_b200.native import NativeBatch
+from test_gpu_parity import _singular_leaf_network
+out = {}
+for bsh in (2.0, 2.0 * (1 + 1e-13), 2.0 * (1 - 1e-10), 1.0):
+    spec = HostEnvSpec(_singular_leaf_network(bsh), "state", 0, 0.5, 0.9, 100)
+    pl = np.array([[-0.3, -0.01], [-0.1, -0.02], [0.0, 0.0], [-1.0, -0.005], [-0.2, -0.3]])
+    B = len(pl)
+    z = np.zeros((B, 0))
+    nb, cpu = NativeBatch(spec, B), anm_oracle.OracleEnv(spec, B)
+    full_g, r_g, e_g, pe_g, conv_g = nb.transition(pl, z, z, z)
+    full_c, r_c, e_c, pe_c, conv_c, nit_c = cpu.transition(pl, z, z, z)
+    sl = spec.full_state_slices()
+    vg, vc = full_g.cpu().numpy()[:, sl["bus_v_magn"]], full_c[:, sl["bus_v_magn"]]
+    ag, ac = full_g.cpu().numpy()[:, sl["bus_v_ang"]], full_c[:, sl["bus_v_ang"]]
+    out[repr(bsh)] = dict(conv_g=conv_g.cpu().numpy().astype(bool).tolist(), conv_c=conv_c.tolist(),
+                          v_err=float(np.nanmax(np.abs(vg - vc) / np.maximum(np.abs(vc), 1e-300))),
+                          a_err=float(np.nanmax(np.abs(ag - ac))), finite=bool(np.isfinite(vg).all() and np.isfinite(vc).all()),
+                          vmax=float(np.abs(vc).max()))
+print("RESULT" + json.dumps(out))
+"""
+
+
+@pytest.mark.parametrize("maxit", [1, 2, 100])
+def test_singular_schur_block_guard_matches_pivoting_oracle(maxit):
+    """Adversarial case for the tree elimination (RadialNR inverts 2x2 blocks without pivoting across blocks; the
+    reference's SuperLU pivots): the leaf block of the first Newton iteration is exactly / nearly singular while the
+    Jacobian is regular.  The singular-block guard must redo that iteration with the dense partially pivoted solver:
+    after ONE iteration (ANM_DEBUG_NR_MAXIT=1, in a subprocess) the iterate is finite and equals the pivoting C oracle's
+    (an unguarded block elimination gives inf / NaN here); after two iterations still; and the full solve takes the
+    same decision.  bsh = 1.0 is the regular control case."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", _SINGULAR_SCRIPT % {"root": root, "maxit": maxit}], capture_output=True,
+                         text=True, timeout=600)  # fmt: skip
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
+    for bsh, o in out.items():
+        assert o["conv_g"] == o["conv_c"], (maxit, bsh, o)
+        if maxit <= 2:
+            assert o["finite"], (maxit, bsh, o)
+            assert o["v_err"] < 1e-8 and o["a_err"] < 1e-8, (maxit, bsh, o)
+        elif float(bsh) == 1.0:
+            assert all(o["conv_c"]) and o["v_err"] < 1e-8
+
+
+def test_fast_math_ulp_sweep():
+    """The kernel's own math routines against libm (NumPy): `sincos_fast` (V = |V| e^{j theta} in the Newton loop),
+    the sqrt(fma) magnitude (|V|, |S|, |I|) and the RCP64H + two Newton steps reciprocal (2x2 block inverses)."""
+    import ctypes as C
+
+    from gym_anm_b200 import _capi
+
+    lib = _capi.load_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rng = np.random.default_rng(7)
+
+    def run(kind, x, y=None):
+        xd = torch.as_tensor(x, device=dev)
+        yd = None if y is None else torch.as_tensor(y, device=dev)
+        a, b = torch.empty_like(xd), torch.empty_like(xd)
+        _capi.check(lib.anm_debug_math(kind, xd.numel(), C.c_void_p(xd.data_ptr()),
+                                       None if yd is None else C.c_void_p(yd.data_ptr()), C.c_void_p(a.data_ptr()),
+                                       C.c_void_p(b.data_ptr()), None), lib)  # fmt: skip
+        torch.cuda.synchronize()
+        return a.cpu().numpy(), b.cpu().numpy()
+
+    def ulps(got, want):
+        return np.abs(got - want) / np.spacing(np.abs(want))
+
+    n = 400000
+    # sincos: angles of converging iterations (|theta| < 4), of wandering ones (up to 1e5: libdevice's fast-path range)
+    for scale, max_ulp in ((4.0, 1.5), (100.0, 2.0), (1e5, 2.0)):
+        x = rng.uniform(-scale, scale, n)
+        sn, cs = run(0, x)
+        big = np.abs(np.sin(x)) > 1e-3  # relative accuracy away from the zeros; absolute accuracy everywhere
+        assert ulps(sn[big], np.sin(x)[big]).max() <= max_ulp
+        big = np.abs(np.cos(x)) > 1e-3
+        assert ulps(cs[big], np.cos(x)[big]).max() <= max_ulp
+        assert np.abs(sn - np.sin(x)).max() < 3e-16 and np.abs(cs - np.cos(x)).max() < 3e-16
+    # divergent trajectories: |theta| up to 2^50 stays on the branch-free path with an absolute error of a few 1e-16
+    x = rng.uniform(-1.0, 1.0, n) * 10.0 ** rng.uniform(5, 15, n)
+    x = x[np.abs(x) < 2.0**50]
+    sn, cs = run(0, x)
+    assert np.abs(sn - np.sin(x)).max() < 1e-15 and np.abs(cs - np.cos(x)).max() < 1e-15
+    # beyond 2^50, inf, NaN: libdevice
+    x = np.array([2.0**51, -2.0**60, 1e300, np.inf, -np.inf, np.nan, 0.0, -0.0])
+    sn, cs = run(0, x)
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_allclose(sn, np.sin(x), rtol=1e-15, atol=1e-15, equal_nan=True)
+        np.testing.assert_allclose(cs, np.cos(x), rtol=1e-15, atol=1e-15, equal_nan=True)
+    # magnitudes: per-unit ranges and far beyond; hypot is the reference (numpy abs of a complex)
+    x = rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-8, 8, n)
+    y = rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-8, 8, n)
+    mag, _ = run(1, x, y)
+    assert ulps(mag, np.hypot(x, y)).max() <= 1.0
+    # reciprocal
+    x = rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-30, 30, n)
+    x = x[x != 0.0]
+    rc, _ = run(2, x)
+    assert ulps(rc, 1.0 / x).max() <= 1.0
 
 
 def test_host_buffer_path_and_terminal_semantics():

@@ -121,7 +121,7 @@ def test_capi_library_exports_every_declared_symbol():
     lib = _capi.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.anm_abi_version() == 2
+    assert lib.anm_abi_version() == 3
     # create must fail loudly (not fall back) without a usable device / with bad arguments
     spec = anm6easy_spec()
     net, env, keep = spec.descs()

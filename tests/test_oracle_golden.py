@@ -15,7 +15,7 @@ import ref_loader
 from golden_util import load, rel_err, transition_spec
 from gym_anm_b200.env_spec import anm6easy_spec
 
-NETS = ["2bus", "3bus_loop", "3bus_xfmr", "3bus_reset", "2bus_flex", "anm6", "synth30"]
+NETS = ["2bus", "3bus_loop", "3bus_xfmr", "3bus_reset", "2bus_flex", "anm6", "synth30", "synth30s"]
 
 
 def _resets(g):
@@ -172,3 +172,33 @@ def test_seed_stream_matches_reference_draw_order():
             s0 = anm_numpy.anm6easy_init_state(spec, rng)
         assert np.array_equal(s0, g["reset_s0"][k])
         rng.integers(1, 365)
+
+
+@pytest.mark.parametrize("name", ["anm6", "3bus_xfmr"])
+def test_list_observation_goldens_c_oracle(name):
+    """List-style observation specs with units (anm_env.py:497-549, constants.py:31-48): the host-side spec gives the
+    reference's observation-space bounds, and the C restatement replays the recorded episode (same s0 / next_vars /
+    actions) to the reference's observations."""
+    from golden_util import listobs_noise_mask, listobs_spec
+
+    g = load("listobs_%s.npz" % name)
+    spec = listobs_spec(g)
+    ok = ~listobs_noise_mask(spec)
+    np.testing.assert_allclose(spec.obs_low, g["obs_low"], rtol=1e-12)
+    np.testing.assert_allclose(spec.obs_high, g["obs_high"], rtol=1e-12)
+    np.testing.assert_allclose(spec.action_low, g["action_low"], rtol=1e-12)
+    np.testing.assert_allclose(spec.action_high, g["action_high"], rtol=1e-12)
+    env = anm_oracle.OracleEnv(spec, 1)
+    resets = {int(t): k for k, t in enumerate(g["reset_before_step"])}
+    for t in range(len(g["actions"])):
+        if t in resets:
+            k = resets[t]
+            obs, state, conv = env.reset(g["s0"][k][None])
+            assert conv[0]
+            assert rel_err(obs[0][ok], g["reset_obs"][k][ok]) < 1e-8, (name, t, "reset obs")
+            assert rel_err(state[0], g["reset_state"][k]) < 1e-8
+        obs, r, term, info = env.step(g["actions"][t][None], g["next_vars"][t][None])
+        assert bool(term[0]) == bool(g["terminated"][t]), (name, t)
+        assert rel_err(obs[0][ok], g["obs"][t][ok]) < 1e-8, (name, t, np.abs(obs[0] - g["obs"][t]).argmax())
+        assert rel_err(r[0], g["reward"][t]) < 1e-8
+        assert rel_err(info["state"][0], g["state"][t]) < 1e-8
