@@ -113,25 +113,13 @@ _PROTOS = {
     "anm_destroy": (C.c_int, [C.c_void_p]),
     "anm_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(Sizes)]),
     "anm_reset": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
-    "anm_set_reset_full_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "anm_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "anm_reset_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 3 + [C.c_void_p]),
-    "anm_rng_state_bytes": (C.c_int64, [C.c_void_p]),
-    "anm_get_rng": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "anm_set_rng": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "anm_debug_set_launch_ordinal": (C.c_int, [C.c_void_p, C.c_uint64]),
-    "anm_debug_math": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_void_p]),
-    "anm_debug_fp64_peak": (C.c_int, [C.c_int, c_double_p]),
     "anm_debug_project": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int32, C.c_double, C.c_double, c_double_p]),
     "anm_debug_blob": (C.c_int64, [C.POINTER(NetworkDesc), C.POINTER(EnvDesc), C.c_void_p, C.c_int64]),
     "anm_debug_rng": (C.c_int, [C.c_uint64, C.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p]),
     "anm_step": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(StepExtras), C.c_void_p]),
     "anm_rollout": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p]),
-    "anm_gather_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
-    "anm_gather_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "anm_step_packed": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int32, C.POINTER(StepExtras), C.c_void_p]),
-    "anm_gather_wait": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
-    "anm_gather_destroy": (C.c_int, [C.c_void_p]),
     "anm_set_autoreset_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "anm_transition": (C.c_int, [C.c_void_p] + [C.c_void_p] * 9 + [C.c_void_p]),
     "anm_get_state": (C.c_int, [C.c_void_p] + [C.c_void_p] * 3 + [C.c_void_p]),
@@ -167,7 +155,7 @@ def load_library(path=None):
     for name, (res, args) in _PROTOS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.anm_abi_version() != 3:
+    if lib.anm_abi_version() != 2:
         raise NativeLibraryError("ABI version mismatch in %s" % path)
     _LIB = lib
     return lib

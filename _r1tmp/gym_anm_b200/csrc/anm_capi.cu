@@ -73,43 +73,6 @@ int var_limit(const AnmConstHeader& H, int quantity) {
 
 }  // namespace
 
-namespace anm {
-/* test hook (anm_debug_math): the kernel's own fast math routines evaluated element-wise */
-__global__ void debug_math_kernel(int kind, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
-                                  double* __restrict__ a, double* __restrict__ b) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (kind == 0) {
-    double sn, cs;
-    sincos_fast(x[i], sn, cs);
-    a[i] = sn;
-    b[i] = cs;
-  } else if (kind == 1) {
-    a[i] = cabs2(x[i], y[i]);
-  } else {
-    a[i] = fast_rcp(x[i]);
-  }
-}
-}  // namespace anm
-
-namespace anm {
-/* fp64 FMA throughput of the device (the denominator of bench.py's fp64 roofline leg): eight independent DFMA
- * chains per thread, no memory traffic */
-__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
-  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-#pragma unroll 1
-  for (int i = 0; i < iters; ++i) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-    }
-  }
-  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-  if (s == 12345.678) out[0] = s; /* keeps the chains alive */
-}
-}  // namespace anm
-
 struct anm_handle_s {
   int device = 0;
   int64_t B = 0;
@@ -120,8 +83,8 @@ struct anm_handle_s {
   double* d_aux = nullptr;
   uint8_t* d_term = nullptr;
   uint32_t* d_episode = nullptr;
-  uint32_t* d_seq = nullptr; /* [B] per-instance launch ordinals (launch chaining, anm_kernels.cuh) */
-  unsigned long long* d_ticket = nullptr; /* [16] (its own 128-byte line) CTAs started so far on this handle */
+  uint32_t* d_seq = nullptr; /* [B + 64] per-instance launch ordinals, then the ticket counter (launch chaining,
+                                anm_kernels.cuh) */
   AnmPcg64* d_rng = nullptr; /* [B] per-instance random streams (anm_seed / anm_reset_seeded) */
   bool seeded = false;
   uint8_t *d_need = nullptr, *d_conv_tmp = nullptr; /* seeded reset: still looking for an initial state / last attempt */
@@ -130,20 +93,6 @@ struct anm_handle_s {
   uint32_t* wd_dev = nullptr;
   const double* pool = nullptr;
   int64_t pool_size = 0;
-  double* reset_full = nullptr; /* optional [B, n_full] output of every reset launch (anm_set_reset_full_state) */
-  /* fused observation all-gather (anm_gather_*): this rank's buffer [flags 1 KB | slots x rows x (O + 2) doubles], the
-   * peers' buffers opened over CUDA IPC, and the device arrays of pointers the kernel reads */
-  struct Gather {
-    int world = 0, rank = 0, slots = 0;
-    int64_t rows = 0, row0 = 0;
-    unsigned char* base = nullptr;            /* own allocation */
-    std::vector<void*> peer_base;             /* [world] mapped base pointers (own: base) */
-    double** d_peers = nullptr;               /* device: [world] data regions */
-    unsigned long long** d_flags = nullptr;   /* device: [world] flag regions */
-    unsigned long long* d_state = nullptr;    /* device: [0] steps completed, [8..72) CTA counters */
-    int64_t steps_host = 0;                   /* gather steps launched so far (host mirror of d_state[0]) */
-    bool attached = false;
-  } g;
   /* launch geometry */
   int lpe = 32, gpb = 4, grid = 1, smem = 0, num_sms = 1;
   /* host-buffer path */
@@ -161,9 +110,7 @@ struct anm_handle_s {
   } hset[2];
   int hset_next = 0;
   cudaStream_t st_in = nullptr, st_out = nullptr;
-  int64_t wd_last = 0;  /* the most recent launch's own share of wd_steps */
-  int64_t wd_steps = 0; /* steps x passes of every launch since the last fully ordered one: a chained launch may have
-                           to wait for all of them (chained waits are transitive) -- the watchdog limit of the next */
+  int64_t last_T = 1; /* steps per instance of the most recent launch (watchdog limit of the next one) */
   bool st_last_was_rollout = false; /* the compute stream's last operation was one of our rollout kernels */
   int64_t launches = 0;
 };
@@ -245,11 +192,6 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
   H.base_mva = net->base_mva; H.delta_t = net->delta_t; H.lamb = net->lamb; H.gamma = env->gamma;
   H.clip_e = env->clip_e_loss; H.clip_pen = env->clip_penalty;
   H.term_reward = -env->clip_penalty / (1.0 - env->gamma); /* anm_env.py:430 */
-  H.nr_maxit = ANM_NR_MAXIT;
-  if (const char* e = getenv("ANM_DEBUG_NR_MAXIT")) { /* single-iteration tests of the solvers; never set in production */
-    const int v = atoi(e);
-    if (v >= 0 && v < ANM_NR_MAXIT) H.nr_maxit = v;
-  }
 
   std::vector<int> dev_bus(D), dev_type(D), dev_slot(D);
   std::vector<int> gens, dess;
@@ -566,8 +508,8 @@ int build_blob(const anm_network_desc* net, const anm_env_desc* env, AnmConstHea
     H.w_devp = take(D); H.w_devq = take(D); H.w_ppot = take(D); H.w_busp = take(N); H.w_busq = take(N);
     H.w_x = take(M); H.w_vre = take(N); H.w_vim = take(N); H.w_ere = take(N); H.w_eim = take(N);
     H.w_ire = take(N); H.w_iim = take(N);
-    /* RadialNR: two sets of exchange slots; its singular-block guard redoes an iteration on the dense M x (M+1) system */
-    H.w_J = take(H.solver == 4 ? 0 : (H.solver == 2 ? std::max(2 * 6 * lanes_for(H), M * (M + 1)) : M * (M + 1))); H.w_rowh = take(2 * H.n_ctrl * ANM_MAX_ROWS + H.n_ctrl); /* -h / -inf, h / 0, finite-row mask per device */
+    H.w_J = take(H.solver == 4 ? 0 : (H.solver == 2 ? 2 * 6 * lanes_for(H) /* RadialNR: two sets of exchange slots */
+                                                                 : M * (M + 1))); H.w_rowh = take(2 * H.n_ctrl * ANM_MAX_ROWS + H.n_ctrl); /* -h / -inf, h / 0, finite-row mask per device */
     H.w_brp = take(L); H.w_brq = take(L); H.w_brs = take(L); H.w_brire = take(L); H.w_briim = take(L);
     H.w_full = take(H.n_full); H.w_s0 = take(H.n_state > K ? H.n_state : K);
     H.w_vx = take(4 * N);
@@ -700,17 +642,11 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
   p.pool = h->pool; p.pool_size = h->pool_size;
   /* launch chaining: wait for the previous launch per instance, publish this one (anm_kernels.cuh) */
   p.seq = h->d_seq;
-  p.ticket = h->d_ticket;
+  p.ticket = h->d_seq + h->B + 32; /* its own 128-byte line */
   {
-    /* Watchdog limit: 2 s plus 2 ms for every step x pass of the launches this one may (transitively) have to wait
-     * for.  A launch that is not chained executes griddepcontrol.wait, i.e. runs after everything earlier has
-     * completed: the sum starts again with it. */
     const int64_t passes = (h->B + (int64_t)h->grid * h->gpb - 1) / ((int64_t)h->grid * h->gpb);
-    const bool chained = pdl_enabled() && (flags & ANM_LF_CHAINED);
-    if (!chained) h->wd_steps = 0;
-    p.wd_limit_ns = 2000000000ull + 2000000ull * (uint64_t)h->wd_steps;
-    h->wd_last = (int64_t)(p.T > 1 ? p.T : 1) * passes;
-    h->wd_steps += h->wd_last;
+    p.wd_limit_ns = 2000000000ull + 2000000ull * (uint64_t)(h->last_T * passes);
+    h->last_T = p.T > 1 ? p.T : 1;
   }
   p.watchdog = h->wd_dev;
   const bool pdl = pdl_enabled();
@@ -802,8 +738,7 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   ALLOC(h->d_aux, B * H.K * sizeof(double));
   ALLOC(h->d_term, B);
   ALLOC(h->d_episode, B * sizeof(uint32_t));
-  ALLOC(h->d_seq, B * sizeof(uint32_t));
-  ALLOC(h->d_ticket, 16 * sizeof(unsigned long long));
+  ALLOC(h->d_seq, (B + 64) * sizeof(uint32_t));
   ALLOC(h->s_action, B * H.n_action * sizeof(double));
   ALLOC(h->s_nv, B * H.n_next_vars * sizeof(double));
   ALLOC(h->s_obs, B * H.n_obs * sizeof(double));
@@ -818,8 +753,7 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   if (e == cudaSuccess) e = cudaMemset(h->d_aux, 0, B * H.K * sizeof(double) + (H.K ? 0 : 16));
   if (e == cudaSuccess) e = cudaMemset(h->d_term, 1, B); /* nothing is runnable before the first reset */
   if (e == cudaSuccess) e = cudaMemset(h->d_episode, 0, B * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(h->d_seq, 0, B * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, 16 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_seq, 0, (B + 64) * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->wd_host, ANM_WD_WORDS * sizeof(uint32_t), cudaHostAllocMapped);
   if (e == cudaSuccess) {
     memset(h->wd_host, 0, ANM_WD_WORDS * sizeof(uint32_t));
@@ -836,10 +770,9 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
 
 int anm_destroy(anm_handle h) {
   if (!h) return ANM_OK;
-  anm_gather_destroy(h);
   DeviceGuard guard(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_soc); cudaFree(h->d_aux); cudaFree(h->d_term); cudaFree(h->d_episode);
-  cudaFree(h->d_seq); cudaFree(h->d_ticket);
+  cudaFree(h->d_seq);
   cudaFree(h->d_rng); cudaFree(h->d_need); cudaFree(h->d_conv_tmp); cudaFree(h->d_remaining);
   if (h->h_remaining) cudaFreeHost(h->h_remaining);
   if (h->wd_host) cudaFreeHost(h->wd_host);
@@ -878,7 +811,6 @@ int anm_reset(anm_handle h, const double* s0, const uint8_t* mask, double* obs, 
   memset(&p, 0, sizeof(p));
   p.mode = ANM_MODE_RESET;
   p.s0 = s0; p.mask = mask; p.obs = obs; p.state = state; p.converged = converged;
-  p.full_state = h->reset_full;
   return launch(h, p, (cudaStream_t)stream);
 }
 
@@ -1020,193 +952,6 @@ int anm_debug_rng(uint64_t seed, int32_t n, const int32_t* kind, const double* l
   anm_pcg_seed(r, seed);
   for (int32_t i = 0; i < n; ++i)
     out[i] = kind[i] ? anm_rng_uniform(r, lo[i], hi[i]) : (double)anm_rng_integers(r, (int64_t)lo[i], (int64_t)hi[i]);
-  return ANM_OK;
-}
-
-int anm_debug_set_launch_ordinal(anm_handle h, uint64_t k) {
-  if (!h) return fail(ANM_E_INVALID, "null handle");
-  DeviceGuard guard(h->device);
-  CUDA_TRY(cudaDeviceSynchronize());
-  const unsigned long long t = (unsigned long long)k * (unsigned long long)h->grid;
-  std::vector<uint32_t> seq((size_t)h->B, (uint32_t)k);
-  CUDA_TRY(cudaMemcpy(h->d_ticket, &t, sizeof(t), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->d_seq, seq.data(), seq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  return ANM_OK;
-}
-
-int64_t anm_rng_state_bytes(anm_handle h) { return h ? (int64_t)h->B * (int64_t)sizeof(AnmPcg64) : 0; }
-
-int anm_get_rng(anm_handle h, void* out, void* stream) {
-  if (!h || !out) return fail(ANM_E_INVALID, "anm_get_rng: null argument");
-  if (!h->seeded) return fail(ANM_E_INVALID, "anm_get_rng: call anm_seed first");
-  DeviceGuard guard(h->device);
-  CUDA_TRY(cudaMemcpyAsync(out, h->d_rng, (size_t)h->B * sizeof(AnmPcg64), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  return ANM_OK;
-}
-
-int anm_set_rng(anm_handle h, const void* in, void* stream) {
-  if (!h || !in) return fail(ANM_E_INVALID, "anm_set_rng: null argument");
-  DeviceGuard guard(h->device);
-  if (!h->d_rng) CUDA_TRY(cudaMalloc((void**)&h->d_rng, (size_t)h->B * sizeof(AnmPcg64)));
-  CUDA_TRY(cudaMemcpyAsync(h->d_rng, in, (size_t)h->B * sizeof(AnmPcg64), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  h->seeded = true;
-  return ANM_OK;
-}
-
-int anm_debug_math(int32_t kind, int64_t n, const double* x, const double* y, double* a, double* b, void* stream) {
-  if (kind < 0 || kind > 2 || n < 0 || !x || !a || (kind == 0 && !b) || (kind == 1 && !y))
-    return fail(ANM_E_INVALID, "anm_debug_math: bad argument");
-  if (n == 0) return ANM_OK;
-  anm::debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, n, x, y, a, b);
-  CUDA_TRY(cudaPeekAtLastError());
-  return ANM_OK;
-}
-
-#define ANM_GATHER_FLAG_BYTES 1024
-#define ANM_GATHER_MAX_WORLD 64
-
-int anm_gather_create(anm_handle h, int32_t world, int32_t rank, int64_t row0, int64_t rows_global, int32_t slots,
-                      void* ipc_handle_out) {
-  if (!h || !ipc_handle_out) return fail(ANM_E_INVALID, "anm_gather_create: null argument");
-  if (world < 1 || world > ANM_GATHER_MAX_WORLD || rank < 0 || rank >= world || slots < 1 || slots > 64)
-    return fail(ANM_E_INVALID, "anm_gather_create: world %d / rank %d / slots %d out of range", world, rank, slots);
-  if (row0 < 0 || rows_global < row0 + h->B) return fail(ANM_E_INVALID, "anm_gather_create: rows [%lld, %lld) do not fit %lld global rows",
-                                                         (long long)row0, (long long)(row0 + h->B), (long long)rows_global);
-  if (h->g.base) return fail(ANM_E_INVALID, "anm_gather_create: a gather is already attached to this handle");
-  DeviceGuard guard(h->device);
-  auto& g = h->g;
-  g.world = world; g.rank = rank; g.slots = slots; g.rows = rows_global; g.row0 = row0;
-  const size_t W = (size_t)h->H.n_obs + 2;
-  const size_t bytes = ANM_GATHER_FLAG_BYTES + (size_t)slots * (size_t)rows_global * W * sizeof(double);
-  CUDA_TRY(cudaMalloc((void**)&g.base, bytes));
-  CUDA_TRY(cudaMemset(g.base, 0, bytes));
-  CUDA_TRY(cudaMalloc((void**)&g.d_state, 128 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(g.d_state, 0, 128 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMalloc((void**)&g.d_peers, ANM_GATHER_MAX_WORLD * sizeof(void*)));
-  CUDA_TRY(cudaMalloc((void**)&g.d_flags, ANM_GATHER_MAX_WORLD * sizeof(void*)));
-  CUDA_TRY(cudaDeviceSynchronize());
-  cudaIpcMemHandle_t mh;
-  CUDA_TRY(cudaIpcGetMemHandle(&mh, g.base));
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
-  memcpy(ipc_handle_out, &mh, sizeof(mh));
-  return ANM_OK;
-}
-
-int anm_gather_attach(anm_handle h, const void* ipc_handles) {
-  if (!h || !ipc_handles) return fail(ANM_E_INVALID, "anm_gather_attach: null argument");
-  auto& g = h->g;
-  if (!g.base || g.attached) return fail(ANM_E_INVALID, "anm_gather_attach: call anm_gather_create first (once)");
-  DeviceGuard guard(h->device);
-  g.peer_base.assign((size_t)g.world, nullptr);
-  std::vector<double*> peers((size_t)g.world);
-  std::vector<unsigned long long*> flags((size_t)g.world);
-  for (int p = 0; p < g.world; ++p) {
-    void* b = g.base;
-    if (p != g.rank) {
-      cudaIpcMemHandle_t mh;
-      memcpy(&mh, (const unsigned char*)ipc_handles + (size_t)p * sizeof(mh), sizeof(mh));
-      cudaError_t e = cudaIpcOpenMemHandle(&b, mh, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) return fail(ANM_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
-    }
-    g.peer_base[(size_t)p] = b;
-    flags[(size_t)p] = (unsigned long long*)b;
-    peers[(size_t)p] = (double*)((unsigned char*)b + ANM_GATHER_FLAG_BYTES);
-  }
-  CUDA_TRY(cudaMemcpy(g.d_peers, peers.data(), peers.size() * sizeof(void*), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(g.d_flags, flags.data(), flags.size() * sizeof(void*), cudaMemcpyHostToDevice));
-  g.attached = true;
-  return ANM_OK;
-}
-
-int anm_gather_destroy(anm_handle h) {
-  if (!h) return ANM_OK;
-  auto& g = h->g;
-  if (!g.base) return ANM_OK;
-  DeviceGuard guard(h->device);
-  cudaDeviceSynchronize();
-  for (int p = 0; p < (int)g.peer_base.size(); ++p)
-    if (p != g.rank && g.peer_base[(size_t)p]) cudaIpcCloseMemHandle(g.peer_base[(size_t)p]);
-  cudaFree(g.base); cudaFree(g.d_state); cudaFree(g.d_peers); cudaFree(g.d_flags);
-  g = anm_handle_s::Gather();
-  return ANM_OK;
-}
-
-int anm_step_packed(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
-                    uint8_t* terminated, double* packed, int32_t gather, const anm_step_extras* ex, void* stream) {
-  if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_packed: null argument");
-  if (!next_vars && h->H.table_len == 0)
-    return fail(ANM_E_INVALID, "anm_step_packed: next_vars is NULL but the environment has no built-in table");
-  if (gather && !h->g.attached) return fail(ANM_E_INVALID, "anm_step_packed: no gather attached (anm_gather_create / _attach)");
-  if (!gather && !packed) return fail(ANM_E_INVALID, "anm_step_packed: neither a packed output nor the gather was asked for");
-  DeviceGuard guard(h->device);
-  AnmLaunch p;
-  memset(&p, 0, sizeof(p));
-  p.mode = ANM_MODE_STEP;
-  p.action = action; p.next_vars = next_vars; p.obs = obs; p.reward = reward; p.term_out = terminated;
-  p.packed = packed;
-  if (ex) {
-    p.state = ex->state; p.e_loss = ex->e_loss; p.penalty = ex->penalty; p.n_iter = ex->n_iter;
-    p.full_state = ex->full_state;
-  }
-  if (gather) {
-    auto& g = h->g;
-    p.g_peers = g.d_peers; p.g_flags = g.d_flags; p.g_state = g.d_state;
-    p.g_rows = g.rows; p.g_row0 = g.row0; p.g_world = g.world; p.g_rank = g.rank; p.g_slots = g.slots;
-    ++g.steps_host;
-  }
-  /* never chained: the gather slot is derived from the completed-step count at kernel entry; remote stores need the
-   * system-scope fence */
-  return launch(h, p, (cudaStream_t)stream, gather ? ANM_LF_SYSOUT : 0u);
-}
-
-int anm_gather_wait(anm_handle h, double** rows_out, void* stream) {
-  if (!h) return fail(ANM_E_INVALID, "null handle");
-  auto& g = h->g;
-  if (!g.attached || g.steps_host < 1) return fail(ANM_E_INVALID, "anm_gather_wait: no gather step has been launched");
-  DeviceGuard guard(h->device);
-  anm::gather_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((const unsigned long long*)g.base, g.d_state, g.world,
-                                                              30000000000ull);
-  CUDA_TRY(cudaPeekAtLastError());
-  if (rows_out) {
-    const size_t W = (size_t)h->H.n_obs + 2;
-    const int64_t slot = (g.steps_host - 1) % g.slots;
-    *rows_out = (double*)(g.base + ANM_GATHER_FLAG_BYTES) + (size_t)slot * (size_t)g.rows * W;
-  }
-  return ANM_OK;
-}
-
-int anm_debug_fp64_peak(int device, double* tflops_out) {
-  if (!tflops_out) return fail(ANM_E_INVALID, "null argument");
-  DeviceGuard guard(device);
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  double* d = nullptr;
-  CUDA_TRY(cudaMalloc((void**)&d, 64));
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0));
-  CUDA_TRY(cudaEventCreate(&e1));
-  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
-  double best = 0.0;
-  for (int rep = 0; rep < 4; ++rep) { /* the first pass warms up; best of the rest */
-    CUDA_TRY(cudaEventRecord(e0, 0));
-    anm::fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
-    CUDA_TRY(cudaEventRecord(e1, 0));
-    CUDA_TRY(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
-    if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d);
-  *tflops_out = best;
-  return ANM_OK;
-}
-
-int anm_set_reset_full_state(anm_handle h, double* full_state) {
-  if (!h) return fail(ANM_E_INVALID, "null handle");
-  h->reset_full = full_state;
   return ANM_OK;
 }
 
@@ -1372,7 +1117,6 @@ int anm_rollout_host_async(anm_handle h, int64_t T, const double* action, const 
   if (hs.used) { /* the set is free once its previous kernel has read the inputs and its outputs are downloaded */
     CUDA_TRY(cudaEventSynchronize(hs.ev_k));
     CUDA_TRY(cudaEventSynchronize(hs.ev_out));
-    h->wd_steps = h->wd_last; /* everything but the most recent launch is known to be complete */
   }
   if (int rc = hostset_reserve(h, hs, rows, next_vars != nullptr)) return rc;
   /* inputs: copy engine, own stream; the HOST waits for the upload (the kernels of the earlier calls are still

@@ -98,21 +98,12 @@ struct AnmLaunch {
                             Newton loop, SM cycles of the whole pass -- or NULL */
   /* cross-launch ordering (see "launch chaining" below) */
   uint32_t* seq;         /* [B] ordinal of the last launch that finished with this instance          */
-  unsigned long long* ticket; /* [1] CTAs started so far on this handle (64-bit: never wraps); ordinal of a launch =
-                                 (uint32)(ticket / grid + 1), compared modulo 2^32 with seq[e] */
+  uint32_t* ticket;      /* [1] CTAs started so far on this handle: ordinal of a launch = ticket / grid + 1 */
   uint32_t* watchdog;    /* [ANM_WD_WORDS] mapped host memory: record of a chaining time-out, or zeros */
   uint32_t flags;        /* ANM_LF_* */
   int32_t* phase_stats;  /* [B, 16] diagnostic builds only: SM cycles at the end of each phase -- or NULL */
   int32_t T;             /* step mode: consecutive steps in this launch; inputs / outputs are [T, B, .] (anm_rollout) */
   uint64_t wd_limit_ns;  /* chaining watchdog: longest legitimate wait for the previous launch */
-  /* packed rows [obs | reward | terminated] of a step: local copy and / or the fused all-gather ("observation
-   * all-gather" below): every rank's gather buffer and arrival flags, mapped into this process over NVLink */
-  double* packed;                      /* [B, O + 2] or NULL */
-  double* const* g_peers;              /* [g_world] rows of every rank's gather buffer [g_slots][g_rows][O + 2], or NULL */
-  unsigned long long* const* g_flags;  /* [g_world] every rank's arrival flags (one word per sender) */
-  unsigned long long* g_state;         /* local: [0] gather steps completed; [8 .. 8 + 64) CTA-done counters */
-  int64_t g_rows, g_row0;              /* rows of one slot (global instances); this rank's first row */
-  int32_t g_world, g_rank, g_slots;
 };
 #define ANM_WD_WORDS 8
 #define ANM_LF_CHAINED 1u /* inputs do not depend on earlier work in the stream: skip griddepcontrol.wait */
@@ -135,8 +126,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
  * Launch k (k = 1, 2, ...) may touch instance e once seq[e] == k-1 and publishes seq[e] = k when it is done with it.
  * k is not a kernel argument (a CUDA graph replays its arguments): every CTA draws a ticket from a device counter
  * when it starts, and because all launches of a handle have the same grid and a launch only becomes resident after
- * every CTA of its predecessor has started (and drawn), k = ticket / gridDim.x + 1 in every CTA of the launch (the
- * ticket counter is 64 bits wide, so it never wraps; k itself is used modulo 2^32, like seq[e]).
+ * every CTA of its predecessor has started (and drawn), k = ticket / gridDim.x + 1 in every CTA of the launch.
  * seq[e] is published with a release store after a fence that covers the whole lane group's writes and consumed
  * with an acquire load; the carried state is read with ld.global.cg (L2), never from a possibly stale L1 line.
  * No deadlock: by the same induction every CTA that is being waited for is already running.  A wait that outlasts
@@ -182,7 +172,7 @@ __device__ __forceinline__ void seq_publish(uint32_t* p, uint32_t v) {
 /* Also draws the CTA's ticket (launch ordinal, see "launch chaining") while the copy is in flight and signals
  * launch_dependents once the ticket is drawn; returns the ordinal of this launch. */
 __device__ __forceinline__ uint32_t stage_constants(unsigned char* smem, const unsigned char* gblob, int bytes,
-                                                    unsigned long long* ticket) {
+                                                    uint32_t* ticket) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* ord = reinterpret_cast<uint32_t*>(smem + 16);
   const uint32_t bar_a = smem_u32(bar);
@@ -200,9 +190,7 @@ __device__ __forceinline__ uint32_t stage_constants(unsigned char* smem, const u
           : "memory");
       done += chunk;
     }
-    const unsigned long long k64 = atomicAdd(ticket, 1ull) / (unsigned long long)gridDim.x;
-    *ord = (uint32_t)k64 + 1u;
-    *reinterpret_cast<unsigned long long*>(smem + 24) = k64; /* launches before this one (64-bit) */
+    *ord = atomicAdd(ticket, 1u) / gridDim.x + 1u;
   }
   __syncthreads();         /* the ticket is drawn (its value has come back) before ...                        */
   pdl_launch_dependents(); /* ... this CTA lets the next launch of the stream become resident                 */
@@ -601,7 +589,7 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
     lmax = g_max<LPE, FULL>(lmax, gm);
     bad = g_any<FULL>(bad, gm);
     diff = bad ? CUDART_NAN : lmax; /* numpy.linalg.norm(F, inf) propagates NaN */
-    if (!(diff > ANM_NR_TOL) || it >= H.nr_maxit) break;
+    if (!(diff > ANM_NR_TOL) || it >= ANM_NR_MAXIT) break;
     ++it;
     gsync<FULL>(gm);
 
@@ -703,7 +691,7 @@ __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws,
     lmax = g_max<LPE, FULL>(lmax, gm);
     bad = g_any<FULL>(bad, gm);
     diff = bad ? CUDART_NAN : lmax;
-    if (!(diff > ANM_NR_TOL) || it >= H.nr_maxit) break;
+    if (!(diff > ANM_NR_TOL) || it >= ANM_NR_MAXIT) break;
     ++it;
     gsync<FULL>(gm);
 
@@ -864,7 +852,6 @@ struct SmallNR {
     const int b = active ? (lane - part * n + 1) : 1; /* bus of my row / unknown */
     const int partner = active ? (part ? lane - n : lane + n) : lane;
     const int giw = (threadIdx.x & 31) / LPE; /* my group's index inside the warp */
-    const int maxit = H.nr_maxit;
     const double2* Yd = reinterpret_cast<const double2*>(C.y_dense) + (size_t)b * NB;
 #if ANM_VAR_YREG
     double yre[NB], yim[NB];
@@ -930,9 +917,9 @@ struct SmallNR {
         bad = (nanb & gm) != 0u; /* numpy: norm(F, inf) is NaN, and `nan > tol` is False (:218) */
         big = (bigb & gm) != 0u;
 #if ANM_DIAG
-        if (bad || !big || it >= maxit) done = true, t_done = clock64(); else ++it;
+        if (bad || !big || it >= ANM_NR_MAXIT) done = true, t_done = clock64(); else ++it;
 #else
-        if (bad || !big || it >= maxit) done = true; else ++it;
+        if (bad || !big || it >= ANM_NR_MAXIT) done = true; else ++it;
 #endif
       }
       if (__all_sync(ANM_FULL, done)) break;
@@ -1036,30 +1023,6 @@ struct SmallNR {
   }
 };
 
-/* ---- singular-block guard of the tree elimination (RadialNR below) ------------------------------------------------
- * RadialNR inverts 2x2 (Schur) blocks without pivoting across blocks; the reference's SuperLU pivots.  Every inverted
- * block is watched: when its determinant has cancelled to less than ANM_SING_TAU of its products
- * (|det| <= tau (|d00 d11| + |d01 d10|)) while the Jacobian itself may be perfectly regular, the instance leaves the
- * tree solver and its whole power flow is redone, from the flat start, by the dense partially pivoted solver
- * (nr_generic) -- what the reference would have computed.  The test costs a handful of instructions per level and one
- * vote per iteration; the redo is a cold path outside the Newton loop and involves only the instance that tripped (an
- * instance's arithmetic never depends on the company it keeps in its warp). */
-#ifndef ANM_SING_TAU
-#define ANM_SING_TAU 1e-7
-#endif
-#ifndef ANM_SING_GUARD
-#define ANM_SING_GUARD 1 /* 0 compiles the guard out (A/B builds only) */
-#endif
-/* out of line (the hot instruction stream stays what it is); returns it | converged << 8 | stable << 9 */
-template <int LPE>
-__device__ __noinline__ int nr_generic_cold(const unsigned char* blob, double* __restrict__ ws, int lane, unsigned gm) {
-  const Cst C(blob); /* resolved here, not passed: the caller's copy stays in registers */
-  int it = 0;
-  bool conv = false, stable = false;
-  nr_generic<LPE, false>(C, ws, lane, gm, true, it, conv, stable);
-  return it | (conv ? 256 : 0) | (stable ? 512 : 0);
-}
-
 /* ---- Newton-Raphson for RADIAL networks (the bus graph is a tree rooted at the slack bus) --------
  * Lane b-1 owns non-slack bus b: its two unknowns (theta_b, |V|_b), its two mismatch rows and the three
  * non-zero 2x2 Jacobian blocks of a tree: D = J[b][b], L = J[b][parent], U = J[parent][b]
@@ -1067,10 +1030,10 @@ __device__ __noinline__ int nr_generic_cold(const unsigned char* blob, double* _
  * along the tree: leaves first, every bus folds  U D^-1 [L | f]  into its parent's (D, f) (one shuffle
  * round per tree level), then the step is back-substituted from the root down -- the critical path is the
  * tree depth instead of 2(N-1) pivots, and an environment needs only N-1 lanes.  2x2 diagonal blocks are
- * inverted by the adjugate.  No pivoting across blocks; instead every inverted block is watched (singular-block
- * guard: |det| <= ANM_SING_TAU (|d00 d11| + |d01 d10|)) and the rare iteration in which a Schur block has all but
- * cancelled while the Jacobian itself is regular is redone by the dense partially pivoted solver (dense_step_cold),
- * which is what the reference's SuperLU does.  Lock-step lane groups, full-mask intrinsics, like SmallNR. */
+ * inverted by the adjugate.  No pivoting across blocks: a (near-)singular Schur block while the Jacobian itself
+ * is regular is non-generic (never observed in 5e5 instance-steps against the pivoting oracle, divergent
+ * instances included); ANM_SOLVER=generic selects the dense partial-pivoting solver.  Lock-step lane groups,
+ * full-mask intrinsics, like SmallNR. */
 #define ANM_RAD_MAXC 4
 template <int LPE, int NB>
 struct RadialNR {
@@ -1087,7 +1050,7 @@ struct RadialNR {
     const int b = bl + 1;
     const int pl = active ? C.rad_parent[bl] : -1; /* parent's lane, -1: the slack bus */
     const int depth = active ? C.rad_depth[bl] : 0;
-    const int maxc = H.rad_maxc, maxd = H.rad_maxdepth, maxit = H.nr_maxit;
+    const int maxc = H.rad_maxc, maxd = H.rad_maxdepth;
     /* Source lane of every child slot.  An empty slot (and every slot of an idle lane) reads lane n, an idle lane
      * whose admittances are zero and whose depth is 0: everything it offers is exactly 0, so the gathers below need
      * no per-slot select. */
@@ -1116,8 +1079,6 @@ struct RadialNR {
 #endif
     int done = live ? 0 : 1, big = 0;
     double vr = 1.0, vi = 0.0, ir = 0.0, ii = 0.0, f0 = 0.0, f1 = 0.0;
-    bool sing = false; /* singular-block guard: a 2x2 block this lane inverted in the previous iteration had all but cancelled */
-    int tripped = 0;   /* ... in this group: it leaves the tree solver (redone by nr_generic after the loop) */
     for (;;) {
       /* V_b = |V| e^{j theta}, E_b = V_b / |V_b| (:167-173, :150) */
       double sn, cs;
@@ -1158,18 +1119,9 @@ struct RadialNR {
       f0 = (vr * ir + vi * ii) - pb;
       f1 = (vi * ir - vr * ii) - qb;
       const unsigned notok = __ballot_sync(ANM_FULL, active && !(fabs(f0) <= ANM_NR_TOL && fabs(f1) <= ANM_NR_TOL));
-#if ANM_SING_GUARD
-      {
-        const unsigned sb = __ballot_sync(ANM_FULL, sing && active);
-        const int tr = (((sb & gm) != 0u) && !done) ? 1 : 0;
-        tripped |= tr;
-        done |= tr;
-        sing = false;
-      }
-#endif
       {
         const int nb = ((notok & gm) != 0u) ? 1 : 0;
-        const int stop = (!nb || it >= maxit) ? 1 : 0;
+        const int stop = (!nb || it >= ANM_NR_MAXIT) ? 1 : 0;
         big = done ? big : nb;
         it += (done | stop) ? 0 : 1;
 #if ANM_DIAG
@@ -1216,13 +1168,9 @@ struct RadialNR {
        * of branches: the body is shared by all levels / child slots and stays in the instruction cache. */
 #pragma unroll 1
       for (int lev = maxd; lev >= 2; --lev) {
-        const double pa = d00 * d11, pb2 = d01 * d10;
-        const double det = pa - pb2;
+        const double det = d00 * d11 - d01 * d10;
         const double rd = fast_rcp(det);
         const bool mine = (depth == lev);
-#if ANM_SING_GUARD
-        sing |= mine & (fabs(det) <= ANM_SING_TAU * (fabs(pa) + fabs(pb2)));
-#endif
         rdet = mine ? rd : rdet;
         const double rdm = mine ? rd : 0.0; /* only the buses of this level offer a non-zero contribution */
         /* T = adj(D) [L | f],  C = U T / det */
@@ -1256,13 +1204,9 @@ struct RadialNR {
       /* root level (children of the slack): plain 2x2 solves */
       double x0 = 0.0, x1 = 0.0;
       {
-        const double pa = d00 * d11, pb2 = d01 * d10;
-        const double det = pa - pb2;
+        const double det = d00 * d11 - d01 * d10;
         const double rr = fast_rcp(det);
         const bool root = (depth == 1);
-#if ANM_SING_GUARD
-        sing |= root & (fabs(det) <= ANM_SING_TAU * (fabs(pa) + fabs(pb2)));
-#endif
         rdet = root ? rr : rdet;
         x0 = root ? (d11 * r0 - d01 * r1) * rr : 0.0;
         x1 = root ? (d00 * r1 - d10 * r0) * rr : 0.0;
@@ -1305,16 +1249,6 @@ struct RadialNR {
     it_out = it;
     converged_out = !bad;            /* numpy: norm(F, inf) is NaN <=> some entry is */
     stable_out = !bad && !big;       /* solve_load_flow.py:49 */
-#if ANM_SING_GUARD
-    if (tripped) { /* cold: this instance's power flow again, by the dense partially pivoted solver (group-private) */
-      const int r = nr_generic_cold<LPE>(reinterpret_cast<const unsigned char*>(C.H), ws, lane, gm);
-      it_out = r & 255;
-      converged_out = (r & 256) != 0;
-      stable_out = (r & 512) != 0;
-      n_fb = 1;
-    }
-    __syncwarp();
-#endif
 #if ANM_DIAG
     n_fb = (n_fb & 0xffff) | ((int)((t_done - t_loop0) >> 4) << 16);
 #endif
@@ -1588,34 +1522,6 @@ __device__ __forceinline__ void gather_full_state(const Cst& C, double* __restri
 /* what a lane group does with its environment in this pass */
 enum { ACT_NONE = 0, ACT_ZERO = 1, ACT_STEP = 2, ACT_RESET = 3, ACT_TRANSITION = 4 };
 
-/* ---- observation all-gather, fused into the step (the one exchange of the path) -----------------
- * With a gather attached (anm_gather_*, anm_capi.cu) every rank's gather buffer is mapped into every process
- * (CUDA IPC, peer access over NVLink / NVSwitch).  The epilogue of a step stores the instance's packed row
- * [obs | reward | terminated] straight into every rank's buffer, row = first row of this rank + instance, slot =
- * gather steps completed so far modulo g_slots: the transfer overlaps the rest of the batch's Newton iterations, and
- * there is no separate collective launch.  When the last CTA of the launch is done (every thread fenced its stores at
- * system scope before its CTA was counted) it raises this rank's arrival word in every rank's flag array; the
- * consumer side (anm_gather_wait: gather_wait_kernel) waits until every sender's word has reached the local step
- * count.  Gather launches are fully ordered (never chained), so the step count read at kernel entry is stable. */
-__device__ __forceinline__ void packed_row_store(const AnmLaunch& P, int64_t e, int64_t row, int O, int lane, int LPE_,
-                                                 unsigned gslot) {
-  /* re-reads this step's row (written by the lanes of this group before the group barrier that precedes the call) */
-  const int W = O + 2;
-#pragma unroll 1
-  for (int k = lane; k < W; k += LPE_) {
-    double v;
-    if (k < O) v = __ldcg(P.obs + row * O + k);
-    else if (k == O) v = __ldcg(P.reward + row);
-    else v = (double)__ldcg(P.term_out + row);
-    if (P.packed) P.packed[e * W + k] = v;
-    if (P.g_peers) {
-      const int64_t off = ((int64_t)gslot * P.g_rows + P.g_row0 + e) * W + k;
-#pragma unroll 1
-      for (int p = 0; p < P.g_world; ++p) P.g_peers[p][off] = v;
-    }
-  }
-}
-
 template <int LPE, int NB, int SOLVER>
 __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_THREADS,
                                    (NB > 0 && LPE <= 16) ? ANM_VAR_MINB : (SOLVER == 4 ? 4 : 1))
@@ -1629,9 +1535,6 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
   /* constants never change: staged before any ordering; `ord` = ordinal of this launch on its handle */
   const uint32_t ord = stage_constants(smem, P.blob, P.blob_bytes, P.ticket);
   if (!(P.flags & ANM_LF_CHAINED)) pdl_wait();     /* everything earlier in the stream is complete+visible */
-  /* fused observation all-gather: the slot of this step (gather launches are never chained: the count is stable) */
-  const unsigned long long gcount = P.g_state ? __ldcg(P.g_state) : 0ull;
-  const unsigned gslot = P.g_state ? (unsigned)(gcount % (unsigned long long)P.g_slots) : 0u;
   const Cst C(smem + ANM_BLOB_SMEM_OFF);
   const AnmConstHeader& H = *C.H;
 
@@ -1925,7 +1828,6 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 #endif
       a_pre = a_next;
       gsync<FULL>(gm); /* the workspace is reused by the next step */
-      if ((P.packed || P.g_peers) && have && P.mode == ANM_MODE_STEP) packed_row_store(P, e, row, O, lane, LPE, gslot);
     }
 
     /* ---- carried state back to global memory, then publish: the whole group's writes first (fence by every
@@ -1946,46 +1848,6 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 #if ANM_DIAG
     if (P.phase_stats && have && lane == 0) P.phase_stats[16 * e + 9] = (int)(clock64() - t_k0); /* fence + publish */
 #endif
-  }
-  if (P.g_state) { /* arrival signal of the fused observation all-gather (see packed_row_store) */
-    __threadfence_system(); /* every thread: its stores into the peers' buffers before its CTA is counted */
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned long long k64 = *reinterpret_cast<const unsigned long long*>(smem + 24);
-      unsigned long long* ctr = P.g_state + 8 + (k64 & 63ull);
-      if (atomicAdd(ctr, 1ull) + 1ull == (unsigned long long)gridDim.x) { /* the last CTA of this launch */
-        atomicExch(ctr, 0ull);
-        __threadfence_system();
-        const unsigned long long g = gcount + 1ull;
-        for (int p = 0; p < P.g_world; ++p)
-          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.g_flags[p] + P.g_rank), "l"(g) : "memory");
-        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.g_state), "l"(g) : "memory");
-      }
-    }
-  }
-}
-
-/* consumer side of the fused observation all-gather: returns (kernel completion = stream order) once every rank's
- * arrival word has reached the local step count, i.e. every rank's rows of the last gather step are in the local
- * buffer.  One warp; lane p polls sender p.  A wait of more than `limit_ns` traps (a peer died). */
-__global__ void gather_wait_kernel(const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ state,
-                                   int world, uint64_t limit_ns) {
-  const unsigned long long want = __ldcg(state);
-  if ((int)threadIdx.x < world) {
-    const unsigned long long* f = flags + threadIdx.x;
-    uint64_t t0 = 0;
-    uint32_t spins = 0;
-    for (;;) {
-      unsigned long long v;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-      if (v >= want) break;
-      __nanosleep(200);
-      if ((++spins & 1023u) == 0u) {
-        const uint64_t now = global_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > limit_ns) __trap();
-      }
-    }
   }
 }
 

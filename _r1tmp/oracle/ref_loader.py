@@ -1,5 +1,4 @@
-"""Import the UNMODIFIED reference package from /root/reference (this container) or from the copy that
-oracle/build_ref.py staged under oracle/_ref/ (the GPU box, where /root/reference does not exist).
+"""Import the UNMODIFIED reference package from /root/reference (this container only).
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product imports this.  The GPU box has no
 /root/reference, so this loader is used (a) by oracle/gen_golden.py to generate the
@@ -10,11 +9,8 @@ the reference tree is present.
 import os
 import sys
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
-_STAGED = os.path.join(_HERE, "_ref")  # written by oracle/build_ref.py (the unmodified package, git-ignored; GPU box)
-REFERENCE_ROOT = os.environ.get("ANM_REFERENCE_ROOT") or (
-    "/root/reference" if os.path.isdir("/root/reference/gym_anm") else _STAGED)
-_SHIMS = os.path.join(_HERE, "shims")
+REFERENCE_ROOT = os.environ.get("ANM_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 
 def reference_available():

@@ -1,47 +1,54 @@
 #!/usr/bin/env python
-"""bench.py -- env-steps/s of the batched ANM6Easy step() path on N B200s (one JSON line).
+"""bench.py -- env-steps/s of the batched gym-anm step() path on N B200s (one JSON line on stdout).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs B] [--config 2|4] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): ANM6Easy-v0, B = 4096 environment instances PER GPU
-(weak scaling), uniform-random actions over the action box, fp64 Newton-Raphson.  A "step"
-is one pass of the hot path over the whole batch: every instance advances by one timestep.
-Terminated instances are re-initialised by the kernel's next-step auto-reset from a pool of
-initial states that are known to converge, so every instance does one full transition per step.
+Workloads (BASELINE.json `configs`):
+  --config 2 (default; the configuration the metric is quoted on): ANM6Easy-v0, B = 4096 environment instances PER GPU
+             (weak scaling), uniform-random actions over the action box, fp64 Newton-Raphson.
+  --config 4: the synthetic 30-bus feeder (gym_anm_b200.networks.synth_feeder_network), B = 8192 instances, random
+             actions and caller-supplied next_vars, block-sparse Newton solver.
+  (configs 3 and 5 are sizes of config 2: `--envs 8192 --gpus 8`, `--envs 2048 --gpus 8`.)
+A "step" is one pass of the hot path over the whole batch: every instance advances by one timestep.  Terminated
+instances are re-initialised by the kernel's next-step auto-reset from a pool of initial states known to converge, so
+every instance does one full transition per step.
 
-* `value`      : K steps as open-loop rollouts: the random agent does not look at the observations, so
-                 its action sequence (a 1000-slot x B x 6 fp64 ring resident in HBM, 197 MB > the 126 MB
-                 L2) is handed to `anm_rollout` 1000 steps at a time.  One kernel launch takes every
-                 instance through its 1000 steps -- carried state on chip, every step's obs / reward /
-                 terminated row written to HBM ([T, B, .] outputs) -- so an instance whose Newton iteration
-                 diverges (100 iterations) only delays the three instances that share its warp.  Timed
-                 with CUDA events, max over ranks.
-                 `per_step_launches` reports the same workload as ONE kernel launch per step (CUDA graph):
-                 `chained` (launches ordered per instance, ANM_STEP_CHAINED) and `lockstep` (every launch
-                 fully ordered after the previous one -- what a closed-loop policy sees).
-* `e2e`        : the same metric through the C-ABI host calls `anm_rollout_host_async` + `anm_host_sync`
-                 -- pinned HOST action arrays in, HOST obs / reward / terminated arrays out, for every
-                 step, H2D + D2H inside the timed region (copy engines, overlapped with the kernels);
-                 100 steps per call, the host waits for call i-1 after queueing call i.
-                 `e2e.sync_every_step` is the synchronous one-step `anm_step_host` (zero-copy).
-* `roofline`   : algorithmic bytes (234 B / env-step) x B / mean kernel time
-                 against the measured HBM copy bandwidth (MEASURED_PEAKS.json).  The path is NOT
-                 HBM-bound (arithmetic intensity ~30 fp64 FLOP/B); the fraction is reported
-                 because the metric asks for it, next to the ncu-measured fp64-pipe utilisation.
-* `cpu_baseline`: the reference-structured NumPy/SciPy port (oracle/anm_numpy.py, bit-exact vs
-                 the reference goldens) on all host cores, plus the scalar C port for context.
-
-`--impl reference` times that NumPy/SciPy port (the reference itself is pure Python and does
-not exist on the GPU box) on all host cores and prints the same line with "impl": "reference".
+Keys of the line (all rates are whole-job env-steps/s over the N GPUs, timed on the device, max over ranks):
+  value, ms_per_step  K steps = one block of `anm_rollout` launches (<= 1000 steps per launch; carried state on chip,
+                      every step's obs / reward / terminated row written to [T, B, .] arrays in HBM).  The block is
+                      repeated back to back (launches chained per instance) in 5 groups of R blocks until >= 0.3 s are
+                      timed; value = median over the groups of R*K*B / t_group.  Every block reads a different window of
+                      a 1000-slot action ring (197 MB > the 126 MB L2) and writes its own window of an output ring.
+  isolated_block      ONE K-step block timed alone (device idle before and after; median of 9): for small K this is
+                      dominated by the slowest warp of the launch (the instances whose Newton iteration ran to 100).
+  chained, lockstep   the same workload as ONE kernel launch per step (CUDA graph of 100 steps): launches ordered per
+                      instance (open-loop actions) / every launch fully ordered after the previous one -- `lockstep`
+                      is the rate a closed-loop policy on the same stream can reach.
+  e2e                 the metric through the C ABI's host calls with pinned HOST arrays: `anm_rollout_host_async`
+                      (100 steps per call, H2D actions + D2H obs / reward / terminated inside the timed region).
+  sync_every_step     the synchronous one-step host call `anm_step_host` (what `env.step(numpy_action)` costs).
+  with_obs_allgather  (N > 1) one launch per step whose epilogue stores every [obs | reward | terminated] row into every
+                      peer's gather buffer over NVLink (fused step + all-gather, no separate collective), plus the
+                      per-step arrival wait; `with_obs_allgather_nccl`: the kernel writes the packed rows locally and
+                      ncclAllGather moves them.  `gather_checksum*`: hashes of the gathered batch.
+  roofline            hbm leg (what the metric asks for): algorithmic bytes per env-step x env-steps per
+                      launch / mean launch duration over the timed region, against MEASURED_PEAKS.json `hbm_gbs`;
+                      fp64 leg: algorithmic fp64 FLOP per env-step / time against the DFMA rate measured
+                      in this run (`anm_debug_fp64_peak`).  Fields under `ncu_static` are constants copied from
+                      profiles/ncu_summary.json (an earlier ncu capture), NOT measurements of this run.
+  cpu_baseline        the reference's own ANM6Easy (`oracle/_ref`, staged by oracle/build_ref.py; kind "reference")
+                      on all usable host cores, one env per process; falls back to the NumPy/SciPy port (kind "port").
+`--impl reference` times that CPU implementation alone and prints the same line with "impl": "reference".
 """
 import argparse
+import hashlib
 import json
+import math
 import multiprocessing as mp
 import os
 import statistics
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -50,9 +57,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-B_MIN_BYTES = 234  # algorithmic bytes / env-step: 8*(A + O + 1 + 2*(n_des + K)) + 2  
-RING = 1000        # action ring slots (x B x 6 x 8 B = 197 MB at B = 4096)
+RING = 1000         # action ring slots of config 2 (x B x 6 x 8 B = 197 MB at B = 4096)
 SEED0 = 2020
+FLOP_PER_ENV_STEP = 8.5e3  # ANM6Easy, fp64: SURVEY.md 8d gives 7-10 kFLOP (NR ~5.5 k at 3.2 iterations, projections, flows)
+GROUPS = 5
 
 
 def usable_cores():
@@ -79,29 +87,41 @@ def usable_cores():
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--envs", type=int, default=4096, help="environment instances per GPU")
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--envs", type=int, default=None, help="environment instances per GPU (default 4096; config 4: 8192)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=1500, help="reference arm: timed env-steps per process")
+    ap.add_argument("--cpu-steps", type=int, default=1500, help="CPU arms: timed env-steps per process")
+    ap.add_argument("--min-timed-s", type=float, default=0.35, help="timed region of every rate (all groups together)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------
 # CPU legs (oracle/ is used here only as the thing being timed for the baseline)
 # ------------------------------------------------------------------------------------------
-def numpy_port_rate(n_proc, n_steps, n_warm=10):
-    import anm_numpy
+def cpu_rate(n_proc, n_steps, n_warm=10):
+    """All host cores, one ANM6Easy env per process.  Returns (kind, total rate, per-process median, resets, what)."""
+    import ref_rollout
 
-    ctx = mp.get_context("spawn")
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["MKL_NUM_THREADS"] = "1"
+    if ref_rollout.available():
+        fn, kind = ref_rollout.random_agent_rollout, "reference"
+        what = ("the reference's own gym_anm ANM6Easy (unmodified package staged under oracle/_ref; cvxpy = the exact-"
+                "projection stand-in, so an UPPER bound on the real CVXPY->OSQP reference; NumPy/SciPy SuperLU Newton-Raphson)")
+    else:
+        import anm_numpy
+
+        fn, kind = anm_numpy.random_agent_rollout, "port"
+        what = "NumPy/SciPy port oracle/anm_numpy.py (reference-structured, bit-exact vs the reference goldens)"
+    ctx = mp.get_context("spawn")
     with ctx.Pool(n_proc) as pool:
-        res = pool.map(anm_numpy.random_agent_rollout, [(SEED0 + i, n_steps, n_warm) for i in range(n_proc)])
+        res = pool.map(fn, [(SEED0 + i, n_steps, n_warm) for i in range(n_proc)])
     rates = [n / t for n, t, _ in res]
-    return sum(rates), statistics.median(rates), sum(r for _, _, r in res)
+    return kind, sum(rates), statistics.median(rates), sum(r for _, _, r in res), what
 
 
 def c_port_rate(B=4096, steps=100):
@@ -134,9 +154,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = usable_cores()
-    n = max(50, min(args.cpu_steps, args.steps))
+    n = max(50, args.cpu_steps)
     t0 = time.perf_counter()
-    total, per_proc, resets = numpy_port_rate(cores, n, n_warm=min(10, max(1, args.warmup)))
+    kind, total, per_proc, resets, what = cpu_rate(cores, n, n_warm=min(10, max(1, args.warmup)))
     wall = time.perf_counter() - t0
     sample = "%d processes x %d timed env-steps of ANM6Easy-v0 (random agent, reset on termination)" % (cores, n)
     line = {
@@ -153,13 +173,9 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {
-            "workload": "ANM6Easy-v0 random-agent step(), reference-structured NumPy/SciPy port "
-            "(oracle/anm_numpy.py; bit-exact vs reference goldens; exact projection instead of CVXPY->OSQP, "
-            "so an UPPER bound on the real reference's speed), one env per host core",
-            "envs_per_gpu": args.envs,
-        },
-        "cpu_baseline": {"value": total, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+        "config": {"workload": "ANM6Easy-v0 random-agent step() on the host cores, one env per core: " + what,
+                   "envs_per_gpu": args.envs or 4096},
+        "cpu_baseline": {"value": total, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample,
                          "per_core_median": per_proc, "wall_s": wall, "resets": resets,
                          "os_cpu_count": os.cpu_count()},  # fmt: skip
         "e2e": {"value": total, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,35 +237,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# GPU arm
+# workloads
 # ------------------------------------------------------------------------------------------
-def run_ours(args):
-    import numpy as np
+def setup_config2(B, dev, rank):
     import torch
-    import torch.distributed as dist
 
     from gym_anm_b200.anm6 import BatchedANM6Easy
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    B, K, W = args.envs, args.steps, max(3, args.warmup)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-
-    # ---- setup: envs (global-index seeding), auto-reset pool, action rings ----------------------
     env = BatchedANM6Easy(B, device=dev, validate_actions=False, env_offset=rank * B)
     nb = env.native
     env.reset(seed=SEED0)
@@ -260,52 +254,154 @@ def run_ours(args):
     lo = torch.as_tensor(env.spec.action_low, device=dev)
     hi = torch.as_tensor(env.spec.action_high, device=dev)
     ring = torch.rand((RING, B, 6), dtype=torch.float64, device=dev, generator=gen) * (hi - lo) + lo
-    ring_host = ring.cpu().pin_memory()  # e2e leg: the agent's actions live in pinned host memory
-    obs, rew, term = nb.empty(B, 18), nb.empty(B), nb.empty(B, dtype=torch.uint8)
+    return {"nb": nb, "keep": env, "ring": ring, "ring_nv": None, "pool_rows": pool.shape[0],
+            "workload": "ANM6Easy-v0, %d parallel envs per GPU, uniform-random actions, fp64 NR solve "
+                        "(BASELINE.json configs[1])" % B,
+            "flop_per_env_step": FLOP_PER_ENV_STEP}  # fmt: skip
 
-    # ---- warm-up (eager launches) ---------------------------------------------------------------------
+
+def setup_config4(B, dev, rank):
+    import numpy as np
+    import torch
+
+    from gym_anm_b200.env_spec import HostEnvSpec
+    from gym_anm_b200.native import NativeBatch
+    from gym_anm_b200.networks import synth_feeder_network
+
+    spec = HostEnvSpec(synth_feeder_network(), "state", 1, 0.25, 0.99, 100, np.array([[0, 95]]), (1, 100))
+    cn = spec.cn
+    nb = NativeBatch(spec, B, dev)
+    rng = np.random.default_rng(30 + rank)
+    D, ns, ng = cn.N_device, cn.N_des, cn.N_non_slack_gen
+    pos = {d: k for k, d in enumerate(cn.devices)}
+    s0 = np.zeros((B, spec.state_N))
+    for i in cn.load_ids:
+        s0[:, pos[i]] = rng.uniform(cn.devices[i].p_min * 100, 0, B)
+    for k, i in enumerate(cn.gen_ids):
+        s0[:, pos[i]] = rng.uniform(0, cn.devices[i].p_max * 100, B)
+        s0[:, 2 * D + ns + k] = rng.uniform(0, cn.devices[i].p_max * 100, B)
+    for k, i in enumerate(cn.des_ids):
+        s0[:, 2 * D + k] = rng.uniform(0, cn.devices[i].soc_max * 100, B)
+    obs, state, conv = nb.reset(s0)
+    assert bool(conv.all())
+    pool = state.clone()
+    nb.set_autoreset_pool(pool)
+    R = 64  # 64 slots x 8192 x (18 + 17) x 8 B = 147 MB > L2
+    g = torch.Generator(device=dev)
+    g.manual_seed(4 + rank)
+    lo, hi = torch.as_tensor(spec.action_low, device=dev), torch.as_tensor(spec.action_high, device=dev)
+    ring = torch.rand((R, B, len(spec.action_low)), dtype=torch.float64, device=dev, generator=g) * (hi - lo) + lo
+    nv_lo = torch.as_tensor([cn.devices[i].p_min * 100 for i in cn.load_ids] + [0.0] * ng + [0.0], device=dev)
+    nv_hi = torch.as_tensor([0.0] * cn.N_load + [cn.devices[i].p_max * 100 for i in cn.gen_ids] + [95.0], device=dev)
+    ring_nv = torch.rand((R, B, spec.n_next_vars), dtype=torch.float64, device=dev, generator=g) * (nv_hi - nv_lo) + nv_lo
+    return {"nb": nb, "keep": spec, "ring": ring, "ring_nv": ring_nv, "pool_rows": pool.shape[0],
+            "workload": "synthetic 30-bus feeder (synth_feeder_network: %d devices, %d branches), %d parallel envs per GPU, "
+                        "random actions and caller-supplied next_vars, fp64 block-sparse NR solve (BASELINE.json configs[3])"
+                        % (cn.N_device, len(cn.branches), B),
+            "flop_per_env_step": None}  # fmt: skip
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gym_anm_b200 import _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.envs or (4096 if args.config == 2 else 8192)
+    K, W = args.steps, max(3, args.warmup)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(vals):
+        """max over ranks of a list of floats (device-timed milliseconds)"""
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    wl = (setup_config2 if args.config == 2 else setup_config4)(B, dev, rank)
+    nb, ring, ring_nv = wl["nb"], wl["ring"], wl["ring_nv"]
+    NR, A, O, NV = ring.shape[0], nb.A, nb.O, nb.NV
+    obs, rew, term = nb.empty(B, O), nb.empty(B), nb.empty(B, dtype=torch.uint8)
+    nvs = (lambda t: None) if ring_nv is None else (lambda t: ring_nv[t % NR])
+    in_bytes = 8 * A + (0 if ring_nv is None else 8 * NV)          # per env-step, read
+    out_bytes = 8 * O + 8 + 1                                       # per env-step, written
+    alg_bytes = in_bytes + out_bytes + 2 * 8 * (nb.n_des + nb.K) + 1  # + carried state in / out (SURVEY.md 8d: 234 B for ANM6Easy)
+
+    # ---- warm-up (eager one-step launches) ------------------------------------------------------------
     for t in range(W):
-        nb.step(ring[t % RING], None, out=(obs, rew, term))
+        nb.step(ring[t % NR], nvs(t), out=(obs, rew, term))
     torch.cuda.synchronize()
 
-    # ---- value: K steps as open-loop rollouts (anm_rollout: T steps per kernel launch) ---------------------------
-    # The random agent is open-loop, so the whole action sequence is handed over at once: one launch takes every
-    # instance through T = RING consecutive steps (carried state on chip) and writes every step's obs / reward /
-    # terminated row; consecutive launches are chained per instance (ANM_STEP_CHAINED).
-    T = min(K, RING)
-    n_roll, rem = divmod(K, T)
-    obs_r, rew_r, term_r = nb.empty(T, B, 18), nb.empty(T, B), nb.empty(T, B, dtype=torch.uint8)
-    nb.rollout(ring[:T], out=(obs_r, rew_r, term_r))  # untimed: instruction cache, allocator
-    torch.cuda.synchronize()
+    # ---- value: K-step blocks of anm_rollout launches, repeated back to back --------------------------------
+    T = min(K, NR)                       # steps per launch
+    n_full, rem = divmod(K, T)
+    launches_per_block = n_full + (1 if rem else 0)
+    n_out = max(1, min(12, int(math.ceil(160e6 / (T * B * out_bytes)))))  # output windows: > L2 in flight
+    outs = [(nb.empty(T, B, O), nb.empty(T, B), nb.empty(T, B, dtype=torch.uint8)) for _ in range(n_out)]
+    state = {"block": 0}
 
-    def timed(fn):
+    def run_block(first_chained=True):
+        """K steps: rollout launches over consecutive windows of the action ring, into the block's output window."""
+        b = state["block"]
+        state["block"] += 1
+        o, r, d = outs[b % n_out]
+        for i in range(launches_per_block):
+            n = T if i < n_full else rem
+            a0 = ((b * launches_per_block + i) * T) % (NR - n + 1)
+            nb.rollout(ring[a0:a0 + n], None if ring_nv is None else ring_nv[a0:a0 + n],
+                       out=(o[:n], r[:n], d[:n]), chained=(first_chained or i > 0))
+
+    def timed_ms(fn, stream=None):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t_host0 = time.perf_counter()
-        ev0.record()
+        ev0.record(stream)
         fn()
-        ev1.record()
+        ev1.record(stream)
         barrier()
         t_host1 = time.perf_counter()
         sampler.mark(t_host0, t_host1)
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
+        return ev0.elapsed_time(ev1), 1000.0 * (t_host1 - t_host0)
 
-    def run_rollouts():
-        for i in range(n_roll):
-            nb.rollout(ring[:T], out=(obs_r, rew_r, term_r), chained=(i > 0))
-        if rem:
-            nb.rollout(ring[:rem], out=(obs_r[:rem], rew_r[:rem], term_r[:rem]), chained=True)
+    run_block(False)  # untimed: instruction cache, allocator
+    torch.cuda.synchronize()
+    iso = maxr([timed_ms(lambda: run_block(False))[0] for _ in range(9)])
+    t_block = statistics.median(iso)
+    R = int(max(1, min(20000, math.ceil(args.min_timed_s * 1000.0 / GROUPS / t_block))))
+
+    def run_group():
+        for i in range(R):
+            run_block(first_chained=(i > 0))
 
     launches0 = nb.launch_count
-    ms_total = timed(run_rollouts)
+    grp_ms = maxr([timed_ms(run_group)[0] for _ in range(GROUPS)])
     gpu_launches = nb.launch_count - launches0
-    frac_reset = float((term_r[-1] != 0).double().mean())
+    rates = [world * B * K * R / (ms / 1000.0) for ms in grp_ms]
+    value = statistics.median(rates)
+    ms_per_step = statistics.median(grp_ms) / (R * K)
+    frac_reset = float((outs[(state["block"] - 1) % n_out][2][(rem or T) - 1] != 0).double().mean())
 
-    # ---- the same K' steps as one kernel launch per step, replayed from a CUDA graph ----------------------------
-    G = min(K, RING)
+    # ---- one kernel launch per step, replayed from a CUDA graph ---------------------------------------------
+    G = min(100, NR)
     side = torch.cuda.Stream()
 
     def capture(chained):
@@ -314,18 +410,20 @@ def run_ours(args):
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
                 for t in range(G):
-                    nb.step(ring[t], None, out=(obs, rew, term), chained=chained)
+                    nb.step(ring[t], nvs(t), out=(obs, rew, term), chained=chained)
         torch.cuda.current_stream().wait_stream(side)
         g.replay()  # untimed replay: graph upload + instruction cache
         return g
 
-    n_g = max(1, min(K // G, 4))
     per_step = {}
     for name, chained in (("chained", True), ("lockstep", False)):
         g = capture(chained)
-        ms_g = timed(lambda: [g.replay() for _ in range(n_g)])
+        t1 = maxr([timed_ms(g.replay)[0]])[0]
+        n_g = int(max(1, min(2000, math.ceil(args.min_timed_s * 1000.0 / 3 / t1))))
+        ms3 = maxr([timed_ms(lambda: [g.replay() for _ in range(n_g)])[0] for _ in range(3)])
+        ms_g = statistics.median(ms3)
         per_step[name] = {"value": world * B * n_g * G / (ms_g / 1000.0), "unit": "env-steps/s",
-                          "ms_per_step": ms_g / (n_g * G), "steps": n_g * G}
+                          "ms_per_step": ms_g / (n_g * G), "steps": n_g * G, "timed_s": sum(ms3) / 1000.0}
         del g
     per_step["chained"]["what"] = ("one kernel launch per step (CUDA graph), launches ordered per instance "
                                    "(programmatic dependent launch + per-instance sequence numbers)")
@@ -335,67 +433,71 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI's host calls (H2D + kernel + D2H for every step) -------------------
     hs = nb.host_stream
     Te = int(os.environ.get("BENCH_E2E_STEPS_PER_CALL", "100"))  # steps per queued rollout call; two sets of pinned
+    Te = min(Te, NR)
     # output buffers; after queueing call i the host waits for call i-1 (whose results it would consume meanwhile)
-    obs_q = torch.empty(2, Te, B, 18, dtype=torch.float64).pin_memory()
+    ring_host = ring.cpu().pin_memory()  # the agent's actions live in pinned host memory
+    nv_host = None if ring_nv is None else ring_nv.cpu().pin_memory()
+    obs_q = torch.empty(2, Te, B, O, dtype=torch.float64).pin_memory()
     rew_q = torch.empty(2, Te, B, dtype=torch.float64).pin_memory()
     term_q = torch.empty(2, Te, B, dtype=torch.uint8).pin_memory()
-    act_ptr = [ring_host[t].data_ptr() for t in range(RING)]
+    act_ptr = [ring_host[t].data_ptr() for t in range(NR)]
+    nv_ptr = [None] * NR if nv_host is None else [nv_host[t].data_ptr() for t in range(NR)]
     out_ptr = [(obs_q[q].data_ptr(), rew_q[q].data_ptr(), term_q[q].data_ptr()) for q in range(2)]
 
-    def e2e_loop(n, queued):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        t_host0 = time.perf_counter()
-        e0.record(hs)
-        if queued:
-            for i in range(n // Te):
-                o, r, d = out_ptr[i % 2]
-                nb.rollout_host_async(Te, act_ptr[(i * Te) % (RING - Te + 1)], None, o, r, d)
-                nb.host_sync_previous()
-            nb.host_sync()
-        else:
-            for t in range(n):
-                nb.step_host(act_ptr[t % RING], None, out_ptr[0][0], out_ptr[0][1], out_ptr[0][2])
-        e1.record(hs)
-        barrier()
-        t_host1 = time.perf_counter()
-        sampler.mark(t_host0, t_host1)
-        ms = torch.tensor([max(e0.elapsed_time(e1), 1000.0 * (t_host1 - t_host0))], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return world * B * n / (float(ms) / 1000.0)
+    def e2e_loop(n_calls, queued):
+        """queued: n_calls x Te steps through anm_rollout_host_async; else n_calls synchronous one-step calls."""
+        def body():
+            if queued:
+                for i in range(n_calls):
+                    o, r, d = out_ptr[i % 2]
+                    a0 = (i * Te) % (NR - Te + 1)
+                    nb.rollout_host_async(Te, act_ptr[a0], nv_ptr[a0], o, r, d)
+                    nb.host_sync_previous()
+                nb.host_sync()
+            else:
+                for t in range(n_calls):
+                    nb.step_host(act_ptr[t % NR], nv_ptr[t % NR], out_ptr[0][0], out_ptr[0][1], out_ptr[0][2])
+        dev_ms, host_ms = timed_ms(body, hs)
+        return max(dev_ms, host_ms)  # the host loop is part of the path: never report less than its wall time
 
-    Ke = max(2 * Te, min(K, 8000) // (2 * Te) * (2 * Te))
-    e2e_loop(2 * Te, True)
-    e2e_rate = e2e_loop(Ke, True)
+    e2e_loop(2, True)
+    t_call = maxr([e2e_loop(4, True)])[0] / 4
+    n_calls = int(max(4, min(4000, math.ceil(args.min_timed_s * 1000.0 / t_call))))
+    e2e_ms = maxr([e2e_loop(n_calls, True)])[0]
+    e2e_rate = world * B * n_calls * Te / (e2e_ms / 1000.0)
     checksum = float(obs_q.sum()) + float(rew_q.sum())
     e2e_loop(3, False)
-    Ks = min(K, 2000)
-    e2e_sync_rate = e2e_loop(Ks, False)
+    t_s = maxr([e2e_loop(20, False)])[0] / 20
+    n_s = int(max(20, min(20000, math.ceil(args.min_timed_s * 1000.0 / t_s))))
+    sync_ms = maxr([e2e_loop(n_s, False)])[0]
+    e2e_sync_rate = world * B * n_s / (sync_ms / 1000.0)
 
-    # ---- optional: the single collective of the path (all-gather of the batched observation) ------------
-    gather_rate = None
+    # ---- the single collective of the path: all-gather of the batched [obs | reward | terminated] rows ---------
+    gather = {}
     if world > 1:
-        from gym_anm_b200.distributed import all_gather_rows
+        from gym_anm_b200.distributed import ObsExchange
 
-        Kg = min(K, 2000)
-        packed = torch.empty(B, 20, dtype=torch.float64, device=dev)
-        for t in range(3):
-            all_gather_rows(packed)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        g0.record()
-        for t in range(Kg):
-            nb.step(ring[t % RING], None, out=(obs, rew, term))
-            packed[:, :18] = obs
-            packed[:, 18] = rew
-            packed[:, 19] = term
-            all_gather_rows(packed)
-        g1.record()
-        barrier()
-        gm = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
-        gather_rate = world * B * Kg / (float(gm) / 1000.0)
+        for mode in ("p2p", "nccl"):
+            try:
+                ex = ObsExchange(nb, mode=mode)
+            except Exception as e:  # noqa: BLE001
+                gather[mode] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+                continue
+            for t in range(3):
+                ex.step(ring[t % NR], nvs(t))
+                ex.wait()
+            t1 = maxr([timed_ms(lambda: [(ex.step(ring[t % NR], nvs(t)), ex.wait()) for t in range(50)])[0]])[0] / 50
+            Kg = int(max(50, min(20000, math.ceil(args.min_timed_s * 1000.0 / t1))))
+            gm = maxr([timed_ms(lambda: [(ex.step(ring[t % NR], nvs(t)), ex.wait()) for t in range(Kg)])[0]])[0]
+            full = ex.wait()  # [B_global, O + 2] of the last step
+            torch.cuda.synchronize()
+            fb = full.cpu().numpy()
+            gather[mode] = {"value": world * B * Kg / (gm / 1000.0), "unit": "env-steps/s", "steps": Kg,
+                            "ms_per_step": gm / Kg,
+                            "checksum_all": hashlib.sha256(fb.tobytes()).hexdigest()[:16],
+                            "checksum_first_shard": hashlib.sha256(fb[:B].tobytes()).hexdigest()[:16]}
+            ex.close()
+            barrier()
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -405,8 +507,6 @@ def run_ours(args):
         return
 
     # ---- rank 0: roofline, CPU baseline, the JSON line ----------------------------------------------------
-    value = world * B * K / (ms_total / 1000.0)
-    kernel_s = (ms_total / 1000.0) / K
     peaks, peak_src = {}, "fallback (B200_PROFILING.md)"
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -414,36 +514,53 @@ def run_ours(args):
     except Exception:  # noqa: BLE001
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    launch_s = (ms_total / 1000.0) / max(gpu_launches, 1)      # one anm_rollout launch = T steps of every instance
-    steps_per_launch = K / max(gpu_launches, 1)
-    achieved = B_MIN_BYTES * B * steps_per_launch / launch_s / 1e9
+    grp_s = statistics.median(grp_ms) / 1000.0
+    launches_per_group = R * launches_per_block
+    launch_s = grp_s / launches_per_group                    # mean launch duration over the timed region (CUDA events)
+    env_steps_per_launch = B * K / launches_per_block
+    achieved = alg_bytes * env_steps_per_launch / launch_s / 1e9
+    import ctypes as C
+
+    tf = C.c_double(0.0)
+    fp64_peak = None
+    try:
+        _capi.check(nb.lib.anm_debug_fp64_peak(local, C.byref(tf)), nb.lib)
+        fp64_peak = tf.value
+    except Exception:  # noqa: BLE001
+        pass
     ncu = {}
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
     except Exception:  # noqa: BLE001
         pass
     per_es = ncu.get("dram_bytes_per_env_step")
+    fp64_leg = None
+    if wl["flop_per_env_step"] and fp64_peak:
+        a = wl["flop_per_env_step"] * env_steps_per_launch / launch_s / 1e12
+        fp64_leg = {"achieved": a, "peak": fp64_peak, "unit": "TFLOP/s", "frac": a / fp64_peak,
+                    "algorithmic_flop_per_env_step": wl["flop_per_env_step"],
+                    "peak_source": "measured in this run: anm_debug_fp64_peak (register-only DFMA chains)"}
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None if per_es is None else per_es * B * steps_per_launch, "peak_source": peak_src,
-        "algorithmic_bytes_per_env_step": B_MIN_BYTES, "env_steps_per_launch": B * steps_per_launch,
-        "kernel_us_mean": launch_s * 1e6, "kernel_us_per_step": kernel_s * 1e6,
-        "traffic_note": "dram bytes per env-step of the ncu capture (a 50-step launch: the 153 B / env-step of outputs "
-                        "were still in the 126 MB L2 when it ended) x env-steps per launch",
-        "note": "compute/latency-bound path (dependent fp64 FMA chains, shuffle / shared-memory latency at 1.7 warps per "
-                "scheduler), not HBM-bound: 234 B against ~1650 warp instructions per env-step; see the fp64 / issue fields",
-        "fp64_pipe_pct_ncu": ncu.get("fp64_pipe_pct"), "issue_slot_pct_ncu": ncu.get("issue_active_pct"),
-        "stall_samples_pct_ncu": ncu.get("stall_samples_pct"), "ncu_profile": ncu.get("source"),
+        "traffic": None if (per_es is None or args.config != 2) else per_es * env_steps_per_launch,
+        "peak_source": peak_src, "algorithmic_bytes_per_env_step": alg_bytes, "env_steps_per_launch": env_steps_per_launch,
+        "kernel_us_mean": launch_s * 1e6, "kernel_us_per_step": launch_s * 1e6 * launches_per_block / K,
+        "binding_resource": "dependent fp64 issue latency at ~1.7 warps per scheduler (B = 4096 is one wave), not HBM: "
+                            "the hbm fraction is reported because the metric asks for it; see `fp64`",
+        "fp64": fp64_leg,
+        "ncu_static": {"static": True, "what": "constants copied from profiles/ncu_summary.json (an earlier ncu capture of this "
+                       "kernel), NOT measurements of this run", "fp64_pipe_pct": ncu.get("fp64_pipe_pct"),
+                       "issue_slot_pct": ncu.get("issue_active_pct"), "stall_samples_pct": ncu.get("stall_samples_pct"),
+                       "dram_bytes_per_env_step": per_es, "profile": ncu.get("source")},
     }  # fmt: skip
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = usable_cores()
-        n = 800
-        total, per_core, resets = numpy_port_rate(cores, n)
+        n = 1000
+        kind, total, per_core, resets, what = cpu_rate(cores, n)
         cpu_baseline = {
-            "value": total, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d processes x %d timed env-steps of ANM6Easy-v0, random agent, NumPy/SciPy port "
-                      "(oracle/anm_numpy.py, reference-structured, exact projection)" % (cores, n),
+            "value": total, "unit": "env-steps/s", "cores": cores, "kind": kind,
+            "sample": "%d processes x %d timed env-steps of ANM6Easy-v0, random agent: %s" % (cores, n, what),
             "per_core_median": per_core,
             "c_port": {"value": c_port_rate(), "unit": "env-steps/s", "threads": cores,
                        "what": "oracle/anm_oracle.c (scalar C, dense LU, OpenMP over 4096 envs)"},
@@ -455,41 +572,52 @@ def run_ours(args):
         "n_gpus": world,
         "steps": K,
         "warmup": W,
-        "ms_per_step": ms_total / K,
+        "ms_per_step": ms_per_step,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": "ANM6Easy-v0, %d parallel envs per GPU, uniform-random actions, fp64 NR solve "
-                        "(BASELINE.json configs[1])" % B,
+            "workload": wl["workload"],
             "envs_per_gpu": B, "global_envs": world * B, "parallelism": "dp%d (independent env shards)" % world,
-            "autoreset": "next-step, from a pool of %d convergent initial states" % pool.shape[0],
-            "l2": "inputs cycle through a %d-slot action ring of %.0f MB (> 126 MB L2)" % (RING, ring.numel() * 8 / 1e6),
-            "launch": "anm_rollout: %d launches x %d steps (+%d); each instance runs its steps back to back with its "
-                      "carried state on chip and writes every step's obs / reward / terminated row to HBM; launches "
-                      "chained per instance" % (n_roll, T, rem),
+            "autoreset": "next-step, from a pool of %d convergent initial states" % wl["pool_rows"],
+            "l2": "inputs cycle through a %d-slot action ring of %.0f MB (> 126 MB L2); every block writes its own window "
+                  "of a %d-window output ring (%.0f MB)" % (NR, (ring.numel() + (0 if ring_nv is None else ring_nv.numel())) * 8 / 1e6,
+                                                          n_out, n_out * T * B * out_bytes / 1e6),
+            "launch": "K = %d steps = %d anm_rollout launch(es) of <= %d steps; the block repeated back to back %d times per "
+                      "group (launches chained per instance), %d groups, median group" % (K, launches_per_block, T, R, GROUPS),
+            "repeats_per_group": R, "groups": GROUPS, "group_ms": grp_ms, "timed_s": sum(grp_ms) / 1000.0,
             "lanes_per_env": nb.sizes["lanes_per_env"], "smem_bytes_per_cta": nb.sizes["smem_bytes"],
             "frac_envs_reset_last_step": frac_reset,
         },
         "clocks": clocks,
-        "per_step_launches": per_step,
-        "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * 6 * 8,
-                "d2h_bytes_per_step": B * (18 * 8 + 8 + 1), "steps": Ke, "steps_per_call": Te,
+        "isolated_block": {"value": world * B * K / (t_block / 1000.0), "unit": "env-steps/s", "ms": t_block,
+                           "ms_min": min(iso), "ms_max": max(iso), "repeats": len(iso),
+                           "what": "ONE K-step block with the device idle before and after (median of 9)"},
+        "chained": per_step["chained"],
+        "lockstep": per_step["lockstep"],
+        "e2e": {"value": e2e_rate, "unit": "env-steps/s", "h2d_bytes_per_step": B * in_bytes,
+                "d2h_bytes_per_step": B * out_bytes, "steps": n_calls * Te, "steps_per_call": Te, "timed_s": e2e_ms / 1000.0,
                 "api": "anm_rollout_host_async (%d steps per call) + anm_host_sync_previous after every call (C ABI; pinned host "
                        "arrays, uploaded / downloaded by the copy engines through device staging buffers while the "
                        "kernels of consecutive calls run back to back)" % Te,
-                "sync_every_step": {"value": e2e_sync_rate, "unit": "env-steps/s", "steps": Ks,
-                                    "api": "anm_step_host (synchronous)"},
                 "checksum": checksum},  # fmt: skip
+        "sync_every_step": {"value": e2e_sync_rate, "unit": "env-steps/s", "steps": n_s, "timed_s": sync_ms / 1000.0,
+                            "api": "anm_step_host (synchronous; pinned host arrays in / out every step)"},
         "gpu_launches": gpu_launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    if gather_rate is not None:
-        line["with_obs_allgather"] = {"value": gather_rate, "unit": "env-steps/s",
-                                      "what": "step + NCCL all-gather of [B,20] (obs|reward|terminated) per step"}  # fmt: skip
+    if gather:
+        if "value" in gather.get("p2p", {}):
+            line["with_obs_allgather"] = dict(gather["p2p"], what="one launch per step; the kernel epilogue stores every "
+                                              "[obs | reward | terminated] row into every peer's gather buffer over NVLink "
+                                              "(fused step + all-gather), then the per-step arrival wait")
+        else:
+            line["with_obs_allgather"] = gather.get("p2p")
+        line["with_obs_allgather_nccl"] = dict(gather.get("nccl", {}), what="one launch per step writing packed rows locally + "
+                                               "ncclAllGather (all_gather_into_tensor) per step")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -214,6 +214,9 @@ int anm_debug_set_launch_ordinal(anm_handle h, uint64_t k);
  * computes magnitudes;  2: a = the MUFU.RCP64H + 2 Newton steps reciprocal of the 2x2 block inversions. */
 int anm_debug_math(int32_t kind, int64_t n, const double* x_dev, const double* y_dev_or_null, double* a_dev,
                    double* b_dev_or_null, void* stream);
+/* Measurement aid: the device's fp64 FMA throughput (TFLOP/s, 2 flops per DFMA) from a register-only kernel of
+ * independent FMA chains -- the denominator of bench.py's fp64 roofline leg.  Synchronous, a few milliseconds. */
+int anm_debug_fp64_peak(int device, double* tflops_out);
 /* Host-only (no device needed): the exact projection of (p, q) on {a_k x + b_k y <= h_k, k < R <= 10}
  * (Generator / StorageUnit.map_pq, devices.py:280-304, 472-522) through the same candidate table that
  * anm_create builds for the kernel, evaluated like the kernel does; out2 = (x, y), NaN if infeasible. */
@@ -260,6 +263,30 @@ int anm_transition(anm_handle h, const double* p_load_dev, const double* p_pot_d
                    const double* p_set_dev, const double* q_set_dev, double* full_state_dev,
                    double* reward_dev, double* e_loss_dev, double* penalty_dev,
                    uint8_t* converged_dev, void* stream);
+
+/* ---- multi-GPU: the observation all-gather, fused into the step ---------------------------------
+ * One process per GPU, instances sharded by contiguous slices; the only exchange of the path is the all-gather of the
+ * batched [obs | reward | terminated] rows for a central learner.  Instead of a collective after the step, the step
+ * kernel's epilogue stores every row straight into every rank's gather buffer over NVLink / NVSwitch (peer memory
+ * mapped with CUDA IPC), and signals arrival per step:
+ *   anm_gather_create   allocates this rank's buffer [slots][rows_global][n_obs + 2] (+ arrival flags) and returns
+ *                       its 64-byte CUDA IPC handle; the caller exchanges the handles of all ranks (any transport);
+ *   anm_gather_attach   maps the other ranks' buffers (ipc_handles: [world][64] bytes, own entry ignored);
+ *   anm_step_packed     anm_step that also writes the packed rows [B, n_obs + 2] (terminated as 0.0 / 1.0) to
+ *                       `packed_dev_or_null` and, with gather != 0, into row row0 + instance of slot (gather steps so
+ *                       far) % slots of EVERY rank's buffer; such a launch is fully stream-ordered (never chained);
+ *   anm_gather_wait     enqueues the arrival wait of the most recent gather step on `stream` and returns the device
+ *                       pointer of its slot [rows_global, n_obs + 2]: work enqueued after it sees every rank's rows.
+ * With S slots a rank may run S - 1 steps ahead of the slowest consumer: keep wait(t) -> consume(t) -> step(t + S - 1)
+ * in stream order (S = 2 for a lock-step closed loop).  All ranks must perform the same sequence of gather steps. */
+int anm_gather_create(anm_handle h, int32_t world, int32_t rank, int64_t row0, int64_t rows_global, int32_t slots,
+                      void* ipc_handle_out64);
+int anm_gather_attach(anm_handle h, const void* ipc_handles);
+int anm_step_packed(anm_handle h, const double* action_dev, const double* next_vars_dev_or_null, double* obs_dev,
+                    double* reward_dev, uint8_t* terminated_dev, double* packed_dev_or_null, int32_t gather,
+                    const anm_step_extras* extras_or_null, void* stream);
+int anm_gather_wait(anm_handle h, double** rows_out, void* stream);
+int anm_gather_destroy(anm_handle h);
 
 /* Carried per-env state: soc [B, n_des] (p.u.), aux [B, K], terminated [B].
  * Any pointer may be NULL.  Device pointers; asynchronous on `stream`. */

@@ -116,7 +116,7 @@ def test_synth30_passes_validators():
 def test_capi_library_exports_every_declared_symbol():
     """The C-ABI library loads (no GPU needed) and exports each function of include/anm_b200.h."""
     hdr = open(os.path.join(ROOT, "include", "anm_b200.h")).read()
-    declared = set(re.findall(r"\b(anm_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(anm_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_capi.EXPORTED_SYMBOLS)
     lib = _capi.load_library()
     for name in declared:
@@ -258,7 +258,7 @@ import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
 import numpy as np, torch, torch.distributed as dist
 import anm_oracle, anm_numpy
-from gym_anm_b200.distributed import shard_slice, all_gather_rows
+from gym_anm_b200.distributed import shard_slice, shard_counts, all_gather_rows
 from gym_anm_b200.env_spec import anm6easy_spec
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank, B = dist.get_rank(), 11                    # uneven shards on purpose (6 + 5)
@@ -273,7 +273,7 @@ def rollout(lo, hi):
     return obs
 sl = shard_slice(B, rank, 2)
 mine = torch.as_tensor(rollout(sl.start, sl.stop))
-full = all_gather_rows(mine)
+full = all_gather_rows(mine, counts=shard_counts(B, 2))
 if rank == 0:
     want = torch.as_tensor(rollout(0, B))
     assert full.shape == want.shape and torch.equal(full, want), "shard-equivalence failed"
