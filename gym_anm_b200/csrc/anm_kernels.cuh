@@ -1050,6 +1050,15 @@ struct SmallNR {
 #ifndef ANM_SING_GUARD
 #define ANM_SING_GUARD 1 /* 0 compiles the guard out (A/B builds only) */
 #endif
+/* The guard watches the first ANM_SING_MAXIT iterations only.  Solves that converge do so within 8 iterations; an
+ * iterate that is still wandering after 12 has typically blown up (|V| ~ 1e7 and more), and there a block's theta
+ * column is EXACTLY zero by absorption (I_b - Y_bb V_b rounds to 0 once |Y_bb V_b| exceeds 2^53 times its neighbours'
+ * terms): ~1 % of the iterations of a divergent solve (measured, tools/trip_probe.py) -- not a pivoting question (the
+ * reference's trajectory is as lost there), and redoing 100 iterations densely for each would triple the cost of
+ * every divergent instance. */
+#ifndef ANM_SING_MAXIT
+#define ANM_SING_MAXIT 12
+#endif
 /* out of line (the hot instruction stream stays what it is); returns it | converged << 8 | stable << 9 */
 template <int LPE>
 __device__ __noinline__ int nr_generic_cold(const unsigned char* blob, double* __restrict__ ws, int lane, unsigned gm) {
@@ -1161,7 +1170,7 @@ struct RadialNR {
 #if ANM_SING_GUARD
       {
         const unsigned sb = __ballot_sync(ANM_FULL, sing && active);
-        const int tr = (((sb & gm) != 0u) && !done) ? 1 : 0;
+        const int tr = (((sb & gm) != 0u) && !done && it <= ANM_SING_MAXIT) ? 1 : 0;
         tripped |= tr;
         done |= tr;
         sing = false;
