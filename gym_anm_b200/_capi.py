@@ -123,6 +123,8 @@ _PROTOS = {
     "anm_debug_math": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_void_p]),
     "anm_debug_fp64_peak": (C.c_int, [C.c_int, c_double_p]),
     "anm_debug_project": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int32, C.c_double, C.c_double, c_double_p]),
+    "anm_debug_project_ex": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int32, C.c_uint32, C.c_int32, C.c_int32,
+                                       C.c_double, C.c_double, c_double_p]),
     "anm_debug_blob": (C.c_int64, [C.POINTER(NetworkDesc), C.POINTER(EnvDesc), C.c_void_p, C.c_int64]),
     "anm_debug_rng": (C.c_int, [C.c_uint64, C.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p]),
     "anm_step": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.POINTER(StepExtras), C.c_void_p]),

@@ -371,7 +371,7 @@ struct Cst {  // resolved pointers into the staged blob
       *sp_blk_y, *sp_step, *sp_row, *sp_col, *sp_nbr, *sp_tgt;
   const double* rad_y;
   const double4* cand_coef; /* [ncand_total][2]: kx, ky of every candidate */
-  const int *cand_info, *cand_ptr, *ctrl_fin;
+  const int *cand_info, *cand_ptr, *ctrl_fin, *cand_short;
   __device__ explicit Cst(const unsigned char* b) {
     H = reinterpret_cast<const AnmConstHeader*>(b);
 #define DP(name, off) name = reinterpret_cast<const double*>(b + H->off)
@@ -388,7 +388,7 @@ struct Cst {  // resolved pointers into the staged blob
     IP(sp_blk_i, o_sp_blk_i); IP(sp_blk_j, o_sp_blk_j); IP(sp_blk_y, o_sp_blk_y); IP(sp_step, o_sp_step);
     IP(sp_row, o_sp_row); IP(sp_col, o_sp_col); IP(sp_nbr, o_sp_nbr); IP(sp_tgt, o_sp_tgt);
     cand_coef = reinterpret_cast<const double4*>(b + H->o_cand_coef);
-    IP(cand_info, o_cand_info); IP(cand_ptr, o_cand_ptr); IP(ctrl_fin, o_ctrl_fin);
+    IP(cand_info, o_cand_info); IP(cand_ptr, o_cand_ptr); IP(ctrl_fin, o_ctrl_fin); IP(cand_short, o_cand_short);
 #undef DP
 #undef IP
   }
@@ -1421,7 +1421,9 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
     const int d = C.ctrl_dev[c];
     const double* rows = C.ctrl_rows + c * 3 * ANM_MAX_ROWS;
     const bool is_des = (c >= H.n_gen);
-    const int c0 = C.cand_ptr[c], nc = C.cand_ptr[c + 1] - c0;
+    const int c0 = C.cand_ptr[c];
+    /* the candidates on a row that a finite dynamic row dominates are left out (anm_capi.cu: build_candidates) */
+    const int nc = ((unsigned)rowfin[c] & (unsigned)C.cand_short[2 * c + 1]) ? C.cand_short[2 * c] : (C.cand_ptr[c + 1] - c0);
     double po, qo;
     project_polygon<LPE, FULL>(rows, rows + ANM_MAX_ROWS, rownh + c * ANM_MAX_ROWS, rowhe + c * ANM_MAX_ROWS,
                                (unsigned)rowfin[c], C.cand_coef + 2 * c0, C.cand_info + c0, nc, is_des ? 10 : 7, in_ps[c], in_qs[c], lane,

@@ -52,6 +52,8 @@ struct AnmConstHeader {
   int32_t o_cand_ptr;                        /* int[n_ctrl+1]: first candidate of each device               */
   int32_t o_cand_info;                       /* int[ncand]: s1 | s2 << 8 | need << 16                       */
   int32_t o_cand_coef;                       /* double[ncand][8]: kx[4], ky[4] on (p, q, h[s1], h[s2])      */
+  int32_t o_cand_short;                      /* int[n_ctrl][2]: (n_short, bit): only the first n_short candidates
+                                                count when the finite-row mask has `bit` (anm_capi.cu)       */
   /* radial networks (bus graph = tree rooted at the slack): per non-slack bus b (lane b-1) */
   int32_t is_radial, rad_maxc, rad_maxdepth;
   int32_t o_rad_parent, o_rad_depth;         /* int[n_bus-1]: parent's lane (-1 = slack), depth >= 1 */

@@ -222,6 +222,11 @@ int anm_debug_fp64_peak(int device, double* tflops_out);
  * anm_create builds for the kernel, evaluated like the kernel does; out2 = (x, y), NaN if infeasible. */
 int anm_debug_project(const double* a, const double* b, const double* h, int32_t R, double p, double q,
                       double* out2);
+/* The same with the table pruned as anm_create prunes it: rows whose bit is NOT in dyn_mask are static (intersections
+ * of two static rows that lie outside the static polygon are dropped); dom_row >= 0: the static row whose candidates
+ * are left out when the dynamic row dom_by (same normal, never looser) is finite. */
+int anm_debug_project_ex(const double* a, const double* b, const double* h, int32_t R, uint32_t dyn_mask,
+                         int32_t dom_row, int32_t dom_by, double p, double q, double* out2);
 /* Host-only (no device needed): the constant blob anm_create would upload for this network / environment
  * (layout: csrc/anm_layout.h); returns its size in bytes and copies at most `cap` bytes to `out`. */
 int64_t anm_debug_blob(const anm_network_desc* net, const anm_env_desc* env, unsigned char* out, int64_t cap);

@@ -130,14 +130,21 @@ def test_capi_library_exports_every_declared_symbol():
     assert rc != 0 and lib.anm_last_error()
 
 
-def _project_host(lib, rows, h, p, q):
+def _project_host(lib, rows, h, p, q, dyn_mask=None, dom=(-1, -1)):
+    """dyn_mask=None: the full candidate table; else the table pruned as anm_create prunes it (rows outside dyn_mask
+    are static, `dom` = (static row, dynamic row that dominates it))."""
     a = np.ascontiguousarray(rows[:, 0], dtype=np.float64)
     b = np.ascontiguousarray(rows[:, 1], dtype=np.float64)
     h = np.ascontiguousarray(h, dtype=np.float64)
     out = np.zeros(2)
-    rc = lib.anm_debug_project(a.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
-                               h.ctypes.data_as(_capi.c_double_p), len(h), float(p), float(q),
-                               out.ctypes.data_as(_capi.c_double_p))  # fmt: skip
+    if dyn_mask is None:
+        rc = lib.anm_debug_project(a.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                                   h.ctypes.data_as(_capi.c_double_p), len(h), float(p), float(q),
+                                   out.ctypes.data_as(_capi.c_double_p))  # fmt: skip
+    else:
+        rc = lib.anm_debug_project_ex(a.ctypes.data_as(_capi.c_double_p), b.ctypes.data_as(_capi.c_double_p),
+                                      h.ctypes.data_as(_capi.c_double_p), len(h), int(dyn_mask), int(dom[0]), int(dom[1]),
+                                      float(p), float(q), out.ctypes.data_as(_capi.c_double_p))  # fmt: skip
     assert rc == 0
     return out
 
@@ -165,7 +172,7 @@ def test_projection_candidate_table_matches_the_exact_projection():
                          [P[T2], -1, -P[R2]], [P[T3], -1, -P[R3]], [-P[T4], 1, P[R4]], [-1, 0, 0], [1, 0, 0]], float)  # fmt: skip
 
     rng = np.random.default_rng(0)
-    worst = 0.0
+    worst = worst_pruned = 0.0
     for d, kind in ((2, "g"), (4, "g"), (6, "s")):
         P = dp[d]
         rows = rows_gen(P) if kind == "g" else rows_des(P)
@@ -177,15 +184,23 @@ def test_projection_candidate_table_matches_the_exact_projection():
                 soc = rng.uniform(P[SMIN], P[SMAX]) if it % 5 else rng.choice([P[SMIN], P[SMAX]])
                 h[8] = -(soc - P[SMAX]) / (0.25 * P[EFF])
                 h[9] = P[EFF] * (soc - P[SMIN]) / 0.25
+            static_ok = True
             if it % 13 == 0:
-                h[rng.integers(3, len(h))] = np.inf  # an unused row
+                k = int(rng.integers(3, len(h)))
+                h[k] = np.inf  # an unused row
+                static_ok = (kind == "s" and k >= 8)  # the pruned table assumes that static rows stay what they are
             p, q = rng.uniform(-0.7, 0.7, 2)
             if it % 11 == 0:
                 p, q = rng.uniform(-0.05, 0.2, 2)  # often inside
             want = project_onto_polygon(rows[:, :2], h, (p, q))
             got = _project_host(lib, rows, h, p, q)
             worst = max(worst, float(np.abs(want - got).max()))
+            if static_ok:  # the pruned table of the kernel: static non-vertex intersections dropped, p <= p_max dominated
+                got2 = _project_host(lib, rows, h, p, q, dyn_mask=4 if kind == "g" else 0x300,
+                                     dom=(1, 2) if kind == "g" else (-1, -1))
+                worst_pruned = max(worst_pruned, float(np.abs(want - got2).max()))
     assert worst < 1e-14, worst
+    assert worst_pruned < 1e-14, worst_pruned
     # box clipping is exact (the reference's assertEqual tests, tests/simulator/test_devices.py:541-549)
     rows = rows_gen(dp[2])
     h = rows[:, 2].copy()
