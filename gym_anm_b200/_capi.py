@@ -115,6 +115,7 @@ _PROTOS = {
     "anm_reset": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_void_p]),
     "anm_set_reset_full_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "anm_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "anm_seed_async": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "anm_reset_seeded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 3 + [C.c_void_p]),
     "anm_rng_state_bytes": (C.c_int64, [C.c_void_p]),
     "anm_get_rng": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -102,7 +102,12 @@ class BatchedANMEnv(EnvBase):
         return out
 
     def next_vars_batch(self, state):
-        """[B, n_load + n_gen + K] array / tensor, or None to use the built-in device table."""
+        """TENSOR-LEVEL HOOK.  `state`: the [B, state_N] float64 CUDA tensor of all instances.  Return the
+        [B, n_load + n_gen + K] stochastic variables of the next step as a CUDA tensor (torch ops, no host round trip) --
+        or a NumPy array --, or None to use the built-in device table.  Override it in a custom environment that runs
+        many instances: the default below calls the reference's per-environment hook `next_vars(s_t)` once per instance
+        on the host (one device-to-host copy and B Python calls per step), which is what keeps an unmodified
+        single-environment subclass (examples/simple_env.py) working."""
         if self.spec.table is not None:
             return None
         s = state.cpu().numpy()
@@ -178,9 +183,18 @@ class BatchedANMEnv(EnvBase):
             self.observation_N = n
         return obs, {}
 
+    def observation_batch(self, state):
+        """TENSOR-LEVEL HOOK for callable observation spaces (anm_env.py:313-331 with a callable `observation`):
+        return the [B, n_obs] observations computed from the [B, state_N] state tensor with torch ops, or None
+        (default) to fall back to calling the per-environment callable row by row on the host."""
+        return None
+
     def _observe(self):
         if self.spec.obs_callable is None:
             return self._obs
+        ob = self.observation_batch(self.state)
+        if ob is not None:
+            return torch.as_tensor(ob, dtype=torch.float64, device=self.device)
         rows = [np.asarray(self.spec.obs_callable(s), dtype=np.float64) for s in self.state.cpu().numpy()]
         return torch.as_tensor(np.stack(rows), device=self.device)
 

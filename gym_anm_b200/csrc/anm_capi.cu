@@ -22,6 +22,22 @@
 #include "anm_kernels.cuh"
 #include "anm_seeded_reset.cuh"
 
+/* NVTX ranges around every entry point that enqueues device work (reset / step / rollout / host copies), so that a
+ * timeline (Nsight Systems, or anything that injects NVTX) shows the calls by name; header-only NVTX3, a no-op when no
+ * tool is attached.  -DANM_NO_NVTX compiles them out. */
+#ifndef ANM_NO_NVTX
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define ANM_NVTX(name) NvtxRange nvtx_range_(name)
+#else
+#define ANM_NVTX(name)
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -41,6 +57,9 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 typedef std::complex<double> cd;
+#ifndef ANM_RESET_ROUNDS
+#define ANM_RESET_ROUNDS 4 /* retry rounds of anm_reset_seeded enqueued per host synchronisation */
+#endif
 
 struct BlobBuilder {
   std::vector<unsigned char> buf;
@@ -915,6 +934,7 @@ int anm_get_sizes(anm_handle h, anm_sizes* o) {
 
 int anm_reset(anm_handle h, const double* s0, const uint8_t* mask, double* obs, double* state, uint8_t* converged,
               void* stream) {
+  ANM_NVTX("anm_reset");
   if (!h || !s0 || !obs || !converged) return fail(ANM_E_INVALID, "anm_reset: null argument");
   DeviceGuard guard(h->device);
   AnmLaunch p;
@@ -927,6 +947,7 @@ int anm_reset(anm_handle h, const double* s0, const uint8_t* mask, double* obs, 
 
 int anm_step(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
              uint8_t* terminated, const anm_step_extras* ex, void* stream) {
+  ANM_NVTX("anm_step");
   if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step: null argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_step: next_vars is NULL but the environment has no built-in table");
@@ -949,6 +970,7 @@ int anm_step(anm_handle h, const double* action, const double* next_vars, double
 
 int anm_rollout(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs, double* reward,
                 uint8_t* terminated, uint32_t flags, void* stream) {
+  ANM_NVTX("anm_rollout");
   if (!h || !action || !obs || !reward || !terminated || T < 0) return fail(ANM_E_INVALID, "anm_rollout: bad argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_rollout: next_vars is NULL but the environment has no built-in table");
@@ -965,20 +987,24 @@ int anm_rollout(anm_handle h, int64_t T, const double* action, const double* nex
   return launch(h, p, (cudaStream_t)stream, (flags & ANM_STEP_CHAINED) ? ANM_LF_CHAINED : 0u);
 }
 
-int anm_seed(anm_handle h, uint64_t seed_first) {
+int anm_seed(anm_handle h, uint64_t seed_first) { return anm_seed_async(h, seed_first, nullptr); }
+
+int anm_seed_async(anm_handle h, uint64_t seed_first, void* stream) {
   if (!h) return fail(ANM_E_INVALID, "null handle");
   DeviceGuard guard(h->device);
-  std::vector<AnmPcg64> host((size_t)h->B);
-  for (int64_t e = 0; e < h->B; ++e) anm_pcg_seed(host[(size_t)e], seed_first + (uint64_t)e);
   if (!h->d_rng) CUDA_TRY(cudaMalloc((void**)&h->d_rng, (size_t)h->B * sizeof(AnmPcg64)));
-  CUDA_TRY(cudaDeviceSynchronize()); /* setup-time call: no launch of this handle may still be using the streams */
-  CUDA_TRY(cudaMemcpy(h->d_rng, host.data(), (size_t)h->B * sizeof(AnmPcg64), cudaMemcpyHostToDevice));
+  /* SeedSequence -> PCG64 expansion on the device, ordered on the caller's stream like every other call: no host
+   * loop over the batch, no device-wide synchronisation */
+  const int threads = 128, blocks = (int)((h->B + threads - 1) / threads);
+  anm::seed_streams_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(h->d_rng, seed_first, h->B);
+  CUDA_TRY(cudaPeekAtLastError());
   h->seeded = true;
   return ANM_OK;
 }
 
 int anm_reset_seeded(anm_handle h, const uint8_t* mask, int32_t max_tries, int32_t date_draw, double* obs, double* state,
                      uint8_t* converged, void* stream) {
+  ANM_NVTX("anm_reset_seeded");
   if (!h || !obs || !converged) return fail(ANM_E_INVALID, "anm_reset_seeded: null argument");
   if (!h->seeded) return fail(ANM_E_INVALID, "anm_reset_seeded: call anm_seed first");
   if (h->H.table_len == 0 || h->H.K < 1)
@@ -995,19 +1021,28 @@ int anm_reset_seeded(anm_handle h, const uint8_t* mask, int32_t max_tries, int32
   }
   const int threads = 128, blocks = (int)((B + threads - 1) / threads);
   /* Round k: instances whose previous attempt converged are finished (date draw), the others draw a new initial
-   * state; the host looks at the number of draws (one stream synchronisation per round, typically two or three
-   * rounds) and stops when nobody drew; then the ordinary reset launch applies the drawn states. */
-  for (int round = 0; round <= max_tries; ++round) {
-    CUDA_TRY(cudaMemsetAsync(h->d_remaining, 0, sizeof(int), st));
-    anm::seeded_draw_kernel<<<blocks, threads, 0, st>>>(h->d_blob, h->B, h->d_rng, h->d_need, mask, round == 0,
-                                                        round == max_tries, h->d_conv_tmp, converged, date_draw, h->s_s0,
-                                                        h->d_remaining);
-    CUDA_TRY(cudaPeekAtLastError());
+   * state; then the ordinary reset launch applies the drawn states of the instances that drew.  Both kernels do
+   * nothing for an instance that is done, so the rounds are enqueued ANM_RESET_ROUNDS at a time (the loop needs two or
+   * three for ANM6Easy) and the host looks at the number of draws of the batch's LAST round only: one stream
+   * synchronisation per reset instead of one per round. */
+  const int batch = ANM_RESET_ROUNDS;
+  for (int round = 0; round <= max_tries;) {
+    const int stop = std::min(round + batch, max_tries + 1);
+    for (; round < stop; ++round) {
+      CUDA_TRY(cudaMemsetAsync(h->d_remaining, 0, sizeof(int), st));
+      anm::seeded_draw_kernel<<<blocks, threads, 0, st>>>(h->d_blob, h->B, h->d_rng, h->d_need, mask, round == 0,
+                                                          round == max_tries, h->d_conv_tmp, converged, date_draw, h->s_s0,
+                                                          h->d_remaining);
+      CUDA_TRY(cudaPeekAtLastError());
+      if (round < max_tries) {
+        int rc = anm_reset(h, h->s_s0, h->d_need, obs, state, h->d_conv_tmp, stream);
+        if (rc) return rc;
+      }
+    }
+    /* the draws of one more (draw-only) look: did anybody still need a state after the batch's last reset? */
     CUDA_TRY(cudaMemcpyAsync(h->h_remaining, h->d_remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (*h->h_remaining == 0) break;
-    int rc = anm_reset(h, h->s_s0, h->d_need, obs, state, h->d_conv_tmp, stream);
-    if (rc) return rc;
   }
   return ANM_OK;
 }
@@ -1187,6 +1222,7 @@ int anm_gather_destroy(anm_handle h) {
 
 int anm_step_packed(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
                     uint8_t* terminated, double* packed, int32_t gather, const anm_step_extras* ex, void* stream) {
+  ANM_NVTX("anm_step_packed");
   if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_packed: null argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_step_packed: next_vars is NULL but the environment has no built-in table");
@@ -1274,6 +1310,7 @@ int anm_set_autoreset_pool(anm_handle h, const double* pool, int64_t pool_size) 
 int anm_transition(anm_handle h, const double* p_load, const double* p_pot, const double* p_set, const double* q_set,
                    double* full_state, double* reward, double* e_loss, double* penalty, uint8_t* converged,
                    void* stream) {
+  ANM_NVTX("anm_transition");
   if (!h) return fail(ANM_E_INVALID, "anm_transition: null handle");
   const AnmConstHeader& H = h->H;
   if ((H.n_load && !p_load) || (H.n_gen && !p_pot) || (H.n_ctrl && (!p_set || !q_set)))
@@ -1356,6 +1393,7 @@ static int step_host_enqueue(anm_handle h, int64_t T, const double* action, cons
 
 int anm_step_host(anm_handle h, const double* action, const double* next_vars, double* obs, double* reward,
                   uint8_t* terminated) {
+  ANM_NVTX("anm_step_host");
   if (!h || !action || !obs || !reward || !terminated) return fail(ANM_E_INVALID, "anm_step_host: null argument");
   if (!next_vars && h->H.table_len == 0)
     return fail(ANM_E_INVALID, "anm_step_host: next_vars is NULL but the environment has no built-in table");
@@ -1406,6 +1444,7 @@ static int hostset_reserve(anm_handle h, anm_handle_s::HostSet& hs, int64_t rows
 
 int anm_rollout_host_async(anm_handle h, int64_t T, const double* action, const double* next_vars, double* obs,
                            double* reward, uint8_t* terminated) {
+  ANM_NVTX("anm_rollout_host_async");
   if (!h || !action || !obs || !reward || !terminated || T < 1 || T > INT32_MAX)
     return fail(ANM_E_INVALID, "anm_rollout_host_async: bad argument");
   if (!next_vars && h->H.table_len == 0)
@@ -1474,6 +1513,7 @@ int anm_host_sync_previous(anm_handle h) {
 }
 
 int anm_reset_host(anm_handle h, const double* s0, const uint8_t* mask, double* obs, double* state, uint8_t* converged) {
+  ANM_NVTX("anm_reset_host");
   if (!h || !s0 || !obs || !converged) return fail(ANM_E_INVALID, "anm_reset_host: null argument");
   DeviceGuard guard(h->device);
   h->st_last_was_rollout = false;

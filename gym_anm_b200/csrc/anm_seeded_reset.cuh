@@ -43,6 +43,16 @@ __device__ inline void draw_init_state(const Cst& C, double* __restrict__ s0, An
   }
 }
 
+/* PCG64(SeedSequence(seed_first + e)) for every instance, expanded on the device (anm_seed): no host loop over the
+ * batch, no blocking copy */
+__global__ void seed_streams_kernel(AnmPcg64* __restrict__ rng, uint64_t seed_first, int64_t B) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  AnmPcg64 r;
+  anm_pcg_seed(r, seed_first + (uint64_t)e);
+  rng[e] = r;
+}
+
 /* One round of the reset loop (anm_env.py:266-289) for every instance that is still looking for an initial state:
  * if its previous attempt converged it is done (and draws ANM6.reset's date, anm6.py:138), otherwise it draws the next
  * initial state -- unless the attempts are used up (`last`). */

@@ -100,7 +100,7 @@ class NativeBatch:
 
     def seed(self, seed_first):
         """Instance e gets the stream Generator(PCG64(SeedSequence(seed_first + e))), kept on the device."""
-        _capi.check(self.lib.anm_seed(self.h, C.c_uint64(int(seed_first))), self.lib)
+        _capi.check(self.lib.anm_seed_async(self.h, C.c_uint64(int(seed_first)), self._stream()), self.lib)
 
     def reset_seeded(self, mask=None, max_tries=100, date_draw=True, obs=None, state=None, converged=None):
         """ANMEnv.reset with ANM6Easy's init_state drawn on the device from the instances' own streams."""

@@ -384,6 +384,70 @@ def test_singular_schur_block_guard_matches_pivoting_oracle(maxit):
             assert all(o["conv_c"]) and o["v_err"] < 1e-8
 
 
+def test_tensor_level_hooks_of_a_custom_env():
+    """A custom environment in the style of the reference's examples/simple_env.py:33 (2-bus grid, random load and
+    auxiliary variable per step, callable observation) written once with the reference's per-environment hooks
+    (`next_vars(s_t)`, a callable `observation`) and once with the tensor-level hooks (`next_vars_batch`,
+    `observation_batch`: torch ops on the [B, .] CUDA tensors, no host round trip): identical trajectories."""
+    from gym_anm_b200.anm_env import BatchedANMEnv
+
+    N_ = None
+    network = {
+        "baseMVA": 100,
+        "bus": np.array([[0, 0, 132, 1.0, 1.0], [1, 1, 33, 1.1, 0.9]]),
+        "device": np.array([[0, 0, 0, N_, 200, -200, 200, -200, N_, N_, N_, N_, N_, N_, N_],
+                            [1, 1, -1, 0.2, 0, -10, N_, N_, N_, N_, N_, N_, N_, N_, N_],
+                            [2, 1, 2, N_, 30, 0, 30, -30, N_, N_, N_, N_, N_, N_, N_]], dtype=object),
+        "branch": np.array([[0, 1, 0.01, 0.1, 0.0, 3, 1, 0]]),
+    }
+    B, T = 512, 12
+    draws = np.random.default_rng(3).uniform(size=(T + 1, B, 2))  # the "random" hooks replay these
+
+    def obs_fn(s):  # a callable observation: scaled load power and the auxiliary variable
+        return np.array([s[1] * 0.125, s[-1]])
+
+    class PerEnv(BatchedANMEnv):
+        def __init__(self, observation):
+            super().__init__(network, observation, 1, 0.25, 0.9, 100, np.array([[0, 10]]), (1, 100), 1, num_envs=B)
+            self.k = 0
+
+        def init_state(self):
+            u = draws[0, self._env_index]
+            s0 = np.zeros(self.state_N)  # [dev_p x3, dev_q x3, gen_p_max, aux]
+            s0[1], s0[4] = -5 * u[0], -u[0]
+            s0[2], s0[5], s0[6] = 10 * u[1], 2 * u[1] - 1, 20 * u[1]
+            return s0
+
+        def next_vars(self, s_t):
+            i = self._env_index
+            return np.array([-10 * draws[self.k, i, 0], 30 * draws[self.k, i, 1], np.floor(10 * draws[self.k, i, 1])])
+
+    class Tensor(PerEnv):
+        def next_vars_batch(self, state):
+            d = torch.as_tensor(draws[self.k], device=self.device)
+            return torch.stack([-10 * d[:, 0], 30 * d[:, 1], torch.floor(10 * d[:, 1])], dim=1)
+
+        def observation_batch(self, state):
+            return torch.stack([state[:, 1] * 0.125, state[:, -1]], dim=1)
+
+    envs = [PerEnv(obs_fn), Tensor(obs_fn)]
+    outs = []
+    for env in envs:
+        obs, _ = env.reset()
+        rows = [obs.clone()]
+        rng = np.random.default_rng(5)
+        for t in range(T):
+            env.k = t + 1
+            a = rng.uniform(env.action_space.low, env.action_space.high, size=(B, env.action_space.shape[0]))
+            o, r, d, _, _ = env.step(a)
+            rows += [o.clone(), r.clone(), d.double()]
+        outs.append(rows)
+    assert envs[0].observation_space.shape == (2,)
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    assert float(outs[1][-3].abs().sum()) > 0
+
+
 def test_fast_math_ulp_sweep():
     """The kernel's own math routines against libm (NumPy): `sincos_fast` (V = |V| e^{j theta} in the Newton loop),
     the sqrt(fma) magnitude (|V|, |S|, |I|) and the RCP64H + two Newton steps reciprocal (2x2 block inverses)."""
