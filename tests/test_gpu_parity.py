@@ -580,6 +580,82 @@ def test_state_dict_roundtrip_and_simulator_view():
     assert set(d) >= {"bus_v_magn", "dev_p", "branch_s", "des_soc", "gen_p_max"} and abs(d["bus_v_magn"]["pu"][0] - 1.0) < 1e-12
 
 
+def test_checkpoint_restores_costs_observation_and_random_streams():
+    """state_dict / load_state_dict: e_loss / penalty / observation of the last step and the random
+    streams -- host Generators and the device-side PCG64 streams of `device_init=True` -- so that the resets AFTER a
+    resume draw the same initial states."""
+    from gym_anm_b200.anm6 import BatchedANM6Easy
+
+    for device_init in (False, True):
+        env = BatchedANM6Easy(128, validate_actions=False, device_init=device_init)
+        env.reset(seed=11)
+        rng = np.random.default_rng(2)
+        acts = rng.uniform(env.spec.action_low, env.spec.action_high, size=(6, 128, 6))
+        for t in range(3):
+            env.step(acts[t])
+        ck = env.state_dict()
+        saved = {k: env.__dict__[k].clone() for k in ("e_loss", "penalty", "_obs")}
+
+        def continue_run(e):
+            out = []
+            for t in range(3, 6):
+                o, r, d, _, _ = e.step(acts[t])
+                out += [o.clone(), r.clone(), d.clone()]
+                if bool(d.any()):
+                    o2, _ = e.reset(mask=d)  # draws from the streams: must continue where the checkpoint left them
+                    out.append(o2.clone())
+            o3, _ = e.reset()  # and a full reset without a new seed
+            return out + [o3.clone()]
+
+        want = continue_run(env)
+        env2 = BatchedANM6Easy(128, validate_actions=False, device_init=device_init)
+        env2.reset(seed=999)  # a different history, then the checkpoint
+        env2.load_state_dict(ck)
+        for k, v in saved.items():
+            assert torch.equal(env2.__dict__[k], v), k
+        got = continue_run(env2)
+        assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want)), device_init
+
+
+def test_launch_ordinals_survive_the_32_bit_wrap():
+    """Launch chaining derives the ordinal of a launch from a device-side ticket counter (ticket / grid + 1).  With a
+    grid that is not a power of two a 32-bit counter would split a launch in two ordinals when it wraps (~2^32 CTA
+    starts: minutes of closed-loop stepping) and dead-lock the next chained wait; the counter is 64 bits wide and the
+    ordinals are compared modulo 2^32.  Presets the handle just below both wraps (the ticket's 2^32 and the ordinal's
+    2^32) and runs chained steps, a rollout and a CUDA-graph replay across them against an untouched twin."""
+    import ctypes as C
+
+    from gym_anm_b200 import _capi
+    from gym_anm_b200.anm6 import BatchedANM6Easy
+
+    B = 1000  # 250 CTAs: not a power of two
+    rng = np.random.default_rng(4)
+    acts = torch.as_tensor(rng.uniform(-1, 1, size=(12, B, 6)) * [15, 25, 30, 50, 50, 50] + [15, 25, 0, 0, 0, 0], device="cuda")
+    twin = BatchedANM6Easy(B, validate_actions=False)
+    twin.reset(seed=3)
+    pool = twin.state.clone()
+    twin.native.set_autoreset_pool(pool)
+    ck = twin.state_dict()
+    want = [tuple(x.clone() for x in twin.native.step(acts[t], None, chained=True)) for t in range(8)]
+    want_roll = tuple(x.clone() for x in twin.native.rollout(acts[8:]))
+    lib = _capi.load_library()
+    grid = (B + 3) // 4
+    for k in (2**32 // grid - 3, 2**32 - 4, 2**40):  # ticket wrap, ordinal wrap, far beyond both
+        env = BatchedANM6Easy(B, validate_actions=False)
+        env.reset(seed=3)
+        env.native.set_autoreset_pool(pool)
+        env.load_state_dict(ck)
+        torch.cuda.synchronize()
+        _capi.check(lib.anm_debug_set_launch_ordinal(env.native.h, C.c_uint64(k)), lib)
+        for t in range(8):
+            o, r, d = env.native.step(acts[t], None, chained=True)
+            assert torch.equal(o, want[t][0]) and torch.equal(r, want[t][1]) and torch.equal(d, want[t][2]), (k, t)
+        got_roll = env.native.rollout(acts[8:], chained=True)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(got_roll, want_roll)), k
+        assert env.native.watchdog() == [0] * 8
+
+
 def test_other_solvers_same_results_subprocess():
     """Re-run the golden / oracle parity tests with the other Newton back-ends forced (ANM_SOLVER):
     the shared-memory generic kernels (default for N >= 10 buses) and the tree-elimination solver."""
