@@ -150,6 +150,7 @@ struct anm_handle_s {
   const double* pool = nullptr;
   int64_t pool_size = 0;
   double* reset_full = nullptr; /* optional [B, n_full] output of every reset launch (anm_set_reset_full_state) */
+  double* d_dense_scratch = nullptr; /* block-sparse solver: [grid x gpb][M x (M+1)] (singular-block guard's redo) */
   /* fused observation all-gather (anm_gather_*): this rank's buffer [flags 1 KB | slots x rows x (O + 2) doubles], the
    * peers' buffers opened over CUDA IPC, and the device arrays of pointers the kernel reads */
   struct Gather {
@@ -775,6 +776,7 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
     h->wd_steps += h->wd_last;
   }
   p.watchdog = h->wd_dev;
+  p.dense_scratch = h->d_dense_scratch;
   const bool pdl = pdl_enabled();
   p.flags = pdl ? flags : (flags & ~ANM_LF_CHAINED);
   cudaLaunchConfig_t cfg;
@@ -892,6 +894,11 @@ int anm_create(const anm_network_desc* net, const anm_env_desc* env, int64_t num
   if (e != cudaSuccess) { anm_destroy(h); return fail(ANM_E_CUDA, "handle init: %s", cudaGetErrorString(e)); }
   rc = choose_geometry(h);
   if (rc) { anm_destroy(h); return rc; }
+  if (h->H.solver == 4) { /* the block-sparse solver's cold redo works on a dense system in global memory */
+    const size_t per = (size_t)h->H.n_unk * (size_t)(h->H.n_unk + 1) * sizeof(double);
+    cudaError_t e2 = cudaMalloc((void**)&h->d_dense_scratch, per * (size_t)h->grid * (size_t)h->gpb);
+    if (e2 != cudaSuccess) { anm_destroy(h); return fail(ANM_E_CUDA, "dense scratch: %s", cudaGetErrorString(e2)); }
+  }
   *out = h;
   return ANM_OK;
 }
@@ -901,7 +908,7 @@ int anm_destroy(anm_handle h) {
   anm_gather_destroy(h);
   DeviceGuard guard(h->device);
   cudaFree(h->d_blob); cudaFree(h->d_soc); cudaFree(h->d_aux); cudaFree(h->d_term); cudaFree(h->d_episode);
-  cudaFree(h->d_seq); cudaFree(h->d_ticket);
+  cudaFree(h->d_seq); cudaFree(h->d_ticket); cudaFree(h->d_dense_scratch);
   cudaFree(h->d_rng); cudaFree(h->d_need); cudaFree(h->d_conv_tmp); cudaFree(h->d_remaining);
   if (h->h_remaining) cudaFreeHost(h->h_remaining);
   if (h->wd_host) cudaFreeHost(h->wd_host);

@@ -107,6 +107,7 @@ struct AnmLaunch {
   uint64_t wd_limit_ns;  /* chaining watchdog: longest legitimate wait for the previous launch */
   /* packed rows [obs | reward | terminated] of a step: local copy and / or the fused all-gather ("observation
    * all-gather" below): every rank's gather buffer and arrival flags, mapped into this process over NVLink */
+  double* dense_scratch;               /* block-sparse solver: [grid x groups][M x (M+1)] for the singular-block guard's redo */
   double* packed;                      /* [B, O + 2] or NULL */
   double* const* g_peers;              /* [g_world] rows of every rank's gather buffer [g_slots][g_rows][O + 2], or NULL */
   unsigned long long* const* g_flags;  /* [g_world] every rank's arrival flags (one word per sender) */
@@ -544,12 +545,13 @@ __device__ __forceinline__ void gj_pivot_smem(double* __restrict__ J, int M, dou
  * (FULL is true only for LPE == 32, where the group is the warp). */
 template <int LPE, bool FULL>
 __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
-                                           int& it_out, bool& converged_out, bool& stable_out) {
+                                           int& it_out, bool& converged_out, bool& stable_out, double* Jext = nullptr) {
   const AnmConstHeader& H = *C.H;
   const int N = H.n_bus, n = N - 1, M = H.n_unk, LD = M + 1;
   double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* x = ws + H.w_x;
   double* vre = ws + H.w_vre; double* vim = ws + H.w_vim; double* ere = ws + H.w_ere; double* eim = ws + H.w_eim;
-  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* J = ws + H.w_J; double* dxs = ws + H.w_dx;
+  double* ire = ws + H.w_ire; double* iim = ws + H.w_iim; double* dxs = ws + H.w_dx;
+  double* J = Jext ? Jext : ws + H.w_J; /* Jext: the dense M x (M+1) system in global scratch (block-sparse solver's redo) */
   it_out = 0;
   converged_out = stable_out = true;
   if (!live) return; /* group-uniform */
@@ -648,9 +650,28 @@ __device__ __forceinline__ void nr_generic(const Cst& C, double* __restrict__ ws
  * kept for the back-substitution) and the degree^2 + degree Schur updates J_ij -= J_ib W_j, f_i -= J_ib w
  * are spread over the lanes.  No pivoting across blocks (a singular Schur block with a regular Jacobian is
  * non-generic; ANM_SOLVER=generic gives the dense partial-pivoting solver).  One environment per warp. */
+/* Singular-block guard (same rule as RadialNR's, see there): a pivot block whose determinant has all but cancelled in one
+ * of the first ANM_SING_MAXIT iterations sends the instance to the dense partially pivoted solver (nr_generic on a
+ * dense system in global scratch memory, `Jscratch`: 27 KB per instance at 30 buses is too much shared memory for a
+ * cold path). */
+#ifndef ANM_SING_TAU
+#define ANM_SING_TAU 1e-7
+#endif
+#ifndef ANM_SING_MAXIT
+#define ANM_SING_MAXIT 12
+#endif
+template <int LPE>
+__device__ __noinline__ int nr_generic_cold_ext(const unsigned char* blob, double* __restrict__ ws, double* Jscratch, int lane,
+                                                unsigned gm) {
+  const Cst C(blob);
+  int it = 0;
+  bool conv = false, stable = false;
+  nr_generic<LPE, (LPE == 32)>(C, ws, lane, gm, true, it, conv, stable, Jscratch);
+  return it | (conv ? 256 : 0) | (stable ? 512 : 0);
+}
 template <int LPE, bool FULL>
 __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
-                                          int& it_out, bool& converged_out, bool& stable_out) {
+                                          int& it_out, bool& converged_out, bool& stable_out, double* Jscratch) {
   const AnmConstHeader& H = *C.H;
   const int N = H.n_bus, n = N - 1, M = H.n_unk, nblk = H.sp_nblk;
   double* busp = ws + H.w_busp; double* busq = ws + H.w_busq; double* x = ws + H.w_x;
@@ -667,6 +688,7 @@ __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws,
   gsync<FULL>(gm);
   int it = 0;
   double diff;
+  bool tripped = false;
   for (;;) {
     for (int b = lane; b < N; b += LPE) { /* V = |V| e^{j theta}, E = V/|V| */
       double re = 1.0, im = 0.0, er = 1.0, ei = 0.0;
@@ -736,7 +758,9 @@ __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws,
       const int* st = C.sp_step + 5 * k;
       const int b = st[0], pb = st[1], d = st[2], off = st[3], toff = st[4];
       const double p0 = blk[4 * pb], p1 = blk[4 * pb + 1], p2 = blk[4 * pb + 2], p3 = blk[4 * pb + 3];
-      const double rd = fast_rcp(p0 * p3 - p1 * p2);
+      const double pa = p0 * p3, pb2 = p1 * p2, det = pa - pb2;
+      tripped = tripped || (fabs(det) <= ANM_SING_TAU * (fabs(pa) + fabs(pb2))); /* uniform in the group */
+      const double rd = fast_rcp(det);
       const double i0 = p3 * rd, i1 = -p1 * rd, i2 = -p2 * rd, i3 = p0 * rd; /* D_b^-1 */
       /* W_j = D_b^-1 J_bj (in place), w = D_b^-1 f_b (in place) */
       for (int t = lane; t <= d; t += LPE) {
@@ -792,6 +816,8 @@ __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws,
       }
       gsync<FULL>(gm);
     }
+    if (tripped && it <= ANM_SING_MAXIT && Jscratch) break; /* singular-block guard: leave the block elimination */
+    tripped = false;
     for (int b = lane + 1; b < N; b += LPE) { /* x <- x - J^{-1} F (:220) */
       x[b - 1] -= f[2 * (b - 1)];
       x[n + b - 1] -= f[2 * (b - 1) + 1];
@@ -801,6 +827,13 @@ __device__ __forceinline__ void nr_sparse(const Cst& C, double* __restrict__ ws,
   it_out = it;
   converged_out = (diff == diff);
   stable_out = converged_out && diff <= ANM_NR_TOL;
+  if (tripped) { /* cold: the whole power flow again, dense with partial pivoting, from the flat start */
+    gsync<FULL>(gm);
+    const int r = nr_generic_cold_ext<LPE>(reinterpret_cast<const unsigned char*>(C.H), ws, Jscratch, lane, gm);
+    it_out = r & 255;
+    converged_out = (r & 256) != 0;
+    stable_out = (r & 512) != 0;
+  }
   (void)M;
 }
 
@@ -1355,7 +1388,7 @@ __device__ __forceinline__ void init_polygon_rows(const Cst& C, double* __restri
  * environment (a dead group runs along for lock-step but skips the Newton iterations). */
 template <int LPE, int NB, int SOLVER, bool FULL>
 __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws, int lane, unsigned gm, bool live,
-                                           double& e_loss, double& penalty, int& n_iter_out, int& n_fb, int& n_big
+                                           double* jscratch, double& e_loss, double& penalty, int& n_iter_out, int& n_fb, int& n_big
 #if ANM_DIAG
                                            , long long* stamp
 #endif
@@ -1466,7 +1499,7 @@ __device__ __forceinline__ bool transition(const Cst& C, double* __restrict__ ws
   bool converged = false, stable = false;
   n_fb = n_big = 0;
   if constexpr (SOLVER == 4)
-    nr_sparse<LPE, FULL>(C, ws, lane, gm, live, it, converged, stable);
+    nr_sparse<LPE, FULL>(C, ws, lane, gm, live, it, converged, stable, jscratch);
   else if constexpr (SOLVER == 2)
     RadialNR<LPE, NB>::run(C, ws, lane, gm, live, it, converged, stable, n_fb, n_big);
   else if constexpr (SOLVER == 1)
@@ -1655,6 +1688,10 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
 
   const int D = H.n_dev, nl = H.n_load, ng = H.n_gen, ns = H.n_des, nc = H.n_ctrl, K = H.K;
   const int S = H.n_state, O = H.n_obs, F = H.n_full, A = H.n_action, NV = H.n_next_vars;
+  /* block-sparse solver: this lane group's dense system in global scratch (the singular-block guard's redo) */
+  double* jscratch = (SOLVER == 4 && P.dense_scratch)
+                         ? P.dense_scratch + ((size_t)blockIdx.x * GPB + grp) * (size_t)H.n_unk * (size_t)(H.n_unk + 1)
+                         : nullptr;
   double* in_pl = ws + H.w_in_pl; double* in_pp = ws + H.w_in_pp; double* in_ps = ws + H.w_in_ps;
   double* in_qs = ws + H.w_in_qs; double* soc = ws + H.w_soc; double* aux = ws + H.w_aux;
   double* s0w = ws + H.w_s0; double* full = ws + H.w_full;
@@ -1811,7 +1848,7 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
       int nit, nfb, nbig;
 #if ANM_DIAG
       const long long t_pass0 = clock64();
-      const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig, stamp);
+      const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, jscratch, el, pe, nit, nfb, nbig, stamp);
       const long long t_trans = clock64();
       if (P.solver_stats && run && lane == 0) {
         P.solver_stats[4 * e] = nfb & 0xffff;
@@ -1820,7 +1857,7 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
         P.solver_stats[4 * e + 3] = (int)(t_trans - t_pass0);
       }
 #else
-      const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, el, pe, nit, nfb, nbig);
+      const bool stable = transition<LPE, NB, SOLVER, FULL>(C, ws, lane, gm, run, jscratch, el, pe, nit, nfb, nbig);
 #endif
 
       /* ---- carried-state updates that feed the state vector ----------------------------------------- */

@@ -333,6 +333,8 @@ import os, sys, json
 import numpy as np
 sys.path[:0] = [%(root)r, os.path.join(%(root)r, "oracle"), os.path.join(%(root)r, "tests")]
 os.environ["ANM_DEBUG_NR_MAXIT"] = "%(maxit)d"
+if "%(solver)s":
+    os.environ["ANM_SOLVER"] = "%(solver)s"
 import anm_oracle
 from gym_anm_b200.env_spec import HostEnvSpec
 from gym_anm_b200.native import NativeBatch
@@ -357,26 +359,28 @@ print("RESULT" + json.dumps(out))
 """
 
 
+@pytest.mark.parametrize("solver", ["", "sparse"])
 @pytest.mark.parametrize("maxit", [1, 2, 100])
-def test_singular_schur_block_guard_matches_pivoting_oracle(maxit):
+def test_singular_schur_block_guard_matches_pivoting_oracle(maxit, solver):
     """Adversarial case for the tree elimination (RadialNR inverts 2x2 blocks without pivoting across blocks; the
     reference's SuperLU pivots): the leaf block of the first Newton iteration is exactly / nearly singular while the
     Jacobian is regular.  The singular-block guard must redo that iteration with the dense partially pivoted solver:
     after ONE iteration (ANM_DEBUG_NR_MAXIT=1, in a subprocess) the iterate is finite and equals the pivoting C oracle's
     (an unguarded block elimination gives inf / NaN here); after two iterations still; and the full solve takes the
-    same decision.  bsh = 1.0 is the regular control case."""
+    same decision.  bsh = 1.0 is the regular control case.  `solver`: the default (radial tree elimination) and the
+    block-sparse LU (ANM_SOLVER=sparse), whose guard redoes the solve on a dense system in global scratch memory."""
     import json
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, "-c", _SINGULAR_SCRIPT % {"root": root, "maxit": maxit}], capture_output=True,
+    res = subprocess.run([sys.executable, "-c", _SINGULAR_SCRIPT % {"root": root, "maxit": maxit, "solver": solver}], capture_output=True,
                          text=True, timeout=600)  # fmt: skip
     assert res.returncode == 0, res.stderr[-2000:]
     out = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("RESULT")][0][6:])
     for bsh, o in out.items():
-        assert o["conv_g"] == o["conv_c"], (maxit, bsh, o)
+        assert o["conv_g"] == o["conv_c"], (maxit, solver, bsh, o)
         if maxit <= 2:
             assert o["finite"], (maxit, bsh, o)
             assert o["v_err"] < 1e-8 and o["a_err"] < 1e-8, (maxit, bsh, o)
@@ -578,6 +582,69 @@ def test_state_dict_roundtrip_and_simulator_view():
                                           {2: 1.0, 4: 2.0, 6: 0.0})  # fmt: skip
     d = sim.state_dict(0)
     assert set(d) >= {"bus_v_magn", "dev_p", "branch_s", "des_soc", "gen_p_max"} and abs(d["bus_v_magn"]["pu"][0] - 1.0) < 1e-12
+
+
+def test_single_env_simulator_state_and_render_bridge():
+    """`ANM6Easy().simulator.state` -- the nested dict the reference's renderer (anm6.py:101-109) and its MPC agents
+    (mpc.py:419, mpc_constant.py:23-29) read -- against the reference's recorded full state, step by step; and the
+    render bridge: `render()` feeds a renderer object the reference's start / update call sequence and payload."""
+    from gym_anm_b200.anm6 import ANM6Easy
+
+    g = load("anm6easy_traj_seed0.npz")
+
+    class Recorder:  # the three functions of gym_anm/envs/anm6_env/rendering/py/rendering.py
+        def __init__(self):
+            self.calls = []
+
+        def start(self, title, dev_type, ps, qs, branch_rate, bus_v_min, bus_v_max, soc_max, costs_range):
+            self.calls.append(("start", title, list(dev_type), list(ps), list(qs), list(branch_rate), list(soc_max), costs_range))
+            return "http", type("Ws", (), {"address": "ws://test"})()
+
+        def update(self, address, date, year_count, dev_p, dev_q, branch_s, des_soc, gen_p_max, bus_v_magn, costs, collapsed):
+            self.calls.append(("update", address, date, year_count, list(dev_p), list(dev_q), list(branch_s), list(des_soc),
+                               list(gen_p_max), list(bus_v_magn), list(costs), collapsed))
+
+        def close(self, http, ws):
+            self.calls.append(("close",))
+
+    rec = Recorder()
+    env = ANM6Easy(renderer=rec)
+    obs, _ = env.reset(seed=0)
+    assert rel_err(obs, g["reset_obs"][0]) < RTOL
+    st = env.simulator.state
+    assert set(st) == {"bus_p", "bus_q", "bus_v_magn", "bus_v_ang", "bus_i_magn", "bus_i_ang", "dev_p", "dev_q", "des_soc",
+                       "gen_p_max", "branch_p", "branch_q", "branch_s", "branch_i_magn", "branch_i_ang"}
+    assert list(st["des_soc"]["MWh"]) == [6] and list(st["gen_p_max"]["MW"]) == [2, 4]
+    assert list(st["branch_s"]["MVA"]) == [(0, 1), (1, 2), (1, 3), (2, 4), (2, 5)]
+    np.testing.assert_allclose([st["dev_p"]["MW"][i] for i in range(7)], g["reset_state"][0][:7], rtol=1e-9, atol=1e-9)
+    env.render()
+    assert rec.calls[0][0] == "start" and rec.calls[0][1] == "ANM6Easy" and rec.calls[0][2] == [0, -1, 2, -1, 2, -1, 3]
+    assert rec.calls[0][5] == [32.0, 25.0, 18.0, 18.0, 18.0] and rec.calls[0][7] == (1, 100)
+    from gym_anm_b200.env_spec import anm6easy_spec
+
+    sl = anm6easy_spec().full_state_slices()
+    n_upd = 1
+    for t in range(40):
+        if g["terminated"][t]:
+            break
+        obs, r, term, trunc, info = env.step(g["actions"][t])
+        assert rel_err(obs, g["obs"][t]) < RTOL and abs(r - g["reward"][t]) <= 1e-8 * max(1.0, abs(g["reward"][t]))
+        st, want = env.simulator.state, g["full_state"][t]
+        np.testing.assert_allclose(list(st["bus_v_magn"]["pu"].values()), want[sl["bus_v_magn"]], rtol=1e-9)
+        np.testing.assert_allclose(list(st["branch_s"]["MVA"].values()), want[sl["branch_s"]] * 100, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(list(st["dev_q"]["MVAr"].values()), want[sl["dev_q"]] * 100, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(st["des_soc"]["pu"][6], want[sl["des_soc"]][6], rtol=1e-9, atol=1e-12)
+        env.render(skip_frames=1)  # every second call updates
+        if (t + 1) % 2 == 0:
+            n_upd += 1
+            u = rec.calls[-1]
+            assert u[0] == "update" and u[1] == "ws://test" and u[2] == env.date and not u[-1]
+            np.testing.assert_allclose(u[4], want[sl["dev_p"]] * 100, rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(u[9], want[sl["bus_v_magn"]], rtol=1e-9)
+            assert u[10] == [env.e_loss, env.penalty]
+    assert sum(c[0] == "update" for c in rec.calls) == n_upd
+    env.close()
+    assert rec.calls[-1] == ("close",)
 
 
 def test_checkpoint_restores_costs_observation_and_random_streams():

@@ -312,3 +312,30 @@ def test_gloo_world2_shard_equivalence(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD_OK" in outs[0]
+
+
+def test_gymnasium_registration_and_env_base_class():
+    """reference gym_anm/__init__.py:8-11: `ANM6Easy-v0` is registered with Gymnasium and the registered class is a
+    `gymnasium.Env` subclass (Gymnasium's wrappers assert that).  Gymnasium is not installed in this image, so the
+    stand-in of oracle/shims/ plays its part: the registration call, the entry point string and the base class are what
+    is pinned here (in a subprocess: the stand-in must be importable BEFORE the package)."""
+    code = r"""
+import sys, os, importlib
+root = %r
+sys.path[:0] = [root, os.path.join(root, "oracle", "shims")]
+import gymnasium
+import gym_anm_b200
+from gymnasium.envs.registration import registry
+entry = registry["ANM6Easy-v0"]
+assert entry == "gym_anm_b200.anm6:ANM6Easy", entry
+mod, cls = entry.split(":")
+klass = getattr(importlib.import_module(mod), cls)
+assert issubclass(klass, gymnasium.Env), klass.__mro__
+from gym_anm_b200.anm_env import BatchedANMEnv
+assert issubclass(BatchedANMEnv, gymnasium.Env)
+from gym_anm_b200.spaces import Box
+assert Box is gymnasium.spaces.Box
+print("REGISTERED_OK")
+""" % ROOT
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "REGISTERED_OK" in res.stdout, res.stderr[-2000:]
