@@ -99,3 +99,22 @@ def test_mpc_perfect_uses_future_profiles():
             np.testing.assert_allclose(Gf[i][:, k] * 100, env.P_maxs[:, (t0 + 1 + k) % 96])
     a = agent.act(env)
     assert a.shape == (2, 6)
+
+
+def test_mpc_worker_pool_equals_serial():
+    """BASELINE config 5's action source at scale: the LPs of a batch spread over worker processes give the same
+    actions as the in-process loop (same LP, same solver, row order kept)."""
+    spec = anm6easy_spec()
+    rng = np.random.default_rng(3)
+    space = Box(spec.action_low, spec.action_high)
+    serial = MPCAgentConstant(_Sim(spec), space, 0.995, safety_margin=0.96, planning_steps=4)
+    pooled = MPCAgentConstant(_Sim(spec), space, 0.995, safety_margin=0.96, planning_steps=4, workers=2)
+    B = 24
+    Lf = np.repeat(rng.uniform(-0.2, 0.0, (B, 3, 1)), 4, axis=2)
+    Gf = np.repeat(rng.uniform(0.0, 0.4, (B, 2, 1)), 4, axis=2)
+    soc = rng.uniform(0.0, 1.0, (B, 1))
+    try:
+        a, b = serial.solve_batch(Lf, Gf, soc), pooled.solve_batch(Lf, Gf, soc)
+    finally:
+        pooled.close()
+    assert a.shape == b.shape == (B, 6) and np.array_equal(a, b)
