@@ -145,7 +145,11 @@ typedef struct anm_step_extras {
   double* state;                  /* dev [B, n_state]  ANMEnv.state after the step    */
   double* e_loss;                 /* dev [B]           ANMEnv.e_loss (clipped)        */
   double* penalty;                /* dev [B]           ANMEnv.penalty (clipped)       */
-  int32_t* n_iter;                /* dev [B]           Newton-Raphson iterations      */
+  int32_t* n_iter;                /* dev [B]           Newton-Raphson iterations: equal to the reference's count
+                                     (_newton_raphson_sparse, solve_load_flow.py:176-226) for every solve that
+                                     converges; for a TERMINAL step whose residual became NaN the reference stops at
+                                     the first NaN while the radial / dense solvers run on to the cap (100): only the
+                                     decision (`terminated`) is identical there */
   double* full_state;             /* dev [B, n_full_state] Simulator.state, p.u.      */
   int32_t* solver_stats;          /* dev [B, 4] diagnostics: Newton iterations that needed the
                                      partial-pivoting fallback, iterations with |theta| > 1e5,
