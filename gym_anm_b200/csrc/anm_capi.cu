@@ -163,6 +163,7 @@ struct anm_handle_s {
     unsigned long long* d_state = nullptr;    /* device: [0] steps completed, [8..72) CTA counters */
     int64_t steps_host = 0;                   /* gather steps launched so far (host mirror of d_state[0]) */
     bool attached = false;
+    bool last_waited_inline = false;          /* the most recent gather step waited for the arrival inside its kernel */
   } g;
   /* launch geometry */
   int lpe = 32, gpb = 4, grid = 1, smem = 0, num_sms = 1;
@@ -1249,11 +1250,12 @@ int anm_step_packed(anm_handle h, const double* action, const double* next_vars,
     auto& g = h->g;
     p.g_peers = g.d_peers; p.g_flags = g.d_flags; p.g_state = g.d_state;
     p.g_rows = g.rows; p.g_row0 = g.row0; p.g_world = g.world; p.g_rank = g.rank; p.g_slots = g.slots;
+    g.last_waited_inline = gather > 1;
     ++g.steps_host;
   }
   /* never chained: the gather slot is derived from the completed-step count at kernel entry; remote stores need the
    * system-scope fence */
-  return launch(h, p, (cudaStream_t)stream, gather ? ANM_LF_SYSOUT : 0u);
+  return launch(h, p, (cudaStream_t)stream, gather ? (ANM_LF_SYSOUT | (gather > 1 ? ANM_LF_GATHER_WAIT : 0u)) : 0u);
 }
 
 int anm_gather_wait(anm_handle h, double** rows_out, void* stream) {
@@ -1261,9 +1263,11 @@ int anm_gather_wait(anm_handle h, double** rows_out, void* stream) {
   auto& g = h->g;
   if (!g.attached || g.steps_host < 1) return fail(ANM_E_INVALID, "anm_gather_wait: no gather step has been launched");
   DeviceGuard guard(h->device);
-  anm::gather_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((const unsigned long long*)g.base, g.d_state, g.world,
-                                                              30000000000ull);
-  CUDA_TRY(cudaPeekAtLastError());
+  if (!g.last_waited_inline) {
+    anm::gather_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((const unsigned long long*)g.base, g.d_state, g.world,
+                                                                30000000000ull);
+    CUDA_TRY(cudaPeekAtLastError());
+  }
   if (rows_out) {
     const size_t W = (size_t)h->H.n_obs + 2;
     const int64_t slot = (g.steps_host - 1) % g.slots;

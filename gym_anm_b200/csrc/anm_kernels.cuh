@@ -118,6 +118,7 @@ struct AnmLaunch {
 #define ANM_WD_WORDS 8
 #define ANM_LF_CHAINED 1u /* inputs do not depend on earlier work in the stream: skip griddepcontrol.wait */
 #define ANM_LF_SYSOUT 2u  /* outputs live in mapped host memory: system-scope fence before publishing   */
+#define ANM_LF_GATHER_WAIT 4u /* fused all-gather: the launch also waits for every rank's rows (arrival inside the kernel) */
 
 namespace anm {
 
@@ -2008,6 +2009,27 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
         for (int p = 0; p < P.g_world; ++p)
           asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.g_flags[p] + P.g_rank), "l"(g) : "memory");
         asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.g_state), "l"(g) : "memory");
+        if (P.flags & ANM_LF_GATHER_WAIT) {
+          /* arrival inside the same kernel: this (last) CTA also waits until every rank's rows of this step are in
+           * the local buffer, so the completion of the launch means "step done and gathered" -- one kernel for the
+           * step, the all-gather and its arrival.  No deadlock: every rank signals before it waits. */
+          const unsigned long long* mine = P.g_flags[P.g_rank];
+          uint64_t t0 = 0;
+          uint32_t spins = 0;
+          for (int p = 0; p < P.g_world; ++p) {
+            for (;;) {
+              unsigned long long v;
+              asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + p) : "memory");
+              if (v >= g) break;
+              __nanosleep(200);
+              if ((++spins & 1023u) == 0u) {
+                const uint64_t now = global_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 30000000000ull) __trap(); /* a peer died */
+              }
+            }
+          }
+        }
       }
     }
   }

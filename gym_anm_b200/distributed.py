@@ -73,12 +73,16 @@ class ObsExchange:
     stream) before launching `step` number t + slots - 1.  Equal shards only for mode="nccl"; `rows_global` / `row0`
     default to equal contiguous shards in rank order."""
 
-    def __init__(self, native, mode="p2p", slots=2, group=None, row0=None, rows_global=None):
+    def __init__(self, native, mode="p2p", slots=2, group=None, row0=None, rows_global=None, inline_wait=True):
         from . import _capi
 
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("ObsExchange needs an initialised torch.distributed process group")
         self.nb, self.mode, self.group, self.slots = native, mode, group, int(slots)
+        # p2p: the step kernel itself waits for every rank's rows (one kernel = step + all-gather + arrival); False: the
+        # arrival wait is a separate small kernel enqueued by wait(), so that work enqueued between step() and wait()
+        # overlaps the slower ranks
+        self.inline_wait = bool(inline_wait)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.B, self.W = native.B, native.O + 2
         self.row0 = self.rank * self.B if row0 is None else int(row0)
@@ -121,7 +125,7 @@ class ObsExchange:
         slot = self._n % self.slots
         packed = None if self.mode == "p2p" else self.packed[slot]
         self._capi.check(self.lib.anm_step_packed(nb.h, p(action), p(nv), p(self.obs), p(self.reward), p(self.term),
-                                                  p(packed), 1 if self.mode == "p2p" else 0,
+                                                  p(packed), (2 if self.inline_wait else 1) if self.mode == "p2p" else 0,
                                                   None if ex is None else C.byref(ex), nb._stream()), self.lib)  # fmt: skip
         if self.mode == "nccl":
             # the pack is done by the kernel on the current stream; only the collective runs on the side stream, which

@@ -284,7 +284,10 @@ int anm_transition(anm_handle h, const double* p_load_dev, const double* p_pot_d
  *   anm_gather_attach   maps the other ranks' buffers (ipc_handles: [world][64] bytes, own entry ignored);
  *   anm_step_packed     anm_step that also writes the packed rows [B, n_obs + 2] (terminated as 0.0 / 1.0) to
  *                       `packed_dev_or_null` and, with gather != 0, into row row0 + instance of slot (gather steps so
- *                       far) % slots of EVERY rank's buffer; such a launch is fully stream-ordered (never chained);
+ *                       far) % slots of EVERY rank's buffer; such a launch is fully stream-ordered (never chained).
+ *                       gather == 2: the launch also waits for the arrival of every rank's rows of this step (its last
+ *                       CTA polls the arrival flags after signalling): ONE kernel is the step, the all-gather and its
+ *                       completion, and anm_gather_wait then only returns the slot pointer;
  *   anm_gather_wait     enqueues the arrival wait of the most recent gather step on `stream` and returns the device
  *                       pointer of its slot [rows_global, n_obs + 2]: work enqueued after it sees every rank's rows.
  * With S slots a rank may run S - 1 steps ahead of the slowest consumer: keep wait(t) -> consume(t) -> step(t + S - 1)

@@ -44,15 +44,13 @@ def main():
             want_env = BatchedANM6Easy(B_global, device=dev, validate_actions=False, device_init=device_init)
             want0, _ = want_env.reset(seed=seed)
             assert torch.equal(want0[sl.start:sl.stop], obs0), "reset observations differ from the single-batch run"
-        for mode in ("p2p", "nccl"):
-            if mode == "nccl":  # both modes replay the same steps from the same carried state
-                env.load_state_dict(snap)
-            else:
-                snap = env.state_dict()
-                snap_want = None if want_env is None else want_env.state_dict()
-            if want_env is not None and mode == "nccl":
+        snap = env.state_dict()
+        snap_want = None if want_env is None else want_env.state_dict()
+        for mode in ("p2p", "p2p_separate_wait", "nccl"):  # every mode replays the same steps from the same carried state
+            env.load_state_dict(snap)
+            if want_env is not None:
                 want_env.load_state_dict(snap_want)
-            ex = ObsExchange(env.native, mode=mode)
+            ex = ObsExchange(env.native, mode=mode.split("_")[0], inline_wait=(mode == "p2p"))
             h = hashlib.sha256()
             for t in range(T):
                 a = actions(env.spec, sl.start, sl.stop, t)
@@ -70,7 +68,7 @@ def main():
             out[(device_init, mode)] = h.hexdigest()[:16]
         del env, want_env
     if rank == 0:
-        assert out[(False, "p2p")] == out[(False, "nccl")] == out[(True, "p2p")] == out[(True, "nccl")], out
+        assert len(set(out.values())) == 1 and len(out) == 6, out
         print("MGPU_OK world=%d B_global=%d T=%d hash=%s" % (world, B_global, T, out[(False, "p2p")]))
     dist.barrier()
     dist.destroy_process_group()
