@@ -120,6 +120,7 @@ _PROTOS = {
     "anm_rng_state_bytes": (C.c_int64, [C.c_void_p]),
     "anm_get_rng": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "anm_set_rng": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "anm_debug_stall_instance": (C.c_int, [C.c_void_p, C.c_int64]),
     "anm_debug_set_launch_ordinal": (C.c_int, [C.c_void_p, C.c_uint64]),
     "anm_debug_math": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_void_p]),
     "anm_debug_fp64_peak": (C.c_int, [C.c_int, c_double_p]),

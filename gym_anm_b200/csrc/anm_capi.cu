@@ -756,7 +756,29 @@ static bool pdl_enabled() {
   return on;
 }
 
+/* base of the chaining watchdog's limit; ANM_WD_LIMIT_MS (environment) shortens it for the tests of the time-out path */
+static uint64_t wd_base_ns() {
+  static const uint64_t v = [] {
+    const char* e = getenv("ANM_WD_LIMIT_MS");
+    const long ms = e ? atol(e) : 2000;
+    return (uint64_t)(ms >= 1 ? ms : 2000) * 1000000ull;
+  }();
+  return v;
+}
+
+/* a launch-chaining time-out is sticky: the kernel that hit it skipped the instance, so the handle's state is no
+ * longer what the caller thinks it is -- every later call fails loudly (the CUDA context is fine) */
+static int check_watchdog(anm_handle h) {
+  if (h->wd_host && ((volatile uint32_t*)h->wd_host)[0] != 0u) {
+    const volatile uint32_t* w = h->wd_host;
+    return fail(ANM_E_TIMEOUT, "launch-chaining time-out: instance %u waited for launch ordinal %u but saw %u (CTA %u of %u); "
+                "the handle is unusable, destroy it", w[1], w[2], w[3], w[4], w[5]);
+  }
+  return 0;
+}
+
 int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
+  if (int rc = check_watchdog(h)) return rc;
   p.blob = h->d_blob;
   p.blob_bytes = h->blob_bytes;
   p.B = h->B;
@@ -772,7 +794,7 @@ int launch(anm_handle h, AnmLaunch& p, cudaStream_t st, uint32_t flags = 0) {
     const int64_t passes = (h->B + (int64_t)h->grid * h->gpb - 1) / ((int64_t)h->grid * h->gpb);
     const bool chained = pdl_enabled() && (flags & ANM_LF_CHAINED);
     if (!chained) h->wd_steps = 0;
-    p.wd_limit_ns = 2000000000ull + 2000000ull * (uint64_t)h->wd_steps;
+    p.wd_limit_ns = wd_base_ns() + 2000000ull * (uint64_t)h->wd_steps;
     h->wd_last = (int64_t)(p.T > 1 ? p.T : 1) * passes;
     h->wd_steps += h->wd_last;
   }
@@ -1128,6 +1150,17 @@ int anm_debug_set_launch_ordinal(anm_handle h, uint64_t k) {
   std::vector<uint32_t> seq((size_t)h->B, (uint32_t)k);
   CUDA_TRY(cudaMemcpy(h->d_ticket, &t, sizeof(t), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(h->d_seq, seq.data(), seq.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return ANM_OK;
+}
+
+int anm_debug_stall_instance(anm_handle h, int64_t e) {
+  if (!h || e < 0 || e >= h->B) return fail(ANM_E_INVALID, "anm_debug_stall_instance: bad argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  uint32_t v = 0;
+  CUDA_TRY(cudaMemcpy(&v, h->d_seq + e, sizeof(v), cudaMemcpyDeviceToHost));
+  v -= 3u; /* as if the last three launches had never finished with this instance */
+  CUDA_TRY(cudaMemcpy(h->d_seq + e, &v, sizeof(v), cudaMemcpyHostToDevice));
   return ANM_OK;
 }
 
@@ -1511,7 +1544,7 @@ int anm_host_sync(anm_handle h) {
   DeviceGuard guard(h->device);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (h->st_out) CUDA_TRY(cudaStreamSynchronize(h->st_out));
-  return ANM_OK;
+  return check_watchdog(h);
 }
 
 int anm_host_sync_previous(anm_handle h) {

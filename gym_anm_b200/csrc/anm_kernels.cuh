@@ -142,8 +142,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
  * seq[e] is published with a release store after a fence that covers the whole lane group's writes and consumed
  * with an acquire load; the carried state is read with ld.global.cg (L2), never from a possibly stale L1 line.
  * No deadlock: by the same induction every CTA that is being waited for is already running.  A wait that outlasts
- * the most the previous launch can take (2 s + 2 ms per step and pass) writes a record to the handle's watchdog
- * words (mapped host memory) and traps. */
+ * the most the launches before it can take (2 s + 2 ms per step and pass of every launch since the last fully ordered
+ * one) writes a record to the handle's watchdog words (mapped host memory); the lane group skips the instance, the
+ * kernel ends normally, and the host fails the next call on the handle with ANM_E_TIMEOUT (recoverable: the CUDA
+ * context survives, the handle does not). */
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint64_t global_ns() {
@@ -152,27 +154,33 @@ __device__ __forceinline__ uint64_t global_ns() {
   return t;
 }
 __device__ __noinline__ void chain_timeout(uint32_t* wd, int64_t e, uint32_t want, uint32_t seen) {
+  /* Recoverable: the record goes to mapped host memory, the lane group gives the instance up (the caller skips it) and
+   * the kernel ends normally -- the CUDA context survives.  The host sees the record at its next call on the handle and
+   * fails that call (and every later one) loudly: ANM_E_TIMEOUT, the handle is unusable from then on. */
   if (wd && atomicCAS(wd, 0u, 1u) == 0u) {
     wd[1] = (uint32_t)e; wd[2] = want; wd[3] = seen; wd[4] = blockIdx.x; wd[5] = gridDim.x; wd[6] = threadIdx.x;
     __threadfence_system();
   }
-  __trap(); /* fail loudly: the launch that owns this instance never finished with it */
 }
 /* `limit_ns`: 2 s plus 2 ms for every step the previous launch takes an instance through (the host knows): a chained
  * launch may legitimately wait for the whole of a long rollout. */
-__device__ __forceinline__ void seq_wait_for(const uint32_t* p, uint32_t want, uint32_t* wd, int64_t e,
+/* false: timed out (the record is written; the caller gives the instance up) */
+__device__ __forceinline__ bool seq_wait_for(const uint32_t* p, uint32_t want, uint32_t* wd, int64_t e,
                                              uint64_t limit_ns) {
   uint32_t v;
   uint32_t spins = 0;
   uint64_t t0 = 0;
   for (;;) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    if ((int32_t)(v - want) >= 0) break;
+    if ((int32_t)(v - want) >= 0) return true;
     __nanosleep(100);
     if ((++spins & 1023u) == 0u) {
       const uint64_t now = global_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > limit_ns) chain_timeout(wd, e, want, v);
+      else if (now - t0 > limit_ns) {
+        chain_timeout(wd, e, want, v);
+        return false;
+      }
     }
   }
 }
@@ -1703,14 +1711,17 @@ __global__ void __launch_bounds__((NB > 0 && LPE <= 16) ? ANM_VAR_THREADS : ANM_
   const int T = (P.mode == ANM_MODE_STEP && P.T > 1) ? P.T : 1;
   for (int64_t base = (int64_t)blockIdx.x * GPB; base < P.B; base += (int64_t)gridDim.x * GPB) {
     const int64_t e = base + grp;
-    const bool have = e < P.B;
+    bool have_ = e < P.B;
+    /* the previous launch is done with the instance (or never will be: a time-out makes this group skip it) */
+    if (have_ && !seq_wait_for(P.seq + e, ord - 1u, P.watchdog, e, P.wd_limit_ns)) have_ = false;
+    have_ = __shfl_sync(mk<FULL>(gm), have_ ? 1 : 0, 0, LPE) != 0; /* one verdict per lane group */
+    const bool have = have_;
 #if ANM_DIAG
     const long long t_staged = clock64();
 #endif
     bool term_c = true;  /* carried: ANMEnv.terminated */
     uint32_t ep_c = 0;   /* carried: auto-reset counter */
     if (have) {
-      seq_wait_for(P.seq + e, ord - 1u, P.watchdog, e, P.wd_limit_ns); /* the previous launch is done with it */
       term_c = __ldcg(P.terminated + e) != 0;
       ep_c = __ldcg(P.episode + e);
 #pragma unroll 1

@@ -37,6 +37,8 @@ extern "C" {
 #define ANM_E_CUDA (-2)      /* CUDA runtime error (message has cudaGetErrorString)  */
 #define ANM_E_NOMEM (-3)
 #define ANM_E_UNSUPPORTED (-4)
+#define ANM_E_TIMEOUT (-5)   /* a launch-chaining wait timed out (anm_watchdog has the record); the handle is
+                                unusable from then on, the CUDA context is not affected                  */
 
 /* device types: column DEV_TYPE of the network dict (components/constants.py:1-19) */
 #define ANM_DEV_LOAD (-1)
@@ -211,6 +213,9 @@ int anm_reset_seeded(anm_handle h, const uint8_t* mask_dev_or_null, int32_t max_
 int64_t anm_rng_state_bytes(anm_handle h);
 int anm_get_rng(anm_handle h, void* out_dev, void* stream);
 int anm_set_rng(anm_handle h, const void* in_dev, void* stream);
+/* Test hook: make instance e look as if the last three launches had never finished with it (the next launch's wait
+ * for it times out: the recoverable error path of launch chaining).  Synchronises the device. */
+int anm_debug_stall_instance(anm_handle h, int64_t e);
 /* Test hook: pretend that k launches have already run on this handle (launch chaining: sets the 64-bit ticket
  * counter to k * grid and every instance's ordinal to (uint32) k).  Synchronises the device. */
 int anm_debug_set_launch_ordinal(anm_handle h, uint64_t k);
@@ -346,10 +351,10 @@ void* anm_host_stream(anm_handle h);
 /* Number of kernels this library has launched on behalf of `h` (for bench accounting). */
 int64_t anm_launch_count(anm_handle h);
 
-/* Diagnostic: a chained launch that waited for an instance longer than the previous launch can
- * possibly take (2 s + 2 ms per step and pass) records
- * [1, instance, ordinal waited for, ordinal seen, CTA, grid, thread, 0] here (host memory, readable
- * even after the CUDA context reported the launch failure) and traps; all zeros otherwise. */
+/* Diagnostic: a launch that waited for an instance longer than the launches before it can possibly take
+ * (2 s + 2 ms per step and pass of every launch since the last fully ordered one) records
+ * [1, instance, ordinal waited for, ordinal seen, CTA, grid, thread, 0] here (mapped host memory), skips the
+ * instance and ends normally; every later call on the handle then returns ANM_E_TIMEOUT.  All zeros otherwise. */
 int anm_watchdog(anm_handle h, uint32_t* out8);
 
 #ifdef __cplusplus

@@ -1182,11 +1182,63 @@ def test_chained_launch_may_wait_longer_than_the_watchdog_window():
     ev0.record()
     nb.rollout(acts, out=out)
     nb.rollout(acts, out=out, chained=True)
+    # transitive waits: two chained one-step launches behind the chained rollout -- the last one waits (through its
+    # predecessor) for BOTH rollouts, far beyond 2 s + 2 ms per step of its direct predecessor alone
+    o1 = nb.step(acts[0], None, chained=True)
+    o2 = nb.step(acts[1], None, chained=True)
     ev1.record()
     torch.cuda.synchronize()
     assert nb.watchdog()[0] == 0
-    assert ev0.elapsed_time(ev1) > 3000.0  # ~2.7 s per launch today: the second one waited beyond the 2 s window
-    assert float(out[0].abs().sum()) > 0.0
+    assert ev0.elapsed_time(ev1) > 3000.0  # ~2.7 s per launch today: the later ones waited beyond the 2 s window
+    assert float(out[0].abs().sum()) > 0.0 and float(o2[0].abs().sum()) > 0.0 and float(o1[0].abs().sum()) > 0.0
+
+
+_TIMEOUT_SCRIPT = r"""
+import os, sys
+import ctypes as C
+sys.path.insert(0, %(root)r)
+os.environ["ANM_WD_LIMIT_MS"] = "200"
+import numpy as np, torch
+from gym_anm_b200 import _capi
+from gym_anm_b200.anm6 import BatchedANM6Easy
+from gym_anm_b200.errors import NativeLibraryError
+env = BatchedANM6Easy(64, validate_actions=False)
+env.reset(seed=1)
+a = np.random.default_rng(0).uniform(env.spec.action_low, env.spec.action_high, size=(64, 6))
+env.step(a)
+torch.cuda.synchronize()
+lib = _capi.load_library()
+_capi.check(lib.anm_debug_stall_instance(env.native.h, 17), lib)
+obs, r, d, _, _ = env.step(a)          # the launch waits 0.2 s for instance 17, gives it up and ends normally
+torch.cuda.synchronize()                # no launch failure: the context is alive
+wd = env.native.watchdog()
+assert wd[0] == 1 and wd[1] == 17, wd
+try:
+    env.step(a)
+    raise SystemExit("the call after a time-out must fail")
+except NativeLibraryError as e:
+    assert "time-out" in str(e) and "rc=-5" in str(e), str(e)
+x = torch.arange(8, device="cuda").double().sum()   # other CUDA work goes on
+assert float(x) == 28.0
+env2 = BatchedANM6Easy(64, validate_actions=False)  # and so does a new handle
+env2.reset(seed=1)
+env2.step(a)
+torch.cuda.synchronize()
+print("TIMEOUT_PATH_OK")
+"""
+
+
+def test_chaining_timeout_is_recoverable_subprocess():
+    """The firing path of the launch-chaining watchdog: an instance whose previous launches 'never finished' makes
+    the next launch time out; the kernel records the event, skips the instance and ends normally (no trap: the CUDA
+    context survives), the next call on the handle fails with ANM_E_TIMEOUT, other handles and CUDA work go on."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", _TIMEOUT_SCRIPT % {"root": root}], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "TIMEOUT_PATH_OK" in res.stdout, (res.stdout[-1500:], res.stderr[-1500:])
 
 
 def test_chaining_off_same_results_subprocess():
