@@ -367,6 +367,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
 /* int(v % len) of ANM6Easy.next_vars (anm6_easy.py:56): v is an integer-valued counter in practice, for which
  * the integer remainder is exact and a dozen instructions; anything else takes fmod. */
 __device__ __forceinline__ int next_slot(double v, double len) {
+  /* the common case: the counter was inside [0, len) and has just been incremented -- one compare and a subtraction
+   * (exact), no integer division */
+  if (v >= 0.0 && v < len + len && v == floor(v) && len == floor(len) && len >= 1.0 && len < 1073741824.0)
+    return (int)(v >= len ? v - len : v);
   if (v >= 0.0 && v < 2147483648.0 && v == floor(v) && len == floor(len) && len >= 1.0 && len < 2147483648.0)
     return (int)v % (int)len;
   return (int)fmod_cold(v, len);

@@ -1,5 +1,5 @@
-"""Import the UNMODIFIED reference package from /root/reference (this container) or from the copy that
-oracle/build_ref.py staged under oracle/_ref/ (the GPU box, where /root/reference does not exist).
+"""Import the UNMODIFIED reference package from /root/reference (this container) or from the archive that
+oracle/build_ref.py staged under oracle/_ref/ (the GPU box, where /root/reference does not exist; zipimport).
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product imports this.  The GPU box has no
 /root/reference, so this loader is used (a) by oracle/gen_golden.py to generate the
@@ -11,14 +11,17 @@ import os
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_STAGED = os.path.join(_HERE, "_ref")  # written by oracle/build_ref.py (the unmodified package, git-ignored; GPU box)
+# written by oracle/build_ref.py: the unmodified package as one archive (git-ignored; what the GPU box has)
+_STAGED = os.path.join(_HERE, "_ref", "gym_anm_ref.zip")
 REFERENCE_ROOT = os.environ.get("ANM_REFERENCE_ROOT") or (
     "/root/reference" if os.path.isdir("/root/reference/gym_anm") else _STAGED)
 _SHIMS = os.path.join(_HERE, "shims")
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "gym_anm"))
+    """A source tree (this container) or the staged archive (zipimport)."""
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "gym_anm")) or (
+        REFERENCE_ROOT.endswith(".zip") and os.path.isfile(REFERENCE_ROOT))
 
 
 def _needs_shim(name):
