@@ -419,6 +419,11 @@ struct Cst {  // resolved pointers into the staged blob
  * stays exact (the reference's assertEqual tests, tests/simulator/test_devices.py:541-549).  `info` packs
  * s1 | s2 << 8 | need << 16, need = bit mask of the rows the candidate lies on: they must have a finite h and are
  * not tested against themselves. */
+/* bit mask of lane 0 of every LPE-lane group of a warp */
+template <int LPE>
+struct ANM_GROUP_LANE0 {
+  static constexpr unsigned mask = (LPE == 32) ? 1u : (LPE == 16) ? 0x00010001u : (LPE == 8) ? 0x01010101u : 0x11111111u;
+};
 template <int LPE, bool FULL>
 __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, const double* __restrict__ rb,
                                                 const double* __restrict__ rnh, const double* __restrict__ rhe,
@@ -497,6 +502,15 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
       best = take ? d : best;
       bx = take ? x[u] : bx;
       by = take ? y[u] : by;
+    }
+    /* Interior set-points (what a sensible policy sends most of the time): candidate 0 is the point itself (lane 0 of
+     * the first trip); if it is feasible its distance is exactly 0 and nothing can beat it -- the other trips are
+     * skipped when that holds for every lane group that runs this code together. */
+    if (c0 == 0 && ncand > U * LPE) {
+      const bool inside = (lane == 0) && (best == 0.0);
+      if (FULL ? ((__ballot_sync(ANM_FULL, inside) & ANM_GROUP_LANE0<LPE>::mask) == ANM_GROUP_LANE0<LPE>::mask)
+               : (__any_sync(gm, inside) != 0))
+        break;
     }
   }
   /* closest candidate of the group: min over the lanes, then the lowest lane that holds it (equal distances
