@@ -1017,7 +1017,11 @@ int anm_rollout(anm_handle h, int64_t T, const double* action, const double* nex
   return launch(h, p, (cudaStream_t)stream, (flags & ANM_STEP_CHAINED) ? ANM_LF_CHAINED : 0u);
 }
 
-int anm_seed(anm_handle h, uint64_t seed_first) { return anm_seed_async(h, seed_first, nullptr); }
+int anm_seed(anm_handle h, uint64_t seed_first) { /* the blocking form: the streams are seeded when it returns */
+  if (int rc = anm_seed_async(h, seed_first, nullptr)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(nullptr));
+  return ANM_OK;
+}
 
 int anm_seed_async(anm_handle h, uint64_t seed_first, void* stream) {
   if (!h) return fail(ANM_E_INVALID, "null handle");
@@ -1283,12 +1287,15 @@ int anm_step_packed(anm_handle h, const double* action, const double* next_vars,
     auto& g = h->g;
     p.g_peers = g.d_peers; p.g_flags = g.d_flags; p.g_state = g.d_state;
     p.g_rows = g.rows; p.g_row0 = g.row0; p.g_world = g.world; p.g_rank = g.rank; p.g_slots = g.slots;
-    g.last_waited_inline = gather > 1;
-    ++g.steps_host;
   }
   /* never chained: the gather slot is derived from the completed-step count at kernel entry; remote stores need the
    * system-scope fence */
-  return launch(h, p, (cudaStream_t)stream, gather ? (ANM_LF_SYSOUT | (gather > 1 ? ANM_LF_GATHER_WAIT : 0u)) : 0u);
+  const int rc = launch(h, p, (cudaStream_t)stream, gather ? (ANM_LF_SYSOUT | (gather > 1 ? ANM_LF_GATHER_WAIT : 0u)) : 0u);
+  if (rc == ANM_OK && gather) {
+    h->g.last_waited_inline = gather > 1;
+    ++h->g.steps_host;
+  }
+  return rc;
 }
 
 int anm_gather_wait(anm_handle h, double** rows_out, void* stream) {

@@ -204,7 +204,7 @@ int anm_set_reset_full_state(anm_handle h, double* full_state_dev_or_null);
  * then consumes the integers(1, 365) of ANM6.reset (anm6.py:138).  converged[b] = 0 for a selected
  * instance that found no convergent state.  Bit-identical to the host-drawn path (anm_reset with s0
  * from NumPy) for the same seeds. */
-int anm_seed(anm_handle h, uint64_t seed_first);                       /* on the legacy default stream */
+int anm_seed(anm_handle h, uint64_t seed_first);                       /* blocking: seeded when it returns */
 int anm_seed_async(anm_handle h, uint64_t seed_first, void* stream);   /* SeedSequence expansion on the device, no sync */
 int anm_reset_seeded(anm_handle h, const uint8_t* mask_dev_or_null, int32_t max_tries, int32_t date_draw,
                      double* obs_dev, double* state_dev_or_null, uint8_t* converged_dev, void* stream);
