@@ -196,8 +196,6 @@ class ANM6Easy(EnvBase):
     def render_message(self):
         """The per-frame payload of the reference's renderer (anm6.py:101-111), from instance 0's full state."""
         full_state = self.simulator.state
-        if full_state is None:  # after a terminal step the reference keeps showing the last electrical state
-            full_state = self.simulator.state_dict(0, full=self._b._full)
         return dict(
             dev_p=list(full_state["dev_p"]["MW"].values()), dev_q=list(full_state["dev_q"]["MVAr"].values()),
             branch_s=list(full_state["branch_s"]["MVA"].values()), des_soc=list(full_state["des_soc"]["MWh"].values()),

@@ -239,6 +239,8 @@ class BatchedANMEnv(EnvBase):
              "host_rng": None if self._rngs is None else [r.bit_generator.state for r in self._rngs]}  # fmt: skip
         if getattr(self, "_device_seeded", False):
             d["device_rng"] = self.native.get_rng()
+        if self.track_full_state:
+            d["full_state"] = self._full.clone()
         return d
 
     def load_state_dict(self, d):
@@ -256,3 +258,5 @@ class BatchedANMEnv(EnvBase):
         if d.get("device_rng") is not None:
             self.native.set_rng(d["device_rng"])
             self._device_seeded = True
+        if self.track_full_state and d.get("full_state") is not None:
+            self._full.copy_(d["full_state"])

@@ -57,9 +57,7 @@ class BatchedSimulator:
         dict the reference's renderer (anm6.py:101-109) and MPC agents (mpc.py:419, mpc_constant.py:23-29) read.
         Follows the environment's resets / steps when it was built with `track_full_state=True`, else the last
         `transition()` call."""
-        if self._env is not None:
-            if bool(self._env._term_u8[self.env_index]):
-                return None  # anm_env.py:446-448: no valid electrical state after a terminal step
+        if self._env is not None:  # after a terminal step every entry is 0 (the kernel zeroes the row, anm_env.py:446-448)
             return self.state_dict(self.env_index, full=self._env._full)
         if self._last_full is None:
             raise AttributeError("no state yet: call transition() or build the environment with track_full_state=True")
