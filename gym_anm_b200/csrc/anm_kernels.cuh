@@ -444,6 +444,9 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
     nh[k] = rnh[k];
   }
   double best = CUDART_INF, bx = CUDART_NAN, by = CUDART_NAN;
+  /* The early-out below votes across the warp, so whether it runs must not depend on the lane group: an idle group's
+   * candidate count is computed from stale workspace contents and may differ from its warp-mates'. */
+  const int ncand_vote = FULL ? __reduce_max_sync(ANM_FULL, ncand) : ncand;
   /* a compact loop on purpose (the body stays in the instruction cache); every lane makes the same trips.
    * Written stage by stage over independent values so that the FMA pipe is kept full. */
 #pragma unroll 1
@@ -506,7 +509,7 @@ __device__ __forceinline__ void project_polygon(const double* __restrict__ ra, c
     /* Interior set-points (what a sensible policy sends most of the time): candidate 0 is the point itself (lane 0 of
      * the first trip); if it is feasible its distance is exactly 0 and nothing can beat it -- the other trips are
      * skipped when that holds for every lane group that runs this code together. */
-    if (c0 == 0 && ncand > U * LPE) {
+    if (c0 == 0 && ncand_vote > U * LPE) {
       const bool inside = (lane == 0) && (best == 0.0);
       if (FULL ? ((__ballot_sync(ANM_FULL, inside) & ANM_GROUP_LANE0<LPE>::mask) == ANM_GROUP_LANE0<LPE>::mask)
                : (__any_sync(gm, inside) != 0))
