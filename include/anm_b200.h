@@ -157,7 +157,7 @@ typedef struct anm_step_extras {
                                      partial-pivoting fallback, iterations with |theta| > 1e5,
                                      SM cycles/16 spent in the Newton loop, SM cycles of the pass.
                                      Only written by diagnostic builds (-DANM_DIAG=1, tools/).   */
-  uint32_t flags;                 /* ANM_STEP_* (ABI 2)                                              */
+  uint32_t flags;                 /* ANM_STEP_* (ABI >= 2)                                            */
   uint32_t reserved;
 } anm_step_extras;
 

@@ -339,3 +339,35 @@ print("REGISTERED_OK")
 """ % ROOT
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "REGISTERED_OK" in res.stdout, res.stderr[-2000:]
+
+
+def test_reference_arm_line_and_staged_reference(tmp_path):
+    """`bench.py --impl reference` (runs on host cores only): one JSON line with the contract's keys, timed on the
+    reference's own ANM6Easy (kind "reference").  And the archive that oracle/build_ref.py stages for the GPU box holds
+    the reference's .py files byte for byte (the reference is imported from it there, unmodified)."""
+    import json
+    import zipfile
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    import ref_loader
+
+    if not os.path.isdir("/root/reference/gym_anm"):
+        pytest.skip("reference tree not present (GPU box)")
+    z = build_ref.build()
+    with zipfile.ZipFile(z) as zf:
+        names = [n for n in zf.namelist() if n.endswith(".py")]
+        assert len(names) >= 25 and "gym_anm/simulator/solve_load_flow.py" in names
+        for n in names:
+            assert zf.read(n) == open(os.path.join("/root/reference", n), "rb").read(), n
+    assert ref_loader.reference_available()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "20", "--warmup", "5",
+                          "--cpu-steps", "50"], capture_output=True, text=True, timeout=600)  # fmt: skip
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
+    assert d["steps"] == 20 and d["warmup"] == 5 and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
