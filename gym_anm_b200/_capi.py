@@ -152,6 +152,20 @@ _PROTOS = {
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 
+# include/anm_lp.h: the batched LP solver behind the MPC action source (same shared library)
+_LP_PROTOS = {
+    "anm_lp_last_error": (C.c_char_p, []),
+    "anm_lp_create": (C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int32, C.c_int,
+                                C.POINTER(C.c_void_p)]),
+    "anm_lp_destroy": (C.c_int, [C.c_void_p]),
+    "anm_lp_solve": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "anm_lp_bytes": (C.c_int64, [C.c_void_p]),
+    "anm_debug_lp_state_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int64]),
+    "anm_debug_lp_solve_host": (C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int32,
+                                          C.c_void_p, C.c_int32] + [C.c_void_p] * 7),
+}
+LP_EXPORTED_SYMBOLS = tuple(_LP_PROTOS)
+
 
 def load_library(path=None):
     """Load libanm_b200.so (fails loudly: there is no CPU fallback)."""
@@ -168,13 +182,20 @@ def load_library(path=None):
         lib = C.CDLL(path)
     except OSError as e:  # e.g. libcudart not found
         raise NativeLibraryError("cannot load %s: %s" % (path, e)) from e
-    for name, (res, args) in _PROTOS.items():
+    for name, (res, args) in list(_PROTOS.items()) + list(_LP_PROTOS.items()):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
     if lib.anm_abi_version() != 3:
         raise NativeLibraryError("ABI version mismatch in %s" % path)
     _LIB = lib
     return lib
+
+
+def check_lp(rc, lib=None):
+    if rc != 0:
+        lib = lib or load_library()
+        msg = lib.anm_lp_last_error()
+        raise NativeLibraryError("anm_lp call failed (rc=%d): %s" % (rc, msg.decode() if msg else "?"))
 
 
 def check(rc, lib=None):
