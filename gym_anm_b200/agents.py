@@ -3,10 +3,13 @@
 `MPCAgentConstant` / `MPCAgentPerfect` mirror reference gym_anm/agents/mpc.py, mpc_constant.py,
 mpc_perfect.py: an N-stage DC optimal power flow over [t+1, t+N] whose first-stage set-points
 become the action.  The reference states the program with CVXPY (not installable here); it is a
-linear program, restated below in standard form and solved with SciPy's HiGHS (`linprog`), one
-LP per environment instance on the host.  LP optima are not unique, so this is NOT bit-parity
-material: the tests check the DC-OPF constraints the reference's own test checks
-(tests/test_dcopf_agent.py) and feed the same action tensor to the GPU path and the oracle.
+linear program, restated below in standard form.  Two solvers: SciPy's HiGHS (`linprog`), one LP per
+environment instance on the host (optionally over a worker-process pool), and -- `device=` -- the batched
+bounded dual simplex of include/anm_lp.h on the GPU (gym_anm_b200/lp.py: the programs of a batch share the
+constraint matrix, every instance keeps its tableau in HBM and is warm-started from its previous basis; the
+state never leaves the device).  LP optima are not unique, so this is NOT bit-parity material: the tests
+check the DC-OPF constraints the reference's own test checks (tests/test_dcopf_agent.py), compare the
+objective values of the two solvers, and feed the same action tensor to the GPU path and the oracle.
 
 Per stage i (variables in p.u.): bus angles theta[n_bus], device injections P[n_dev], per storage
 unit (p_ch, p_dis) >= 0, per branch an epigraph variable z >= max(0, |B_kl (theta_k - theta_l)| -
@@ -38,10 +41,16 @@ class MPCAgent:
     (mpc.py:32-50): simulator (any object with the Simulator attributes: `BatchedSimulator` works),
     action_space, gamma, safety_margin, planning_steps."""
 
-    def __init__(self, simulator, action_space, gamma, safety_margin=0.9, planning_steps=1, workers=0):
+    def __init__(self, simulator, action_space, gamma, safety_margin=0.9, planning_steps=1, workers=0, device=None,
+                 refresh=64):
         """`workers` > 0: the LPs of a batch are solved by that many worker processes (one HiGHS LP per instance and
-        step stays the unit of work; BASELINE config 5 drives 16 384 instances with it).  0: in this process."""
+        step stays the unit of work).  0: in this process.
+        `device` (e.g. "cuda:0"): `act(env)` on a batched environment whose state lives on that device solves the
+        whole batch with the GPU solver and returns the actions as a CUDA tensor (`act_device`); every instance's
+        basis is dropped and rebuilt every `refresh` solves (drift insurance for the warm-started tableaux)."""
         self.workers, self._pool = int(workers), None
+        self.device, self.refresh, self._dev = device, int(refresh), None
+        self.lp_stats = {"solves": 0, "second_solves": 0, "host_fallbacks": 0}
         self.safety_margin, self.gamma, self.planning_steps = safety_margin, gamma, planning_steps
         self.action_space = action_space
         self.baseMVA, self.lamb, self.delta_t = simulator.baseMVA, simulator.lamb, simulator.delta_t
@@ -194,6 +203,8 @@ class MPCAgent:
         """Actions for every instance of a (batched or single) environment: ndarray [num_envs, A]
         (a single reference-shaped env gives shape [A])."""
         st = env.state
+        if self.device is not None and hasattr(st, "is_cuda") and st.is_cuda and st.ndim == 2:
+            return self.act_device(env)
         st = st.detach().cpu().numpy() if hasattr(st, "detach") else np.asarray(st)
         single = st.ndim == 1
         p_load, p_gen_max, soc = self.state_to_pu(st)
@@ -224,10 +235,112 @@ class MPCAgent:
         if self._pool is not None:
             self._pool.shutdown()
             self._pool = None
+        if self._dev is not None:
+            self._dev.lp.close()
+            self._dev = None
+
+    # ---- the batch on the GPU (include/anm_lp.h) -----------------------------------------------------------
+    def forecast_batch_device(self, env, state, p_load, p_gen_max):
+        """Torch version of `forecast_batch`: [B, n_load, N], [B, n_gen, N] CUDA tensors."""
+        raise NotImplementedError
+
+    def act_device(self, env):
+        """Actions [B, A] (CUDA tensor, MW / MVAr) for a batched environment whose state tensor is on the device: new
+        bounds -> one warm-started solve of every instance's program -> first-stage set-points.  Every solution is
+        checked on the device (status, bound violations recomputed from the constraint matrix, the angle box
+        |theta| <= pi of mpc.py:298, the added big-M boxes); an instance that fails is solved again from scratch, and
+        handed to the host LP if that fails too (one host look per step: the number of such instances)."""
+        import torch
+
+        from . import lp as _lp
+
+        st = env.state
+        B = st.shape[0]
+        if self._dev is None or self._dev.B != B:
+            self._dev = _DeviceProgram(self, B, st.device)
+        dv = self._dev
+        m = self.baseMVA
+        p_load, soc, p_gen_max = st[:, dv.load_cols] / m, st[:, dv.soc_cols] / m, st[:, dv.gen_cols] / m
+        Lf, Gf = self.forecast_batch_device(env, st, p_load, p_gen_max)
+        N, n = self.planning_steps, dv.red.n
+        lp = dv.lp
+        lf = Lf.reshape(B, -1).t()
+        lp.lo[dv.col_load, :B] = lf
+        lp.up[dv.col_load, :B] = lf
+        lp.up[dv.col_gen, :B] = torch.maximum(dv.gmin, torch.minimum(dv.gmax, Gf.reshape(B, -1).t()))
+        lp.lo[dv.row_soc, :B] = (dv.soc_min - soc).repeat_interleave(N, dim=1).t()
+        lp.up[dv.row_soc, :B] = (dv.soc_max - soc).repeat_interleave(N, dim=1).t()
+        restart = dv.all_restart if (self.refresh > 0 and lp.solves > 0 and lp.solves % self.refresh == 0) else None
+        lp.solve(restart)
+        self.lp_stats["solves"] += 1
+        bad = dv.failed()
+        n_bad = int(bad.sum())  # the step's one host look
+        if n_bad:
+            lp.solve(bad.to(torch.uint8))
+            self.lp_stats["second_solves"] += 1
+            bad = dv.failed()
+            n_bad = int(bad.sum())
+        x = lp.x[:, :B]
+        P_gen = x[dv.act_gen].t() * m
+        P_des = (dv.act_des @ x).t() * m
+        a = torch.cat([P_gen, torch.zeros_like(P_gen), P_des, torch.zeros_like(P_des)], dim=1)
+        a = torch.minimum(torch.maximum(a, dv.a_lo), dv.a_hi)
+        if n_bad:  # rare: the host LP on the full program (angles included)
+            idx = torch.nonzero(bad).flatten()
+            Lh, Gh, sh = Lf[idx].cpu().numpy(), Gf[idx].cpu().numpy(), soc[idx].cpu().numpy()
+            rows = np.stack([self.solve_one(Lh[k], Gh[k], sh[k])[0] for k in range(len(idx))])
+            a[idx] = torch.as_tensor(rows, device=a.device)
+            self.lp_stats["host_fallbacks"] += len(idx)
+        return a.contiguous()
+
+
+class _DeviceProgram:
+    """Device-side constants of one agent's reduced program for a batch of B instances (lp.reduce_dcopf)."""
+
+    def __init__(self, agent, B, device):
+        import torch
+
+        from . import lp as _lp
+
+        self.B = B
+        self.red = red = _lp.reduce_dcopf(agent)
+        self.lp = lp = _lp.BatchedLP(red.A, red.c, B, device)
+        t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)  # noqa: E731
+        lp.lo[:] = t(red.lo)[:, None]
+        lp.up[:] = t(red.up)[:, None]
+        D, n, N = agent.n_dev, red.n, agent.planning_steps
+        self.load_cols = t([agent.dev_pos[d] for d in agent.load_ids], torch.long)
+        self.soc_cols = t(np.arange(2 * D, 2 * D + agent.n_des), torch.long)
+        self.gen_cols = t(np.arange(2 * D + agent.n_des, 2 * D + agent.n_des + agent.n_gen), torch.long)
+        self.col_load, self.col_gen = t(red.col_load.ravel(), torch.long), t(red.col_gen.ravel(), torch.long)
+        self.row_soc = t(n + red.row_soc.ravel(), torch.long)
+        self.gmin, self.gmax = t(np.repeat(agent.P_gen_min, N))[:, None], t(np.repeat(agent.P_gen_max, N))[:, None]
+        lp.lo[self.col_gen] = self.gmin
+        self.soc_min, self.soc_max = t(agent.soc_min)[None, :], t(agent.soc_max)[None, :]
+        self.theta_map, self.free_cols = t(red.theta_map), t(red.free_cols, torch.long)
+        self.act_gen = t(red.col_gen[:, 0], torch.long)
+        self.act_des = t(red.A[red.row_pdes[:, 0]])
+        self.a_lo, self.a_hi = t(agent.action_space.low)[None, :], t(agent.action_space.high)[None, :]
+        self.all_restart = torch.ones(B, dtype=torch.uint8, device=device)
+        self.big = _lp.BIG
+
+    def failed(self):
+        """[B] bool: instances whose solution of the last solve cannot be used as it is."""
+        lp, B = self.lp, self.B
+        x = lp.x[:, :B]
+        bad = (lp.status != 0) | (lp.violation() > 1e-7)
+        bad |= (self.theta_map @ x).abs().amax(dim=0) > np.pi + 1e-9
+        if self.free_cols.numel():
+            bad |= x[self.free_cols].abs().amax(dim=0) > 0.5 * self.big
+        return bad
 
 
 class MPCAgentConstant(MPCAgent):
     """Constant forecasts over the horizon (reference mpc_constant.py:21-35)."""
+
+    def forecast_batch_device(self, env, state, p_load, p_gen_max):
+        N = self.planning_steps
+        return p_load[:, :, None].expand(-1, -1, N), p_gen_max[:, :, None].expand(-1, -1, N)
 
     def forecast_batch(self, env, p_load, p_gen_max):
         N = self.planning_steps
@@ -237,6 +350,17 @@ class MPCAgentConstant(MPCAgent):
 class MPCAgentPerfect(MPCAgent):
     """Perfect forecasts from the environment's fixed daily profiles (reference mpc_perfect.py:21-37);
     needs `env.P_loads`, `env.P_maxs` (ANM6Easy) and the aux time index in the last state entry."""
+
+    def forecast_batch_device(self, env, state, p_load, p_gen_max):
+        import torch
+
+        if getattr(self, "_tables", None) is None or self._tables[0].device != state.device:
+            self._tables = tuple(torch.as_tensor(np.asarray(a, dtype=np.float64), device=state.device) / self.baseMVA
+                                 for a in (env.P_loads, env.P_maxs))
+        PL, PM = self._tables
+        T, N = PL.shape[1], self.planning_steps
+        idx = (state[:, -1].long()[:, None] + 1 + torch.arange(N, device=state.device)[None, :]) % T
+        return PL[:, idx].permute(1, 0, 2), PM[:, idx].permute(1, 0, 2)
 
     def forecast_batch(self, env, p_load, p_gen_max):
         st = env.state

@@ -27,7 +27,7 @@ int lp_fail(int code, const char* fmt, ...) {
 
 // byte offsets of the per-batch arrays inside one allocation (device handle and host test state alike)
 struct Layout {
-  int64_t T, d, xB, rval, bid, nid, ridx, atup, total;
+  int64_t T, d, xB, rval, bl, bu, nl, nu, bid, nid, ridx, atup, total;
 };
 
 Layout layout_of(int64_t n, int64_t m, int64_t stride) {
@@ -42,6 +42,10 @@ Layout layout_of(int64_t n, int64_t m, int64_t stride) {
   L.d = take(n, 8);
   L.xB = take(m, 8);
   L.rval = take(n, 8);
+  L.bl = take(m, 8);
+  L.bu = take(m, 8);
+  L.nl = take(n, 8);
+  L.nu = take(n, 8);
   L.bid = take(m, 4);
   L.nid = take(n, 4);
   L.ridx = take(n, 4);
@@ -55,6 +59,10 @@ void bind(anm_lp::Batch& b, char* base, const Layout& L) {
   b.d = reinterpret_cast<double*>(base + L.d);
   b.xB = reinterpret_cast<double*>(base + L.xB);
   b.rval = reinterpret_cast<double*>(base + L.rval);
+  b.bl = reinterpret_cast<double*>(base + L.bl);
+  b.bu = reinterpret_cast<double*>(base + L.bu);
+  b.nl = reinterpret_cast<double*>(base + L.nl);
+  b.nu = reinterpret_cast<double*>(base + L.nu);
   b.bid = reinterpret_cast<int32_t*>(base + L.bid);
   b.nid = reinterpret_cast<int32_t*>(base + L.nid);
   b.ridx = reinterpret_cast<int32_t*>(base + L.ridx);

@@ -51,6 +51,10 @@ struct Batch {
   double* xB;       // [m, stride]  scratch: values of the basic variables
   double* rval;     // [n, stride]  scratch: non-zeros of the pivot row
   int32_t* ridx;    // [n, stride]
+  double* bl;       // [m, stride]  scratch: bounds of the basic variables, in row order (gathered per solve, swapped
+  double* bu;       // [m, stride]           with the column's on a pivot: no lo[bid[i]] indirection in the loops)
+  double* nl;       // [n, stride]  scratch: bounds of the non-basic variables, in column order
+  double* nu;       // [n, stride]
 };
 
 LP_HD inline bool is_inf(double v) { return v > 0.5 * kInf || v < -0.5 * kInf; }
@@ -65,13 +69,12 @@ LP_HD inline double nonbasic_value(double l, double u, bool up) {
 
 // Bound flags follow the sign of the reduced costs (boxed variables: always possible).  Returns false when a
 // column's cost pulls towards an infinite bound.
-LP_HD inline bool restore_dual_feasibility(const Batch& b, int64_t e, const double* lo, const double* up, bool* changed) {
+LP_HD inline bool restore_dual_feasibility(const Batch& b, int64_t e, bool* changed) {
   const int64_t S = b.stride;
   bool ok = true;
   *changed = false;
   for (int j = 0; j < b.n; ++j) {
-    const int v = LP_AT(b.nid, j);
-    const double l = LP_AT(lo, v), u = LP_AT(up, v);
+    const double l = LP_AT(b.nl, j), u = LP_AT(b.nu, j);
     if (!(l < u)) continue;  // fixed
     const double dj = LP_AT(b.d, j);
     uint8_t want = LP_AT(b.atup, j);
@@ -93,23 +96,38 @@ LP_HD inline bool restore_dual_feasibility(const Batch& b, int64_t e, const doub
   return ok;
 }
 
-LP_HD inline void compute_basic_values(const Batch& b, int64_t e, const double* lo, const double* up) {
+LP_HD inline void compute_basic_values(const Batch& b, int64_t e) {
   const int64_t S = b.stride;
   const int n = b.n, m = b.m;
-  for (int j = 0; j < n; ++j) {  // rval doubles as the vector of non-basic values here
-    const int v = LP_AT(b.nid, j);
-    LP_AT(b.rval, j) = nonbasic_value(LP_AT(lo, v), LP_AT(up, v), LP_AT(b.atup, j) != 0);
-  }
+  for (int j = 0; j < n; ++j)  // rval doubles as the vector of non-basic values here
+    LP_AT(b.rval, j) = nonbasic_value(LP_AT(b.nl, j), LP_AT(b.nu, j), LP_AT(b.atup, j) != 0);
   for (int i = 0; i < m; ++i) {
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four independent chains: loads in flight, not FMA latency
     const double* Ti = b.T + (int64_t)i * n * S + e;
     int j = 0;
-    for (; j + 1 < n; j += 2) {
+    for (; j + 3 < n; j += 4) {
       s0 = fma(Ti[(int64_t)j * S], LP_AT(b.rval, j), s0);
       s1 = fma(Ti[(int64_t)(j + 1) * S], LP_AT(b.rval, j + 1), s1);
+      s2 = fma(Ti[(int64_t)(j + 2) * S], LP_AT(b.rval, j + 2), s2);
+      s3 = fma(Ti[(int64_t)(j + 3) * S], LP_AT(b.rval, j + 3), s3);
     }
-    if (j < n) s0 = fma(Ti[(int64_t)j * S], LP_AT(b.rval, j), s0);
-    LP_AT(b.xB, i) = s0 + s1;
+    for (; j < n; ++j) s0 = fma(Ti[(int64_t)j * S], LP_AT(b.rval, j), s0);
+    LP_AT(b.xB, i) = (s0 + s1) + (s2 + s3);
+  }
+}
+
+// lo / up ([variable, stride]) gathered into row order (basic) and column order (non-basic)
+LP_HD inline void gather_bounds(const Batch& b, int64_t e, const double* lo, const double* up) {
+  const int64_t S = b.stride;
+  for (int i = 0; i < b.m; ++i) {
+    const int v = LP_AT(b.bid, i);
+    LP_AT(b.bl, i) = LP_AT(lo, v);
+    LP_AT(b.bu, i) = LP_AT(up, v);
+  }
+  for (int j = 0; j < b.n; ++j) {
+    const int v = LP_AT(b.nid, j);
+    LP_AT(b.nl, j) = LP_AT(lo, v);
+    LP_AT(b.nu, j) = LP_AT(up, v);
   }
 }
 
@@ -118,37 +136,46 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
                            double* obj, int32_t* iters) {
   const int64_t S = b.stride;
   const int n = b.n, m = b.m;
-  if (restart) {
-    for (int i = 0; i < m; ++i) {
-      LP_AT(b.bid, i) = n + i;
-      for (int j = 0; j < n; ++j) LP_AT(b.T, i * n + j) = b.A[i * n + j];
-    }
-    for (int j = 0; j < n; ++j) {
-      LP_AT(b.d, j) = b.c[j];
-      LP_AT(b.nid, j) = j;
-      LP_AT(b.atup, j) = 0;
-    }
-  }
   int status = ANM_LP_OPTIMAL, it = 0;
   bool changed;
-  if (!restore_dual_feasibility(b, e, lo, up, &changed)) status = ANM_LP_DUAL_INFEASIBLE;
-  compute_basic_values(b, e, lo, up);
-  bool verified = false;  // x_B recomputed from T since the last pivot and the bound flags agree with d
+  for (int attempt = 0;; ++attempt) {
+    if (restart) {
+      for (int i = 0; i < m; ++i) {
+        LP_AT(b.bid, i) = n + i;
+        for (int j = 0; j < n; ++j) LP_AT(b.T, i * n + j) = b.A[i * n + j];
+      }
+      for (int j = 0; j < n; ++j) {
+        LP_AT(b.d, j) = b.c[j];
+        LP_AT(b.nid, j) = j;
+        LP_AT(b.atup, j) = 0;
+      }
+    }
+    gather_bounds(b, e, lo, up);
+    if (restore_dual_feasibility(b, e, &changed)) break;
+    // A kept basis can lose its dual feasibility when a bound that a non-basic variable sits at has become
+    // infinite since the last solve: start again from the all-slack basis (only columns are non-basic there).
+    if (restart || attempt > 0) {
+      status = ANM_LP_DUAL_INFEASIBLE;
+      break;
+    }
+    restart = true;
+  }
+  compute_basic_values(b, e);
+  bool verified = true;  // x_B recomputed from T since the last pivot and the bound flags agree with d
   while (status == ANM_LP_OPTIMAL) {
     // ---- leaving row: largest scaled bound violation
     int r = -1;
     double worst = 0.0, target = 0.0, sgn = 0.0;
     for (int i = 0; i < m; ++i) {
-      const int v = LP_AT(b.bid, i);
-      const double xi = LP_AT(b.xB, i), l = LP_AT(lo, v), u = LP_AT(up, v);
+      const double xi = LP_AT(b.xB, i), l = LP_AT(b.bl, i), u = LP_AT(b.bu, i);
       const double below = (l - xi) / (1.0 + fabs(l)), above = (xi - u) / (1.0 + fabs(u));
       if (below > kFeasTol && below > worst) worst = below, r = i, target = l, sgn = 1.0;
       if (above > kFeasTol && above > worst) worst = above, r = i, target = u, sgn = -1.0;
     }
     if (r < 0) {
       if (verified) break;
-      restore_dual_feasibility(b, e, lo, up, &changed);
-      compute_basic_values(b, e, lo, up);
+      restore_dual_feasibility(b, e, &changed);
+      compute_basic_values(b, e);
       verified = true;
       continue;
     }
@@ -174,8 +201,7 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
     double tmax = kInf;
     for (int k = 0; k < nnz; ++k) {
       const int j = LP_AT(b.ridx, k);
-      const int v = LP_AT(b.nid, j);
-      const double l = LP_AT(lo, v), u = LP_AT(up, v);
+      const double l = LP_AT(b.nl, j), u = LP_AT(b.nu, j);
       if (!(l < u)) continue;
       const double as = sgn * LP_AT(b.rval, k);
       const bool atu = LP_AT(b.atup, j) != 0, fr = is_inf(l) && is_inf(u);
@@ -190,8 +216,7 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
     double best = 0.0;
     for (int k = 0; k < nnz; ++k) {
       const int j = LP_AT(b.ridx, k);
-      const int v = LP_AT(b.nid, j);
-      const double l = LP_AT(lo, v), u = LP_AT(up, v);
+      const double l = LP_AT(b.nl, j), u = LP_AT(b.nu, j);
       if (!(l < u)) continue;
       const double a = LP_AT(b.rval, k), as = sgn * a;
       const bool atu = LP_AT(b.atup, j) != 0, fr = is_inf(l) && is_inf(u);
@@ -202,7 +227,8 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
     const double p = LP_AT(b.rval, kq), inv_p = 1.0 / p;
     const double delta = (target - LP_AT(b.xB, r)) * inv_p;  // change of the entering variable
     const int ev = LP_AT(b.nid, q), lv = LP_AT(b.bid, r);
-    const double x_enter = nonbasic_value(LP_AT(lo, ev), LP_AT(up, ev), LP_AT(b.atup, q) != 0) + delta;
+    const double el = LP_AT(b.nl, q), eu = LP_AT(b.nu, q);
+    const double x_enter = nonbasic_value(el, eu, LP_AT(b.atup, q) != 0) + delta;
     // ---- pivot: the other rows
     for (int i = 0; i < m; ++i) {
       if (i == r) continue;
@@ -226,8 +252,7 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
       const double a = LP_AT(b.rval, k);
       Trw[(int64_t)j * S] = -a * inv_p;
       double dj = fma(-fd, a, LP_AT(b.d, j));
-      const int v = LP_AT(b.nid, j);
-      if (LP_AT(lo, v) < LP_AT(up, v)) {  // Harris: a sign lost within the tolerance is a zero
+      if (LP_AT(b.nl, j) < LP_AT(b.nu, j)) {  // Harris: a sign lost within the tolerance is a zero
         const bool atu = LP_AT(b.atup, j) != 0;
         if ((!atu && dj < 0.0 && dj > -16.0 * kDualTol) || (atu && dj > 0.0 && dj < 16.0 * kDualTol)) dj = 0.0;
       }
@@ -237,6 +262,8 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
     LP_AT(b.d, q) = fd;
     LP_AT(b.bid, r) = ev;
     LP_AT(b.nid, q) = lv;
+    LP_AT(b.nl, q) = LP_AT(b.bl, r), LP_AT(b.nu, q) = LP_AT(b.bu, r);
+    LP_AT(b.bl, r) = el, LP_AT(b.bu, r) = eu;
     LP_AT(b.atup, q) = sgn < 0.0 ? 1 : 0;
     LP_AT(b.xB, r) = x_enter;
     ++it;
@@ -244,7 +271,7 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
   // ---- the columns' values and the objective (original costs)
   for (int j = 0; j < n; ++j) {
     const int v = LP_AT(b.nid, j);
-    if (v < n) LP_AT(x, v) = nonbasic_value(LP_AT(lo, v), LP_AT(up, v), LP_AT(b.atup, j) != 0);
+    if (v < n) LP_AT(x, v) = nonbasic_value(LP_AT(b.nl, j), LP_AT(b.nu, j), LP_AT(b.atup, j) != 0);
   }
   for (int i = 0; i < m; ++i) {
     const int v = LP_AT(b.bid, i);

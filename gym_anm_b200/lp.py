@@ -138,21 +138,14 @@ class BatchedLP:
     def __init__(self, A, c, batch, device, max_iter=0):
         import torch
 
-        if not torch.cuda.is_available():
-            raise NativeLibraryError("a CUDA device is required (the batched LP solver has no CPU fallback)")
         self.lib = _capi.load_library()
         self.device = torch.device(device)
-        if self.device.index is None:
-            self.device = torch.device("cuda", torch.cuda.current_device())
-        A, c = np.ascontiguousarray(A, np.float64), np.ascontiguousarray(c, np.float64)
-        self.m, self.n = A.shape
-        self.B = int(batch)
+        self.A_host, self.c_host = np.ascontiguousarray(A, np.float64), np.ascontiguousarray(c, np.float64)
+        self.m, self.n = self.A_host.shape
+        self.B, self.max_iter = int(batch), int(max_iter)
         self.stride = (self.B + 31) // 32 * 32
-        h = C.c_void_p()
-        _capi.check_lp(self.lib.anm_lp_create(self.n, self.m, A.ctypes.data_as(_capi.c_double_p),
-                                              c.ctypes.data_as(_capi.c_double_p), self.B, self.stride, int(max_iter),
-                                              int(self.device.index), C.byref(h)), self.lib)
-        self.h = h
+        self.h = None
+        self._create()
         kw = dict(device=self.device)
         self.lo = torch.zeros((self.n + self.m, self.stride), dtype=torch.float64, **kw)
         self.up = torch.zeros((self.n + self.m, self.stride), dtype=torch.float64, **kw)
@@ -160,21 +153,37 @@ class BatchedLP:
         self.obj = torch.zeros(self.B, dtype=torch.float64, **kw)
         self.status = torch.zeros(self.B, dtype=torch.int32, **kw)
         self.iters = torch.zeros(self.B, dtype=torch.int32, **kw)
-        self.A_dev = torch.as_tensor(A, **kw)
+        self.A_dev = torch.as_tensor(self.A_host, **kw)
         self.solves = 0
+
+    def _create(self):
+        import torch
+
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise NativeLibraryError("a CUDA device is required (the batched LP solver has no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        h = C.c_void_p()
+        _capi.check_lp(self.lib.anm_lp_create(self.n, self.m, self.A_host.ctypes.data_as(_capi.c_double_p),
+                                              self.c_host.ctypes.data_as(_capi.c_double_p), self.B, self.stride,
+                                              self.max_iter, int(self.device.index), C.byref(h)), self.lib)
+        self.h = h
 
     @property
     def bytes(self):
         return int(self.lib.anm_lp_bytes(self.h))
 
-    def solve(self, restart=None):
-        """Enqueue one solve on the current stream.  `restart`: optional [B] uint8 tensor (non-zero = cold start)."""
+    def _launch(self, restart):
         import torch
 
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         _capi.check_lp(self.lib.anm_lp_solve(self.h, p(self.lo), p(self.up), p(restart), p(self.x), p(self.obj),
                                              p(self.status), p(self.iters), st), self.lib)
+
+    def solve(self, restart=None):
+        """Enqueue one solve on the current stream.  `restart`: optional [B] uint8 tensor (non-zero = cold start)."""
+        self._launch(restart)
         self.solves += 1
         return self.x
 
