@@ -36,6 +36,7 @@ constexpr double kFeasTol = 1e-9;   // bound violation that makes a basic variab
 constexpr double kDualTol = 1e-9;   // Harris slack on the reduced costs
 constexpr double kPivRel = 1e-7;    // pivot candidates below kPivRel * max |row| are ignored
 constexpr double kPivAbs = 1e-11;
+constexpr int kPivotsPerEval = 24;  // x_B is re-evaluated from the tableau before "optimal" after more pivots than this
 constexpr double kInf = 1e300;      // bounds beyond +-kInf/2 count as infinite (HUGE_VAL included)
 
 struct Batch {
@@ -161,7 +162,8 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
     restart = true;
   }
   compute_basic_values(b, e);
-  bool verified = true;  // x_B recomputed from T since the last pivot and the bound flags agree with d
+  bool verified = true;  // nothing has changed since the bound flags were last checked against d
+  int it_eval = 0;       // pivot count at the last evaluation of x_B from scratch
   while (status == ANM_LP_OPTIMAL) {
     // ---- leaving row: largest scaled bound violation
     int r = -1;
@@ -174,10 +176,16 @@ LP_HD inline int solve_one(const Batch& b, int64_t e, const double* lo, const do
     }
     if (r < 0) {
       if (verified) break;
+      // Bound flags against the signs of d once more; x_B from scratch if a flag moved or many pivots have been
+      // accumulated into it since the solve's initial evaluation (rounding drift), otherwise the updated values stand.
       restore_dual_feasibility(b, e, &changed);
-      compute_basic_values(b, e);
       verified = true;
-      continue;
+      if (changed || it - it_eval > kPivotsPerEval || (restart && it_eval == 0 && it > 0)) {
+        compute_basic_values(b, e);  // (a cold solve always: its first pivots move the big-M boxes' huge values)
+        it_eval = it;
+        continue;
+      }
+      break;
     }
     if (it >= b.max_iter) {
       status = ANM_LP_ITER_LIMIT;
