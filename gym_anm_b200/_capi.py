@@ -160,6 +160,10 @@ _LP_PROTOS = {
     "anm_lp_destroy": (C.c_int, [C.c_void_p]),
     "anm_lp_solve": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7 + [C.c_void_p]),
     "anm_lp_bytes": (C.c_int64, [C.c_void_p]),
+    "anm_lp_kernel": (C.c_int, [C.c_void_p]),
+    "anm_debug_lp_warp_state_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int64]),
+    "anm_debug_lp_solve_host_warp": (C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int64, C.c_int64,
+                                               C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 7 + [C.c_int32]),
     "anm_debug_lp_state_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int64]),
     "anm_debug_lp_solve_host": (C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int32,
                                           C.c_void_p, C.c_int32] + [C.c_void_p] * 7),

@@ -6,6 +6,8 @@
 
 #include "../../include/anm_lp.h"
 #include "anm_lp.cuh"
+#include "anm_lp_warp.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -79,6 +81,8 @@ int check_dims(int32_t n, int32_t m, int64_t batch, int64_t stride) {
 
 struct anm_lp_batch {
   anm_lp::Batch b;
+  anm_lp::WarpBatch w;
+  int mode;  // ANM_LP_KERNEL_THREAD / ANM_LP_KERNEL_WARP
   int64_t batch, bytes;
   int device;
   bool first;
@@ -101,14 +105,21 @@ int anm_lp_create(int32_t n, int32_t m, const double* a_host, const double* c_ho
   LP_CUDA(cudaSetDevice(device));
   anm_lp_batch* h = new anm_lp_batch();
   memset(&h->b, 0, sizeof h->b);
+  memset(&h->w, 0, sizeof h->w);
+  const char* km = getenv("ANM_LP_KERNEL");  // "thread" | "warp" (A/B switch; default below)
+  h->mode = ANM_LP_KERNEL_DEFAULT;
+  if (km && !strcmp(km, "thread")) h->mode = ANM_LP_KERNEL_THREAD;
+  if (km && !strcmp(km, "warp")) h->mode = ANM_LP_KERNEL_WARP;
   const Layout L = layout_of(n, m, stride);
-  h->batch = batch, h->device = device, h->first = true, h->bytes = L.total + (int64_t)(m * n + n) * 8;
+  const int64_t wblock = anm_lp::warp_block_doubles(n, m);
+  const int64_t total = h->mode == ANM_LP_KERNEL_WARP ? wblock * batch * 8 : L.total;
+  h->batch = batch, h->device = device, h->first = true, h->bytes = total + (int64_t)(m * n + n) * 8;
   h->state = nullptr, h->consts = nullptr;
-  if (cudaMalloc(&h->state, L.total) != cudaSuccess || cudaMalloc(&h->consts, (size_t)(m * n + n) * 8) != cudaSuccess) {
+  if (cudaMalloc(&h->state, total) != cudaSuccess || cudaMalloc(&h->consts, (size_t)(m * n + n) * 8) != cudaSuccess) {
     cudaGetLastError();
     if (h->state) cudaFree(h->state);
     delete h;
-    return lp_fail(ANM_LP_E_NOMEM, "cudaMalloc of %lld bytes failed", (long long)L.total);
+    return lp_fail(ANM_LP_E_NOMEM, "cudaMalloc of %lld bytes failed", (long long)total);
   }
   cudaError_t e1 = cudaMemcpy(h->consts, a_host, (size_t)m * n * 8, cudaMemcpyHostToDevice);
   cudaError_t e2 = cudaMemcpy(h->consts + (size_t)m * n, c_host, (size_t)n * 8, cudaMemcpyHostToDevice);
@@ -121,6 +132,8 @@ int anm_lp_create(int32_t n, int32_t m, const double* a_host, const double* c_ho
   h->b.max_iter = max_iter > 0 ? max_iter : 4 * (n + m) + 50;
   h->b.A = h->consts, h->b.c = h->consts + (size_t)m * n;
   bind(h->b, h->state, L);
+  h->w.n = n, h->w.m = m, h->w.stride = stride, h->w.max_iter = h->b.max_iter, h->w.block = wblock;
+  h->w.A = h->b.A, h->w.c = h->b.c, h->w.mem = reinterpret_cast<double*>(h->state);
   *out = h;
   return ANM_LP_OK;
 }
@@ -136,16 +149,24 @@ int anm_lp_destroy(anm_lp_handle h) {
 
 int64_t anm_lp_bytes(anm_lp_handle h) { return h ? h->bytes : 0; }
 
+int anm_lp_kernel(anm_lp_handle h) { return h ? h->mode : ANM_LP_E_INVALID; }
+
 int anm_lp_solve(anm_lp_handle h, const double* lo_dev, const double* up_dev, const uint8_t* restart_dev_or_null,
                  double* x_dev, double* obj_dev_or_null, int32_t* status_dev_or_null, int32_t* iters_dev_or_null,
                  void* stream) {
   if (!h || !lo_dev || !up_dev || !x_dev) return lp_fail(ANM_LP_E_INVALID, "null argument");
   LP_CUDA(cudaSetDevice(h->device));
   const int threads = 32;
-  const unsigned blocks = (unsigned)((h->batch + threads - 1) / threads);
-  anm_lp::lp_solve_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      h->b, h->batch, lo_dev, up_dev, restart_dev_or_null, h->first ? 1 : 0, x_dev, obj_dev_or_null, status_dev_or_null,
-      iters_dev_or_null);
+  if (h->mode == ANM_LP_KERNEL_WARP) {  // one warp (= one block) per program
+    anm_lp::lp_solve_warp_kernel<<<(unsigned)h->batch, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->w, h->batch, lo_dev, up_dev, restart_dev_or_null, h->first ? 1 : 0, x_dev, obj_dev_or_null,
+        status_dev_or_null, iters_dev_or_null);
+  } else {  // one thread per program
+    const unsigned blocks = (unsigned)((h->batch + threads - 1) / threads);
+    anm_lp::lp_solve_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->b, h->batch, lo_dev, up_dev, restart_dev_or_null, h->first ? 1 : 0, x_dev, obj_dev_or_null,
+        status_dev_or_null, iters_dev_or_null);
+  }
   LP_CUDA(cudaGetLastError());
   h->first = false;
   return ANM_LP_OK;
@@ -172,6 +193,37 @@ int anm_debug_lp_solve_host(int32_t n, int32_t m, const double* a_host, const do
     int32_t it;
     const bool rs = first || (restart_or_null && restart_or_null[e]);
     const int st = anm_lp::solve_one(b, e, lo, up, rs, x, &z, &it);
+    if (obj_or_null) obj_or_null[e] = z;
+    if (status_or_null) status_or_null[e] = st;
+    if (iters_or_null) iters_or_null[e] = it;
+  }
+  return ANM_LP_OK;
+}
+
+int64_t anm_debug_lp_warp_state_bytes(int32_t n, int32_t m, int64_t batch) {
+  if (n <= 0 || m <= 0 || batch <= 0) return 0;
+  return anm_lp::warp_block_doubles(n, m) * batch * 8;
+}
+
+int anm_debug_lp_solve_host_warp(int32_t n, int32_t m, const double* a_host, const double* c_host, int64_t batch,
+                                 int64_t stride, int32_t max_iter, void* state_host, int32_t first, const double* lo,
+                                 const double* up, const uint8_t* restart_or_null, double* x, double* obj_or_null,
+                                 int32_t* status_or_null, int32_t* iters_or_null, int32_t reverse_lanes) {
+  if (!a_host || !c_host || !state_host || !lo || !up || !x) return lp_fail(ANM_LP_E_INVALID, "null argument");
+  if (int rc = check_dims(n, m, batch, stride)) return rc;
+  anm_lp::WarpBatch w;
+  memset(&w, 0, sizeof w);
+  w.n = n, w.m = m, w.stride = stride, w.max_iter = max_iter > 0 ? max_iter : 4 * (n + m) + 50;
+  w.block = anm_lp::warp_block_doubles(n, m);
+  w.A = a_host, w.c = c_host, w.mem = static_cast<double*>(state_host);
+  double tile[32 * 33], rv[32];
+  int32_t ri[32];
+  anm_lp::WarpScratch s{tile, rv, ri, reverse_lanes != 0};
+  for (int64_t e = 0; e < batch; ++e) {
+    double z;
+    int32_t it;
+    const bool rs = first || (restart_or_null && restart_or_null[e]);
+    const int st = anm_lp::solve_one_warp(w, e, lo, up, rs, x, &z, &it, s);
     if (obj_or_null) obj_or_null[e] = z;
     if (status_or_null) status_or_null[e] = st;
     if (iters_or_null) iters_or_null[e] = it;

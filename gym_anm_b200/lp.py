@@ -112,23 +112,29 @@ def instance_bounds(red, agent, Lf, Gf, soc):
     return lo, up
 
 
-def solve_host(red, lo, up, state=None, restart=None, max_iter=0):
-    """TEST HOOK (anm_debug_lp_solve_host): the solver's code compiled for the host.  lo / up: [B, n + m].  Returns
-    (x [B, n], obj [B], status [B], iters [B], state) -- pass `state` back in for a warm start."""
+def solve_host(red, lo, up, state=None, restart=None, max_iter=0, kernel="thread", reverse_lanes=False):
+    """TEST HOOK (anm_debug_lp_solve_host / _host_warp): the solver's code compiled for the host.  lo / up:
+    [B, n + m].  Returns (x [B, n], obj [B], status [B], iters [B], state) -- pass `state` back in for a warm start.
+    `kernel`: "thread" (one thread per program) or "warp" (the warp kernel's lane phases as loops, optionally with
+    the lanes in reverse order)."""
     lib = _capi.load_library()
     B = lo.shape[0]
     n, m = red.n, red.m
     first = state is None
     if first:
-        state = np.zeros(lib.anm_debug_lp_state_bytes(n, m, B), np.uint8)
+        nbytes = lib.anm_debug_lp_state_bytes(n, m, B) if kernel == "thread" else lib.anm_debug_lp_warp_state_bytes(n, m, B)
+        state = np.zeros(nbytes, np.uint8)
     lo_t, up_t = np.ascontiguousarray(lo.T), np.ascontiguousarray(up.T)  # interleaved [n + m, B]
     x = np.zeros((n, B))
     obj, status, iters = np.zeros(B), np.zeros(B, np.int32), np.zeros(B, np.int32)
     rs = None if restart is None else np.ascontiguousarray(restart, np.uint8)
     p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
-    _capi.check_lp(lib.anm_debug_lp_solve_host(n, m, red.A.ctypes.data_as(_capi.c_double_p),
-                                               red.c.ctypes.data_as(_capi.c_double_p), B, B, int(max_iter), p(state),
-                                               int(first), p(lo_t), p(up_t), p(rs), p(x), p(obj), p(status), p(iters)), lib)
+    args = (n, m, red.A.ctypes.data_as(_capi.c_double_p), red.c.ctypes.data_as(_capi.c_double_p), B, B, int(max_iter),
+            p(state), int(first), p(lo_t), p(up_t), p(rs), p(x), p(obj), p(status), p(iters))
+    if kernel == "thread":
+        _capi.check_lp(lib.anm_debug_lp_solve_host(*args), lib)
+    else:
+        _capi.check_lp(lib.anm_debug_lp_solve_host_warp(*args, int(bool(reverse_lanes))), lib)
     return x.T.copy(), obj, status, iters, state
 
 
@@ -172,6 +178,10 @@ class BatchedLP:
     @property
     def bytes(self):
         return int(self.lib.anm_lp_bytes(self.h))
+
+    @property
+    def kernel(self):
+        return {0: "thread", 1: "warp"}[int(self.lib.anm_lp_kernel(self.h))]
 
     def _launch(self, restart):
         import torch

@@ -45,6 +45,12 @@ extern "C" {
 #define ANM_LP_ITER_LIMIT 2
 #define ANM_LP_DUAL_INFEASIBLE 3 /* a column whose cost pulls towards an infinite bound                  */
 
+/* the two device kernels (same algorithm, same pivoting rules): one thread or one warp per program.  The
+ * environment variable ANM_LP_KERNEL = "thread" | "warp" read by anm_lp_create overrides the default. */
+#define ANM_LP_KERNEL_THREAD 0
+#define ANM_LP_KERNEL_WARP 1
+#define ANM_LP_KERNEL_DEFAULT ANM_LP_KERNEL_THREAD
+
 typedef struct anm_lp_batch* anm_lp_handle;
 
 /* A [m, n] row-major and c [n] are HOST pointers (copied).  `batch` programs, interleaved stride `stride`
@@ -61,8 +67,9 @@ int anm_lp_solve(anm_lp_handle h, const double* lo_dev, const double* up_dev, co
                  double* x_dev, double* obj_dev_or_null, int32_t* status_dev_or_null, int32_t* iters_dev_or_null,
                  void* stream);
 
-/* Bytes of device memory the handle holds (tableaux + bases + scratch). */
+/* Bytes of device memory the handle holds (tableaux + bases + scratch); the kernel it launches (ANM_LP_KERNEL_*). */
 int64_t anm_lp_bytes(anm_lp_handle h);
+int anm_lp_kernel(anm_lp_handle h);
 
 /* Host build of the very same solver code (test hook: the CPU suite checks the algorithm against HiGHS without a
  * GPU).  All pointers are host pointers, same layouts; `state_host` is an opaque buffer of
@@ -73,6 +80,15 @@ int anm_debug_lp_solve_host(int32_t n, int32_t m, const double* a_host, const do
                             int64_t stride, int32_t max_iter, void* state_host, int32_t first, const double* lo,
                             const double* up, const uint8_t* restart_or_null, double* x, double* obj_or_null,
                             int32_t* status_or_null, int32_t* iters_or_null);
+
+/* The warp kernel's code on the host: its lane phases run as loops over the 32 lanes, forwards or (reverse_lanes)
+ * backwards -- a phase whose lanes depended on each other would differ between the two orders.  `state_host`:
+ * anm_debug_lp_warp_state_bytes(n, m, batch) bytes (one contiguous block per program). */
+int64_t anm_debug_lp_warp_state_bytes(int32_t n, int32_t m, int64_t batch);
+int anm_debug_lp_solve_host_warp(int32_t n, int32_t m, const double* a_host, const double* c_host, int64_t batch,
+                                 int64_t stride, int32_t max_iter, void* state_host, int32_t first, const double* lo,
+                                 const double* up, const uint8_t* restart_or_null, double* x, double* obj_or_null,
+                                 int32_t* status_or_null, int32_t* iters_or_null, int32_t reverse_lanes);
 
 const char* anm_lp_last_error(void);
 

@@ -77,16 +77,22 @@ def _highs(A, c, lo, up):
                    bounds=np.stack([lo[:n], up[:n]], axis=1), method="highs")
 
 
-@pytest.mark.parametrize("n,m,density", [(6, 4, 1.0), (12, 20, 0.5), (30, 25, 0.2), (40, 60, 0.15)])
-def test_random_boxed_programs_match_highs_cold_and_warm(n, m, density):
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+@pytest.mark.parametrize("n,m,density", [(6, 4, 1.0), (12, 20, 0.5), (30, 25, 0.2), (40, 60, 0.15), (70, 33, 0.3)])
+def test_random_boxed_programs_match_highs_cold_and_warm(n, m, density, kernel):
     rng = np.random.default_rng(100 * n + m)
     A, c = _random_program(rng, n, m, density)
     red = types.SimpleNamespace(A=A, c=c, n=n, m=m)
-    B, state = 24, None
+    B, state, state_rev = 24, None, None
     for rnd in range(4):  # round 0 cold, then new bounds on the old bases; round 3 restarts every other instance
         lo, up = _random_bounds(rng, A, B)
         restart = (np.arange(B) % 2).astype(np.uint8) if rnd == 3 else None
-        x, obj, status, iters, state = LP.solve_host(red, lo, up, state=state, restart=restart)
+        x, obj, status, iters, state = LP.solve_host(red, lo, up, state=state, restart=restart, kernel=kernel)
+        if kernel == "warp":  # the lanes of every phase in reverse order: bit-identical, tableaux included
+            x2, obj2, status2, iters2, state_rev = LP.solve_host(red, lo, up, state=state_rev, restart=restart,
+                                                                 kernel="warp", reverse_lanes=True)
+            assert np.array_equal(x, x2) and np.array_equal(obj, obj2) and np.array_equal(iters, iters2)
+            assert np.array_equal(status, status2) and np.array_equal(state, state_rev)
         assert (status == 0).all(), status
         act = np.concatenate([x, x @ A.T], axis=1)
         assert np.maximum(lo - act, act - up).max() <= 1e-8
@@ -106,16 +112,18 @@ def test_infeasible_and_unboxed_programs_are_reported():
     # towards an infinite bound
     lo = np.array([[0.0, 0.0, 5.0, -inf], [0.0, 0.0, 1.0, -inf], [-inf, 0.0, 1.0, -inf]])
     up = np.array([[1.0, 1.0, inf, inf], [1.0, 1.0, inf, inf], [1.0, 1.0, inf, inf]])
-    x, obj, status, iters, _ = LP.solve_host(red, lo, up)
-    assert list(status) == [1, 0, 3]
-    assert abs(obj[1] - 1.0) < 1e-12
+    for kernel in ("thread", "warp"):
+        x, obj, status, iters, _ = LP.solve_host(red, lo, up, kernel=kernel)
+        assert list(status) == [1, 0, 3]
+        assert abs(obj[1] - 1.0) < 1e-12
     # an iteration cap of one pivot on a program that needs more
     rng = np.random.default_rng(5)
     A, c = _random_program(rng, 12, 20, 0.5)
     lo, up = _random_bounds(rng, A, 8)
     red = types.SimpleNamespace(A=A, c=c, n=12, m=20)
-    _, _, status, iters, _ = LP.solve_host(red, lo, up, max_iter=1)
-    assert set(status) <= {0, 2} and (status == 2).any() and iters.max() == 1
+    for kernel in ("thread", "warp"):
+        _, _, status, iters, _ = LP.solve_host(red, lo, up, max_iter=1, kernel=kernel)
+        assert set(status) <= {0, 2} and (status == 2).any() and iters.max() == 1
 
 
 def _full_solution(red, x):
@@ -138,13 +146,21 @@ def test_reduced_dcopf_closed_loop_matches_highs(N, cls):
     red = LP.reduce_dcopf(agent)
     assert red.n == N * (agent.n_load + agent.n_gen + 2 * agent.n_des + agent.n_branch)
     assert red.m == N * (2 * agent.n_branch + 2 * agent.n_des)
-    state, pivots = None, []
+    state, state_w, state_wr, pivots = None, None, None, []
     for t in range(6):
         p_load, p_gen_max, soc = agent.state_to_pu(env.state)
         Lf, Gf = agent.forecast_batch(env, p_load, p_gen_max)
         lo, up = LP.instance_bounds(red, agent, Lf, Gf, soc)
         x, obj, status, iters, state = LP.solve_host(red, lo, up, state=state)
         assert (status == 0).all()
+        # the warp kernel's code (lane phases as loops, forwards and backwards): same optimum, same pivots
+        xw, objw, stw, itw, state_w = LP.solve_host(red, lo, up, state=state_w, kernel="warp")
+        xr, objr, str_, itr, state_wr = LP.solve_host(red, lo, up, state=state_wr, kernel="warp", reverse_lanes=True)
+        assert np.array_equal(xw, xr) and np.array_equal(objw, objr) and np.array_equal(state_w, state_wr)
+        assert (stw == 0).all() and (itw == iters).mean() > 0.8
+        np.testing.assert_allclose(objw, obj, rtol=1e-10, atol=1e-10)
+        actw = np.concatenate([xw, xw @ red.A.T], axis=1)
+        assert np.maximum(lo - actw, actw - up).max() <= 1e-9
         pivots.append(iters.mean())
         assert not (np.abs(x[:, red.free_cols]) > LP.BIG / 2).any()
         assert np.abs(x @ red.theta_map.T).max() < np.pi
@@ -170,13 +186,14 @@ class _TensorEnv:  # what `act_device` reads from a batched environment
         self.P_loads, self.P_maxs = env.P_loads, env.P_maxs
 
 
-@pytest.mark.parametrize("cls,N", [(MPCAgentConstant, 10), (MPCAgentPerfect, 4)])
-def test_agent_device_path_through_host_standin(monkeypatch, cls, N):
+@pytest.mark.parametrize("cls,N,kernel", [(MPCAgentConstant, 10, "thread"), (MPCAgentPerfect, 4, "thread"),
+                                          (MPCAgentConstant, 10, "warp")])
+def test_agent_device_path_through_host_standin(monkeypatch, cls, N, kernel):
     """`MPCAgent(device=...).act(env)` end to end (torch bounds scatter, checks, action extraction, periodic refresh,
     second solve and host fallback) with the device handle replaced by its host stand-in."""
-    from lp_host_standin import HostLP
+    from lp_host_standin import HostLP, HostWarpLP
 
-    monkeypatch.setattr(LP, "BatchedLP", HostLP)
+    monkeypatch.setattr(LP, "BatchedLP", HostLP if kernel == "thread" else HostWarpLP)
     spec = anm6easy_spec()
     B = 20
     env = tm._Env(spec, B, seed=11)

@@ -28,8 +28,13 @@ def _bounds_from_tables(spec, agent, red, B, rng, prev=None):
     return LP.instance_bounds(red, agent, Lf, Gf, soc) + ((t, scale, soc),)
 
 
-def test_device_solver_equals_host_build_cold_warm_and_restart():
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+def test_device_solver_equals_host_build_cold_warm_and_restart(monkeypatch, kernel):
+    """Both device kernels (one thread / one warp per program; ANM_LP_KERNEL) against the host build of their own code
+    and against HiGHS."""
     import torch
+
+    monkeypatch.setenv("ANM_LP_KERNEL", kernel)
 
     import test_mpc_agent as tm
     from gym_anm_b200 import lp as LP
@@ -42,7 +47,7 @@ def test_device_solver_equals_host_build_cold_warm_and_restart():
     red = LP.reduce_dcopf(agent)
     B = 1000  # not a multiple of the warp size: stride 1024
     dev = LP.BatchedLP(red.A, red.c, B, "cuda:0")
-    assert dev.stride == 1024 and dev.bytes > red.m * red.n * 8 * B
+    assert dev.stride == 1024 and dev.bytes > red.m * red.n * 8 * B and dev.kernel == kernel
     rng = np.random.default_rng(7)
     state = prev = None
     for rnd in range(4):
@@ -51,7 +56,7 @@ def test_device_solver_equals_host_build_cold_warm_and_restart():
         dev.lo[:, :B] = torch.as_tensor(lo.T, device="cuda:0")
         dev.up[:, :B] = torch.as_tensor(up.T, device="cuda:0")
         dev.solve(None if restart is None else torch.as_tensor(restart, device="cuda:0"))
-        x_h, obj_h, st_h, it_h, state = LP.solve_host(red, lo, up, state=state, restart=restart)
+        x_h, obj_h, st_h, it_h, state = LP.solve_host(red, lo, up, state=state, restart=restart, kernel=kernel)
         torch.cuda.synchronize()
         st_d, obj_d, it_d = dev.status.cpu().numpy(), dev.obj.cpu().numpy(), dev.iters.cpu().numpy()
         assert (st_h == 0).all() and (st_d == 0).all()
@@ -76,10 +81,13 @@ def test_device_solver_equals_host_build_cold_warm_and_restart():
     dev.close()
 
 
-def test_mpc_agents_on_device_drive_the_batched_env():
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+def test_mpc_agents_on_device_drive_the_batched_env(monkeypatch, kernel):
     """BASELINE config 5 with the whole loop on the GPU: state tensor -> bounds -> batched LP -> action tensor -> step.
     Objective values against HiGHS on the full program (a sample), the stepped batch against the C oracle."""
     import torch
+
+    monkeypatch.setenv("ANM_LP_KERNEL", kernel)
 
     import anm_oracle
     from golden_util import rel_err
@@ -114,4 +122,5 @@ def test_mpc_agents_on_device_drive_the_batched_env():
             total += float(r_g.mean())
         assert total / 6 > -5.0  # the MPC policy operates the grid at low cost
         assert agent.lp_stats["host_fallbacks"] == 0 and agent.lp_stats["solves"] == 6
+        assert agent._dev.lp.kernel == kernel
         agent.close()

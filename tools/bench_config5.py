@@ -107,20 +107,21 @@ def main():
     assert worst < 1e-8, worst
     stats = dict(agent.lp_stats)
     lp_bytes = agent._dev.lp.bytes if a.lp == "gpu" else 0
+    lp_kernel = agent._dev.lp.kernel if a.lp == "gpu" else None
     agent.close()
     tt = torch.tensor([wall, t_lp, t_step, cold_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
         wall, t_lp, t_step, cold_s = (float(v) for v in tt)
-        how = ("batched dual simplex on the GPU (anm_lp_solve: one thread per program, %d x %d tableau per instance "
+        how = ("batched dual simplex on the GPU (anm_lp_solve: one %s per program, %d x %d tableau per instance "
                "resident in HBM = %.2f GB per rank, warm-started; basis rebuilt every %d solves)"
-               % (agent_dims(a.planning_steps) + (lp_bytes / 1e9, a.refresh))) if a.lp == "gpu" else (
+               % ((lp_kernel,) + agent_dims(a.planning_steps) + (lp_bytes / 1e9, a.refresh))) if a.lp == "gpu" else (
                "one HiGHS LP per instance and step on %d worker processes per rank (%d host cores)" % (workers, cores))
         print(json.dumps({
             "config": "BASELINE config 5: ANM6Easy-v0, %d instances on %d GPU(s), MPC-constant actions (planning_steps %d, "
                       "safety_margin 0.96); LPs: %s" % (a.envs_global, world, a.planning_steps, how),
-            "lp": a.lp, "value": a.envs_global * steps / wall, "unit": "env-steps/s", "n_gpus": world, "steps": steps,
+            "lp": a.lp, "lp_kernel": lp_kernel, "value": a.envs_global * steps / wall, "unit": "env-steps/s", "n_gpus": world, "steps": steps,
             "s_per_step": wall / steps, "lp_s_per_step": t_lp / steps, "env_step_s_per_step": t_step / steps,
             "lp_per_s": a.envs_global * steps / t_lp, "first_solve_s": cold_s,
             "mean_pivots_per_solve": float(pivots[1:].mean()) if a.lp == "gpu" else None, "lp_stats": stats,
