@@ -49,7 +49,7 @@ extern "C" {
  * environment variable ANM_LP_KERNEL = "thread" | "warp" read by anm_lp_create overrides the default. */
 #define ANM_LP_KERNEL_THREAD 0
 #define ANM_LP_KERNEL_WARP 1
-#define ANM_LP_KERNEL_DEFAULT ANM_LP_KERNEL_THREAD
+#define ANM_LP_KERNEL_DEFAULT ANM_LP_KERNEL_WARP
 
 typedef struct anm_lp_batch* anm_lp_handle;
 
