@@ -216,9 +216,9 @@ int anm_debug_lp_solve_host_warp(int32_t n, int32_t m, const double* a_host, con
   w.n = n, w.m = m, w.stride = stride, w.max_iter = max_iter > 0 ? max_iter : 4 * (n + m) + 50;
   w.block = anm_lp::warp_block_doubles(n, m);
   w.A = a_host, w.c = c_host, w.mem = static_cast<double*>(state_host);
-  double tile[32 * 33], rv[32];
-  int32_t ri[32];
-  anm_lp::WarpScratch s{tile, rv, ri, reverse_lanes != 0};
+  double tile[32 * 33], rv[32], col[anm_lp::kColScratch];
+  int32_t ri[32], rows[anm_lp::kColScratch];
+  anm_lp::WarpScratch s{tile, rv, ri, col, rows, reverse_lanes != 0};
   for (int64_t e = 0; e < batch; ++e) {
     double z;
     int32_t it;

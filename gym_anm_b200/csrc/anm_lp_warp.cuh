@@ -27,18 +27,22 @@ struct WarpBatch {
   int64_t block;       // doubles per program block
   const double* A;
   const double* c;
-  double* mem;         // [batch, block]: T[m*n] d[n] xB[m] bl[m] bu[m] nl[n] nu[n] rval[n] cq[m] | bid[m] nid[n] atup[n] (int32)
+  double* mem;         // [batch, block]: T[m*n] d[n] xB[m] bl[m] bu[m] nl[n] nu[n] rval[n] cq[m] | bid[m] nid[n] atup[n] rows[m] (int32)
 };
 
 LP_HD inline int64_t warp_block_doubles(int64_t n, int64_t m) {
-  const int64_t dbl = m * n + 4 * n + 4 * m, ints = m + 2 * n;
+  const int64_t dbl = m * n + 4 * n + 4 * m, ints = 2 * m + 2 * n;
   return (dbl + (ints + 1) / 2 + 31) / 32 * 32;  // 256-byte multiple
 }
+
+constexpr int kColScratch = 256;  // programs with m <= this keep the pivot column and its row list in the warp's scratch
 
 struct WarpScratch {   // device: shared memory of the program's warp; host: local arrays
   double* tile;        // [32 * 33]
   double* rv;          // [32]
   int32_t* ri;         // [32]
+  double* col;         // [kColScratch]: the pivot column (read by every lane for every row of the update)
+  int32_t* rows;       // [kColScratch]: the rows a pivot touches
   bool rev;            // host only: run the lanes of a phase backwards
 };
 
@@ -54,7 +58,7 @@ struct WarpScratch {   // device: shared memory of the program's warp; host: loc
 
 struct WarpView {
   double *T, *d, *xB, *bl, *bu, *nl, *nu, *rval, *cq;
-  int32_t *bid, *nid, *atup;
+  int32_t *bid, *nid, *atup, *rows;
 };
 
 LP_HD inline WarpView warp_view(const WarpBatch& b, int64_t e) {
@@ -73,7 +77,8 @@ LP_HD inline WarpView warp_view(const WarpBatch& b, int64_t e) {
   int32_t* q = reinterpret_cast<int32_t*>(p);
   v.bid = q, q += m;
   v.nid = q, q += n;
-  v.atup = q;
+  v.atup = q, q += n;
+  v.rows = q;
   return v;
 }
 
@@ -119,11 +124,27 @@ LP_HD inline void warp_compute_basic_values(const WarpBatch& b, const WarpView& 
   for (int i0 = 0; i0 < m; i0 += 32) {
     const int rows = m - i0 < 32 ? m - i0 : 32;
     LPW_LANES
-      for (int ii = 0; ii < rows; ++ii) {  // this lane's share of each of the 32 rows' dot products
-        const double* Ti = v.T + (int64_t)(i0 + ii) * n;
-        double acc = 0.0;
-        for (int j = lane; j < n; j += 32) acc = fma(Ti[j], v.rval[j], acc);
-        s.tile[ii * 33 + lane] = acc;
+      // This lane's share of each of the 32 rows' dot products, eight rows at a time: eight independent loads per
+      // column in flight (a row at a time, every row waits for its own loads: the evaluation was latency-bound).
+      for (int i1 = 0; i1 < rows; i1 += 8) {
+        const int cnt = rows - i1 < 8 ? rows - i1 : 8;
+        const double* T0 = v.T + (int64_t)(i0 + i1) * n;
+        double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (cnt == 8) {
+          for (int j = lane; j < n; j += 32) {
+            const double xv = v.rval[j];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fma(T0[(int64_t)k * n + j], xv, acc[k]);
+          }
+        } else {
+          for (int j = lane; j < n; j += 32) {
+            const double xv = v.rval[j];
+            for (int k = 0; k < cnt; ++k) acc[k] = fma(T0[(int64_t)k * n + j], xv, acc[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < cnt) s.tile[(i1 + k) * 33 + lane] = acc[k];
       }
     LPW_END
     LPW_LANES
@@ -300,15 +321,61 @@ LP_HD inline int solve_one_warp(const WarpBatch& b, int64_t e, const double* lo,
     const double x_enter = nonbasic_value(el, eu, v.atup[q] != 0) + delta;
     const double fd = v.d[q] * inv_p;
     LPW_SYNC();
-    // ---- the pivot column, then the rows it touches
+    // ---- the pivot column (into the warp's scratch when it fits) and the list of the rows it touches
+    double* const cq = m <= kColScratch ? s.col : v.cq;
+    int32_t* const rows = m <= kColScratch ? s.rows : v.rows;
     LPW_LANES
-      for (int i = lane; i < m; i += 32) v.cq[i] = v.T[(int64_t)i * n + q];
+      int cnt = 0;
+      for (int i = lane; i < m; i += 32) {
+        const double tiq = v.T[(int64_t)i * n + q];
+        cq[i] = tiq;
+        cnt += (i != r && tiq != 0.0) ? 1 : 0;
+      }
+      s.ri[lane] = cnt;
     LPW_END
     LPW_LANES
-      for (int i = 0; i < m; ++i) {
-        const double tiq = v.cq[i];
-        if (i == r || tiq == 0.0) continue;
-        const double f = tiq * inv_p;
+      int at = 0;  // this lane's rows go behind those of the lanes before it
+      for (int l = 0; l < lane; ++l) at += s.ri[l];
+      for (int i = lane; i < m; i += 32)
+        if (i != r && cq[i] != 0.0) rows[at++] = i;
+    LPW_END
+    int touched = 0;
+    for (int l = 0; l < 32; ++l) touched += s.ri[l];
+    LPW_SYNC();
+    // ---- the update of those rows, four at a time: the four rows' loads are in flight together (row by row, each
+    //      row's read-modify-write waited for its own loads: ~1 us per touched row)
+    LPW_LANES
+      int t = 0;
+      for (; t + 3 < touched; t += 4) {
+        const int i0 = rows[t], i1 = rows[t + 1], i2 = rows[t + 2], i3 = rows[t + 3];
+        const double q0 = cq[i0], q1 = cq[i1], q2 = cq[i2], q3 = cq[i3];
+        const double f0 = q0 * inv_p, f1 = q1 * inv_p, f2 = q2 * inv_p, f3 = q3 * inv_p;
+        double* T0 = v.T + (int64_t)i0 * n;
+        double* T1 = v.T + (int64_t)i1 * n;
+        double* T2 = v.T + (int64_t)i2 * n;
+        double* T3 = v.T + (int64_t)i3 * n;
+        for (int j = lane; j < n; j += 32) {
+          if (j == q) {
+            T0[j] = f0, T1[j] = f1, T2[j] = f2, T3[j] = f3;
+          } else {
+            const double a = v.rval[j];
+            if (a != 0.0) {
+              const double t0 = T0[j], t1 = T1[j], t2 = T2[j], t3 = T3[j];
+              T0[j] = fma(-f0, a, t0);
+              T1[j] = fma(-f1, a, t1);
+              T2[j] = fma(-f2, a, t2);
+              T3[j] = fma(-f3, a, t3);
+            }
+          }
+        }
+        if ((i0 & 31) == lane) v.xB[i0] = fma(q0, delta, v.xB[i0]);
+        if ((i1 & 31) == lane) v.xB[i1] = fma(q1, delta, v.xB[i1]);
+        if ((i2 & 31) == lane) v.xB[i2] = fma(q2, delta, v.xB[i2]);
+        if ((i3 & 31) == lane) v.xB[i3] = fma(q3, delta, v.xB[i3]);
+      }
+      for (; t < touched; ++t) {
+        const int i = rows[t];
+        const double tiq = cq[i], f = tiq * inv_p;
         double* Ti = v.T + (int64_t)i * n;
         for (int j = lane; j < n; j += 32) {
           if (j == q) {
@@ -383,9 +450,11 @@ __global__ void __launch_bounds__(32) lp_solve_warp_kernel(WarpBatch b, int64_t 
   __shared__ double tile[32 * 33];
   __shared__ double rv[32];
   __shared__ int32_t ri[32];
+  __shared__ double col[kColScratch];
+  __shared__ int32_t rows[kColScratch];
   const int64_t e = blockIdx.x;  // one warp = one block = one program
   if (e >= batch) return;
-  WarpScratch s{tile, rv, ri, false};
+  WarpScratch s{tile, rv, ri, col, rows, false};
   double z;
   int32_t it;
   const bool rs = restart_all || (restart != nullptr && restart[e] != 0);

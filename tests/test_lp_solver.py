@@ -78,7 +78,8 @@ def _highs(A, c, lo, up):
 
 
 @pytest.mark.parametrize("kernel", ["thread", "warp"])
-@pytest.mark.parametrize("n,m,density", [(6, 4, 1.0), (12, 20, 0.5), (30, 25, 0.2), (40, 60, 0.15), (70, 33, 0.3)])
+@pytest.mark.parametrize("n,m,density", [(6, 4, 1.0), (12, 20, 0.5), (30, 25, 0.2), (40, 60, 0.15), (70, 33, 0.3),
+                                         (16, 300, 0.2)])  # the last: more rows than the warp kernel keeps in its scratch
 def test_random_boxed_programs_match_highs_cold_and_warm(n, m, density, kernel):
     rng = np.random.default_rng(100 * n + m)
     A, c = _random_program(rng, n, m, density)
