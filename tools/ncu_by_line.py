@@ -18,8 +18,11 @@ import tempfile
 def line_map(so, kernel_substr):
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+    txt = ""
+    for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):  # one cubin per translation unit
+        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+        if kernel_substr in txt:
+            break
     m, cur, infn, fn = {}, None, False, None
     for ln in txt.splitlines():
         if ln.startswith("//---------------------"):
