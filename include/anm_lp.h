@@ -13,11 +13,11 @@
  *                                       lo[n+i] <= (A x)[i] <= up[n+i]    (i <  m: rows)
  *
  * for every instance of the batch, A [m, n] and c [n] common to the batch, lo / up per instance.
- * Method: bounded dual simplex on the condensed tableau (one GPU thread per program, the tableau of every
- * instance resident in HBM between calls: consecutive MPC steps change bounds only, so the previous optimal
- * basis stays dual feasible and a step costs a handful of pivots).  Every column needs a finite bound on the
- * side its cost pulls towards (c[j] > 0: lo[j], c[j] < 0: up[j]); the caller adds box bounds where the
- * program has none.
+ * Method: bounded dual simplex on the condensed tableau (one warp per program -- or one thread, see
+ * ANM_LP_KERNEL_* -- the tableau of every instance resident in HBM between calls: consecutive MPC steps change
+ * bounds only, so the previous optimal basis stays dual feasible and a step costs a handful of pivots).  Every
+ * column needs a finite bound on the side its cost pulls towards (c[j] > 0: lo[j], c[j] < 0: up[j]); the
+ * caller adds box bounds where the program has none.
  *
  * Batch layout: "interleaved" -- element k of instance e lives at [k * stride + e] (stride >= B, the value
  * passed to anm_lp_create), so that neighbouring threads touch neighbouring addresses.  All pointers of the
