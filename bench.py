@@ -36,6 +36,12 @@ Keys of the line (all rates are whole-job env-steps/s over the N GPUs, timed on 
                       fp64 leg: algorithmic fp64 FLOP per env-step / time against the DFMA rate measured
                       in this run (`anm_debug_fp64_peak`).  Fields under `ncu_static` are constants copied from
                       profiles/ncu_summary.json (an earlier ncu capture), NOT measurements of this run.
+  config5             BASELINE configs[4] beside the headline: 16 384 instances (global, sharded over the N GPUs) in closed
+                      loop with the MPC-constant agent (planning_steps 10, safety_margin 0.96) whose DC-OPF programs are
+                      solved on the GPU by the batched dual simplex of include/anm_lp.h (state tensor -> bounds -> LPs ->
+                      action tensor -> anm_step); device-timed, max over ranks, a sample replayed through the C oracle
+                      after the timed region.  `--no-config5` skips it; a failure is reported as {"error": ...} and
+                      leaves the rest of the line intact.
   cpu_baseline        the reference's own ANM6Easy (`oracle/_ref`, staged by oracle/build_ref.py; kind "reference")
                       on all usable host cores, one env per process; falls back to the NumPy/SciPy port (kind "port").
 `--impl reference` times that CPU implementation alone and prints the same line with "impl": "reference".
@@ -93,6 +99,8 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=[2, 4])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the closed-loop MPC leg (BASELINE configs[4])")
+    ap.add_argument("--config5-envs", type=int, default=16384, help="global instances of the MPC leg")
     ap.add_argument("--cpu-steps", type=int, default=1500, help="CPU arms: timed env-steps per process")
     ap.add_argument("--min-timed-s", type=float, default=0.35, help="timed region of every rate (all groups together)")
     return ap.parse_args()
@@ -304,6 +312,92 @@ def setup_config4(B, dev, rank):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+class Config5Leg:
+    """BASELINE configs[4] on this rank's shard: ANM6Easy-v0, `envs_global` instances over `world` GPUs, actions from the
+    MPC-constant agent (examples/mpc_constant.py: planning_steps 10, safety_margin 0.96) whose DC-OPF programs are solved
+    for the whole shard by the batched LP kernel (include/anm_lp.h); closed loop, nothing leaves the device except the
+    per-step count of failed solutions.  No collective in here (the caller agrees on the step count and reduces the
+    times).  A sample of the stepped shard is replayed through the C oracle after the timed region (same actions)."""
+
+    def __init__(self, envs_global, world, rank, dev, n_check=32):
+        from gym_anm_b200.agents import MPCAgentConstant
+        from gym_anm_b200.anm6 import BatchedANM6Easy
+        from gym_anm_b200.distributed import shard_slice
+
+        sl = shard_slice(envs_global, rank, world)
+        self.B, self.dev = sl.stop - sl.start, dev
+        self.env = BatchedANM6Easy(self.B, device=dev, env_offset=sl.start, validate_actions=False)
+        self.env.reset(seed=2020)
+        self.agent = MPCAgentConstant(self.env.simulator, self.env.action_space, self.env.gamma, safety_margin=0.96,
+                                      planning_steps=10, device=dev)
+        self.n_chk = min(n_check, self.B)
+        soc, aux, term = self.env.native.get_state()
+        self.chk0 = [t[: self.n_chk].cpu().numpy().copy() for t in (soc, aux, term)]
+        self.launches0 = self.env.native.launch_count
+        self.rec = []
+
+    def one_step(self, record):
+        act = self.agent.act(self.env)  # CUDA tensor [B, A]
+        obs, r, d, _, _ = self.env.step(act)
+        if record:
+            k = self.n_chk
+            self.rec.append((act[:k].clone(), obs[:k].clone(), d[:k].clone()))
+        return r
+
+    def estimate(self):
+        """Seconds per step after the cold solve (every instance's first basis) and two warm ones."""
+        import torch
+
+        for _ in range(3):
+            self.one_step(True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            self.one_step(True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / 5
+
+    def timed(self, n):
+        import torch
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        piv = torch.zeros((), dtype=torch.float64, device=self.dev)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(n):
+            r = self.one_step(False)
+            piv += self.agent._dev.lp.iters.double().mean()
+        ev1.record()
+        torch.cuda.synchronize()
+        lp = self.agent._dev.lp
+        self.out = {"B": self.B, "mean_pivots_per_solve": float(piv) / n, "lp_kernel": lp.kernel, "lp_bytes": lp.bytes,
+                    "lp_stats": dict(self.agent.lp_stats), "mean_reward": float(r.mean()),
+                    "terminated_frac": float(self.env.terminated.double().mean()),
+                    "launches": self.env.native.launch_count - self.launches0 + lp.solves}
+        return ev0.elapsed_time(ev1)
+
+    def check(self):
+        import numpy as np
+
+        import anm_oracle
+
+        cpu = anm_oracle.OracleEnv(self.env.spec, self.n_chk)
+        cpu.soc[:], cpu.aux[:], cpu.terminated[:] = self.chk0
+        worst, same = 0.0, True
+        for a_t, o_t, d_t in self.rec:
+            o_c, r_c, d_c, _ = cpu.step(a_t.cpu().numpy())
+            same = same and np.array_equal(d_t.cpu().numpy().astype(bool), np.asarray(d_c).astype(bool))
+            worst = max(worst, float(np.max(np.abs(o_t.cpu().numpy() - o_c) / np.maximum(np.abs(o_c), 1.0))))
+        return {"instances": self.n_chk, "steps": len(self.rec), "max_rel_err_obs": worst, "terminated_equal": bool(same)}
+
+    def close(self):
+        import torch
+
+        self.agent.close()
+        self.agent = self.env = None
+        torch.cuda.empty_cache()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -519,6 +613,51 @@ def run_ours(args):
             ex.close()
             barrier()
 
+    # ---- BASELINE configs[4]: 16 384 instances (global) driven by the MPC-constant agent, LPs on the GPU ----------
+    # Every stage may fail on its own rank without costing the line its other numbers; the collectives (maxr) are outside
+    # the try blocks and a failed rank contributes +inf, so that all ranks take the same branches.
+    config5 = None
+    if args.config == 2 and not args.no_config5:
+        leg, err, est, ms, chk = None, None, float("inf"), float("inf"), None
+        try:
+            barrier()
+            leg = Config5Leg(args.config5_envs, world, rank, dev)
+            est = leg.estimate()
+        except Exception as e:  # noqa: BLE001
+            err = "%s: %s" % (type(e).__name__, e)
+        est = maxr([est])[0]
+        if math.isfinite(est):
+            n5 = int(max(10, min(400, math.ceil(args.min_timed_s / max(est, 1e-5)))))
+            try:
+                barrier()
+                ms = leg.timed(n5)
+                chk = leg.check()
+            except Exception as e:  # noqa: BLE001
+                ms, err = float("inf"), "%s: %s" % (type(e).__name__, e)
+            ms = maxr([ms])[0]
+        if math.isfinite(ms) and leg is not None:
+            g5, o5 = args.config5_envs, leg.out
+            config5 = {
+                "value": g5 * n5 / (ms / 1000.0), "unit": "env-steps/s", "n_gpus": world, "global_envs": g5,
+                "envs_per_gpu": o5["B"], "steps": n5, "ms_per_step": ms / n5, "timed_s": ms / 1000.0,
+                "lp_kernel": o5["lp_kernel"], "lp_bytes_per_gpu": o5["lp_bytes"],
+                "mean_pivots_per_solve": o5["mean_pivots_per_solve"], "lp_stats": o5["lp_stats"],
+                "mean_reward_last_step": o5["mean_reward"], "terminated_frac": o5["terminated_frac"],
+                "gpu_launches": o5["launches"], "oracle_check": chk,
+                "what": "BASELINE configs[4]: ANM6Easy-v0, %d instances over %d GPU(s), closed loop with the MPC-constant agent "
+                        "(planning_steps 10, safety_margin 0.96): state tensor -> bounds -> batched dual simplex on the GPU "
+                        "(anm_lp_solve, one %s per program, tableaux resident in HBM, warm-started) -> action tensor -> "
+                        "anm_step; device-timed, max over ranks; counters and oracle check are rank 0's"
+                        % (g5, world, o5["lp_kernel"]),
+            }  # fmt: skip
+        else:
+            config5 = {"error": err or "the leg failed on another rank"}
+        try:
+            if leg is not None:
+                leg.close()
+        except Exception:  # noqa: BLE001
+            pass
+
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
@@ -629,6 +768,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
+    if config5 is not None:
+        line["config5"] = config5
     if gather:
         if "value" in gather.get("p2p", {}):
             line["with_obs_allgather"] = dict(gather["p2p"], what="one launch per step; the kernel epilogue stores every "
