@@ -160,8 +160,9 @@ class MPCAgent:
         self.lb, self.ub = lb, ub
 
     # ---- one LP -------------------------------------------------------------------------------------
-    def solve_one(self, P_load_forecast, P_gen_forecast, soc0):
-        """P_load_forecast [n_load, N], P_gen_forecast [n_gen, N], soc0 [n_des] in p.u. -> (action, result)."""
+    def instance_arrays(self, P_load_forecast, P_gen_forecast, soc0):
+        """The instance-dependent part of the full program: (lb, ub, b_ub) for forecasts [n_load, N], [n_gen, N] and the
+        state of charge [n_des] (p.u.) -- the values `_update_parameters` sets in the reference (mpc.py:395-420)."""
         lb, ub, b_ub = self.lb.copy(), self.ub.copy(), self.b_ub.copy()
         S = self.stride
         for i in range(self.planning_steps):
@@ -173,6 +174,11 @@ class MPCAgent:
                 lb[o + self.dev_pos[d]], ub[o + self.dev_pos[d]] = lo, max(lo, hi)
         for row, s, sgn in self.ub_soc_rows:
             b_ub[row] = (self.soc_max[s] - soc0[s]) if sgn > 0 else (soc0[s] - self.soc_min[s])
+        return lb, ub, b_ub
+
+    def solve_one(self, P_load_forecast, P_gen_forecast, soc0):
+        """P_load_forecast [n_load, N], P_gen_forecast [n_gen, N], soc0 [n_des] in p.u. -> (action, result)."""
+        lb, ub, b_ub = self.instance_arrays(P_load_forecast, P_gen_forecast, soc0)
         res = linprog(self.c, A_ub=self.A_ub, b_ub=b_ub, A_eq=self.A_eq, b_eq=self.b_eq,
                       bounds=np.stack([lb, ub], axis=1), method="highs")
         if res.status != 0:

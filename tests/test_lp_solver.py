@@ -234,3 +234,48 @@ def test_agent_device_path_through_host_standin(monkeypatch, cls, N, kernel):
     p_load, p_gen_max, soc = host.state_to_pu(env.state)
     Lf, Gf = host.forecast_batch(env, p_load, p_gen_max)
     np.testing.assert_allclose(a[1], host.solve_one(Lf[1], Gf[1], soc[1])[0], atol=1e-12)
+
+
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+def test_reduced_dcopf_on_a_meshed_30_bus_feeder(kernel):
+    """The reduction and the solver on a general network (config 4's synthetic 30-bus feeder: 29 + 2 branches, so the
+    eliminated angles are a genuine linear solve, 10 loads, 6 generators, 3 storage units): the reconstructed full
+    solution satisfies the agent's FULL program (equalities, inequalities, every bound) and has HiGHS's optimal value;
+    cold, then warm from perturbed states."""
+    from gym_anm_b200.env_spec import HostEnvSpec
+    from gym_anm_b200.networks import synth_feeder_network
+    from gym_anm_b200.spaces import Box
+
+    spec = HostEnvSpec(synth_feeder_network(), "state", 1, 0.25, 0.99, 100, np.array([[0, 95]]), (1, 100))
+    cn = spec.cn
+    N, B = 3, 10
+    agent = MPCAgentConstant(tm._Sim(spec), Box(spec.action_low, spec.action_high), 0.99, safety_margin=0.9, planning_steps=N)
+    red = LP.reduce_dcopf(agent)
+    nl = agent.n_branch
+    assert (agent.n_bus, agent.n_load, agent.n_gen, agent.n_des) == (30, 10, 6, 3) and nl == 31
+    assert red.n == N * (10 + 6 + 2 * 3 + nl) and red.m == N * (2 * nl + 2 * 3)
+    rng = np.random.default_rng(4)
+    p_load = rng.uniform([cn.devices[i].p_min for i in cn.load_ids], 0.0, size=(B, 10))
+    p_gen = rng.uniform(0.0, [cn.devices[i].p_max for i in cn.gen_ids], size=(B, 6))
+    soc = rng.uniform(agent.soc_min, agent.soc_max, size=(B, 3))
+    state = None
+    for rnd in range(3):
+        Lf, Gf = np.repeat(p_load[:, :, None], N, axis=2), np.repeat(p_gen[:, :, None], N, axis=2)
+        lo, up = LP.instance_bounds(red, agent, Lf, Gf, soc)
+        x, obj, status, iters, state = LP.solve_host(red, lo, up, state=state, kernel=kernel)
+        assert (status == 0).all()
+        assert np.abs(x @ red.theta_map.T).max() < np.pi and not (np.abs(x[:, red.free_cols]) > LP.BIG / 2).any()
+        for i in range(B):
+            xf = _full_solution(red, x[i])
+            lb, ub, b_ub = agent.instance_arrays(Lf[i], Gf[i], soc[i])
+            assert np.abs(agent.A_eq @ xf).max() < 1e-9
+            assert (agent.A_ub @ xf - b_ub).max() < 1e-8
+            assert (lb - xf).max() < 1e-8 and (xf - ub).max() < 1e-8
+            res = agent.solve_one(Lf[i], Gf[i], soc[i])[1]
+            assert res.status == 0 and abs(res.fun - obj[i]) <= 1e-8 * max(1.0, abs(res.fun))
+        if rnd > 0:
+            assert iters.mean() < 0.7 * cold
+        cold = iters.mean() if rnd == 0 else cold
+        p_load = np.clip(p_load * rng.uniform(0.97, 1.03, p_load.shape), [cn.devices[i].p_min for i in cn.load_ids], 0.0)
+        p_gen = np.clip(p_gen * rng.uniform(0.97, 1.03, p_gen.shape), 0.0, [cn.devices[i].p_max for i in cn.gen_ids])
+        soc = np.clip(soc + rng.normal(0, 0.01, soc.shape), agent.soc_min, agent.soc_max)
