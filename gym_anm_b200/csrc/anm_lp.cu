@@ -27,6 +27,19 @@ int lp_fail(int code, const char* fmt, ...) {
     if (err_ != cudaSuccess) return lp_fail(ANM_LP_E_CUDA, "%s: %s", #call, cudaGetErrorString(err_)); \
   } while (0)
 
+// the caller's current device is restored on return (as in anm_capi.cu)
+struct LpDeviceGuard {
+  int prev = -1;
+  explicit LpDeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~LpDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // byte offsets of the per-batch arrays inside one allocation (device handle and host test state alike)
 struct Layout {
   int64_t T, d, xB, rval, bl, bu, nl, nu, bid, nid, ridx, atup, total;
@@ -102,7 +115,7 @@ int anm_lp_create(int32_t n, int32_t m, const double* a_host, const double* c_ho
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
     return lp_fail(ANM_LP_E_CUDA, "no usable CUDA device %d (%d visible): the LP solver has no CPU fallback", device, count);
-  LP_CUDA(cudaSetDevice(device));
+  LpDeviceGuard guard(device);
   anm_lp_batch* h = new anm_lp_batch();
   memset(&h->b, 0, sizeof h->b);
   memset(&h->w, 0, sizeof h->w);
@@ -140,7 +153,7 @@ int anm_lp_create(int32_t n, int32_t m, const double* a_host, const double* c_ho
 
 int anm_lp_destroy(anm_lp_handle h) {
   if (!h) return ANM_LP_OK;
-  cudaSetDevice(h->device);
+  LpDeviceGuard guard(h->device);
   cudaFree(h->state);
   cudaFree(h->consts);
   delete h;
@@ -155,7 +168,7 @@ int anm_lp_solve(anm_lp_handle h, const double* lo_dev, const double* up_dev, co
                  double* x_dev, double* obj_dev_or_null, int32_t* status_dev_or_null, int32_t* iters_dev_or_null,
                  void* stream) {
   if (!h || !lo_dev || !up_dev || !x_dev) return lp_fail(ANM_LP_E_INVALID, "null argument");
-  LP_CUDA(cudaSetDevice(h->device));
+  LpDeviceGuard guard(h->device);
   const int threads = 32;
   if (h->mode == ANM_LP_KERNEL_WARP) {  // one warp (= one block) per program
     anm_lp::lp_solve_warp_kernel<<<(unsigned)h->batch, threads, 0, static_cast<cudaStream_t>(stream)>>>(
