@@ -42,12 +42,18 @@ class MPCAgent:
     action_space, gamma, safety_margin, planning_steps."""
 
     def __init__(self, simulator, action_space, gamma, safety_margin=0.9, planning_steps=1, workers=0, device=None,
-                 refresh=64):
+                 refresh=64, on_lp_failure="raise"):
         """`workers` > 0: the LPs of a batch are solved by that many worker processes (one HiGHS LP per instance and
         step stays the unit of work).  0: in this process.
         `device` (e.g. "cuda:0"): `act(env)` on a batched environment whose state lives on that device solves the
         whole batch with the GPU solver and returns the actions as a CUDA tensor (`act_device`); every instance's
-        basis is dropped and rebuilt every `refresh` solves (drift insurance for the warm-started tableaux)."""
+        basis is dropped and rebuilt every `refresh` solves (drift insurance for the warm-started tableaux).
+        `on_lp_failure`: what `act_device` does with instances whose solution fails its checks twice -- "raise"
+        (default: LPSolverError; there is no silent CPU path) or "host" (opt-in: those instances' programs go to the
+        host LP, counted in `lp_stats["host_fallbacks"]`)."""
+        if on_lp_failure not in ("raise", "host"):
+            raise ValueError("on_lp_failure must be 'raise' or 'host'")
+        self.on_lp_failure = on_lp_failure
         self.workers, self._pool = int(workers), None
         self.device, self.refresh, self._dev = device, int(refresh), None
         self.lp_stats = {"solves": 0, "second_solves": 0, "host_fallbacks": 0}
@@ -254,8 +260,9 @@ class MPCAgent:
         """Actions [B, A] (CUDA tensor, MW / MVAr) for a batched environment whose state tensor is on the device: new
         bounds -> one warm-started solve of every instance's program -> first-stage set-points.  Every solution is
         checked on the device (status, bound violations recomputed from the constraint matrix, the angle box
-        |theta| <= pi of mpc.py:298, the added big-M boxes); an instance that fails is solved again from scratch, and
-        handed to the host LP if that fails too (one host look per step: the number of such instances)."""
+        |theta| <= pi of mpc.py:298, the added big-M boxes); an instance that fails is solved again from scratch; if it
+        fails again, LPSolverError (or, with on_lp_failure="host", the host LP for that instance).  One host look per
+        step: the number of failed instances."""
         import torch
 
         from . import lp as _lp
@@ -291,7 +298,14 @@ class MPCAgent:
         P_des = (dv.act_des @ x).t() * m
         a = torch.cat([P_gen, torch.zeros_like(P_gen), P_des, torch.zeros_like(P_des)], dim=1)
         a = torch.minimum(torch.maximum(a, dv.a_lo), dv.a_hi)
-        if n_bad:  # rare: the host LP on the full program (angles included)
+        if n_bad and self.on_lp_failure != "host":
+            from .errors import LPSolverError
+
+            idx = torch.nonzero(bad).flatten()[:8].tolist()
+            raise LPSolverError("%d of %d programs have no usable solution after a second solve from scratch (instances %s, "
+                                "status %s); build the agent with on_lp_failure='host' to hand such instances to the host LP"
+                                % (n_bad, B, idx, [_lp.LP_STATUS.get(int(s_), s_) for s_ in lp.status[idx].tolist()]))
+        if n_bad:  # opt-in: the host LP on the full program (angles included)
             idx = torch.nonzero(bad).flatten()
             Lh, Gh, sh = Lf[idx].cpu().numpy(), Gf[idx].cpu().numpy(), soc[idx].cpu().numpy()
             rows = np.stack([self.solve_one(Lh[k], Gh[k], sh[k])[0] for k in range(len(idx))])

@@ -90,3 +90,8 @@ class EnvNextVarsError(ANMEnvConfigurationError):
 # ---- native-library errors (new) ----------------------------------------------------
 class NativeLibraryError(RuntimeError):
     """The CUDA extension is missing or a C-ABI call failed.  There is NO CPU fallback."""
+
+
+class LPSolverError(RuntimeError):
+    """The batched LP solver (include/anm_lp.h) left instances without a usable solution (after a second solve from
+    scratch).  Raised by `MPCAgent.act_device` unless the agent was built with `on_lp_failure="host"`."""

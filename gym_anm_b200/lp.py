@@ -9,7 +9,8 @@ simplex, one GPU thread per program, tableaux resident in HBM, warm-started from
 charge / discharge, branch epigraphs; equality + inequality rows) into that shape: the equality rows determine the bus
 angles, the slack injection and the storage injections from the remaining columns, so those are eliminated
 (`x_elim = G x_keep`); the angle box |theta| <= pi (mpc.py:298) is not carried as rows (it is never active on a
-sensible network) but CHECKED on every solution -- an instance that violates it is handed to the host LP by the agent.
+sensible network) but CHECKED on every solution -- an instance that violates it counts as failed (agents.act_device:
+second solve, then LPSolverError, or the host LP on the full program if the agent was built with on_lp_failure="host").
 """
 import ctypes as C
 

@@ -229,8 +229,15 @@ def test_agent_device_path_through_host_standin(monkeypatch, cls, N, kernel):
         return bad
 
     monkeypatch.setattr(type(dev._dev), "failed", failed)
+    from gym_anm_b200.errors import LPSolverError
+
+    with pytest.raises(LPSolverError, match="1 of 20 programs"):  # the default: no silent CPU path
+        dev.act_device(_TensorEnv(env))
+    assert dev.lp_stats["second_solves"] == 1 and dev.lp_stats["host_fallbacks"] == 0
+    calls["n"] = 0
+    dev.on_lp_failure = "host"  # opt-in
     a = dev.act_device(_TensorEnv(env)).numpy()
-    assert dev.lp_stats["second_solves"] == 1 and dev.lp_stats["host_fallbacks"] == 1
+    assert dev.lp_stats["second_solves"] == 2 and dev.lp_stats["host_fallbacks"] == 1
     p_load, p_gen_max, soc = host.state_to_pu(env.state)
     Lf, Gf = host.forecast_batch(env, p_load, p_gen_max)
     np.testing.assert_allclose(a[1], host.solve_one(Lf[1], Gf[1], soc[1])[0], atol=1e-12)
