@@ -286,3 +286,28 @@ def test_reduced_dcopf_on_a_meshed_30_bus_feeder(kernel):
         p_load = np.clip(p_load * rng.uniform(0.97, 1.03, p_load.shape), [cn.devices[i].p_min for i in cn.load_ids], 0.0)
         p_gen = np.clip(p_gen * rng.uniform(0.97, 1.03, p_gen.shape), 0.0, [cn.devices[i].p_max for i in cn.gen_ids])
         soc = np.clip(soc + rng.normal(0, 0.01, soc.shape), agent.soc_min, agent.soc_max)
+
+
+@pytest.mark.parametrize("kernel", ["thread", "warp"])
+def test_solutions_do_not_depend_on_the_batch_an_instance_is_in(kernel):
+    """Shard equivalence of the action source (config 5 shards the instances over the GPUs): a program's pivots and
+    solution are bit-identical whether it is solved in the whole batch or in a shard of it, cold and warm."""
+    spec = anm6easy_spec()
+    B = 12
+    env = tm._Env(spec, B, seed=21)
+    agent = MPCAgentConstant(env.simulator, env.action_space, 0.995, safety_margin=0.96, planning_steps=4)
+    red = LP.reduce_dcopf(agent)
+    whole, lo_s, hi_s = None, None, None
+    for t in range(3):
+        p_load, p_gen_max, soc = agent.state_to_pu(env.state)
+        Lf, Gf = agent.forecast_batch(env, p_load, p_gen_max)
+        lo, up = LP.instance_bounds(red, agent, Lf, Gf, soc)
+        x, obj, status, iters, whole = LP.solve_host(red, lo, up, state=whole, kernel=kernel)
+        x0, obj0, _, it0, lo_s = LP.solve_host(red, lo[:5], up[:5], state=lo_s, kernel=kernel)
+        x1, obj1, _, it1, hi_s = LP.solve_host(red, lo[5:], up[5:], state=hi_s, kernel=kernel)
+        assert np.array_equal(x, np.concatenate([x0, x1])) and np.array_equal(obj, np.concatenate([obj0, obj1]))
+        assert np.array_equal(iters, np.concatenate([it0, it1]))
+        P_gen = x[:, red.col_gen[:, 0]] * agent.baseMVA
+        P_des = (x @ red.A[red.row_pdes[:, 0]].T) * agent.baseMVA
+        a = np.concatenate([P_gen, np.zeros_like(P_gen), P_des, np.zeros_like(P_des)], axis=1)
+        env.step(np.clip(a, env.action_space.low, env.action_space.high))
