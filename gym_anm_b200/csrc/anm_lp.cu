@@ -9,6 +9,20 @@
 #include "anm_lp_warp.cuh"
 #include <stdlib.h>
 
+/* NVTX range around the solve (as anm_capi.cu does for reset / step / rollout); -DANM_NO_NVTX compiles it out. */
+#ifndef ANM_NO_NVTX
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct LpNvtxRange {
+  explicit LpNvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~LpNvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define ANM_LP_NVTX(name) LpNvtxRange lp_nvtx_range_(name)
+#else
+#define ANM_LP_NVTX(name)
+#endif
+
 namespace {
 
 thread_local char g_lp_err[512] = "";
@@ -168,6 +182,7 @@ int anm_lp_solve(anm_lp_handle h, const double* lo_dev, const double* up_dev, co
                  double* x_dev, double* obj_dev_or_null, int32_t* status_dev_or_null, int32_t* iters_dev_or_null,
                  void* stream) {
   if (!h || !lo_dev || !up_dev || !x_dev) return lp_fail(ANM_LP_E_INVALID, "null argument");
+  ANM_LP_NVTX("anm_lp_solve");
   LpDeviceGuard guard(h->device);
   const int threads = 32;
   if (h->mode == ANM_LP_KERNEL_WARP) {  // one warp (= one block) per program
