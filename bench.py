@@ -398,6 +398,52 @@ class Config5Leg:
         torch.cuda.empty_cache()
 
 
+def run_config5(envs_global, min_timed_s, world, rank, dev, barrier, maxr, leg_factory=None):
+    """The `config5` key of the line.  Every stage may fail on its own rank without costing the line its other numbers:
+    the collectives (`barrier`, `maxr`) are outside the try blocks and a failed rank contributes +inf, so that all ranks
+    take the same branches and nobody waits for a rank that has given up."""
+    leg, err, est, ms, chk, n5 = None, None, float("inf"), float("inf"), None, 0
+    barrier()
+    try:
+        leg = (leg_factory or Config5Leg)(envs_global, world, rank, dev)
+        est = leg.estimate()
+    except Exception as e:  # noqa: BLE001
+        err = "%s: %s" % (type(e).__name__, e)
+    est = maxr([est])[0]
+    if math.isfinite(est):
+        n5 = int(max(10, min(400, math.ceil(min_timed_s / max(est, 1e-5)))))
+        barrier()
+        try:
+            ms = leg.timed(n5)
+            chk = leg.check()
+        except Exception as e:  # noqa: BLE001
+            ms, err = float("inf"), "%s: %s" % (type(e).__name__, e)
+        ms = maxr([ms])[0]
+    if math.isfinite(ms) and leg is not None:
+        o5 = leg.out
+        config5 = {
+            "value": envs_global * n5 / (ms / 1000.0), "unit": "env-steps/s", "n_gpus": world, "global_envs": envs_global,
+            "envs_per_gpu": o5["B"], "steps": n5, "ms_per_step": ms / n5, "timed_s": ms / 1000.0,
+            "lp_kernel": o5["lp_kernel"], "lp_bytes_per_gpu": o5["lp_bytes"],
+            "mean_pivots_per_solve": o5["mean_pivots_per_solve"], "lp_stats": o5["lp_stats"],
+            "mean_reward_last_step": o5["mean_reward"], "terminated_frac": o5["terminated_frac"],
+            "gpu_launches": o5["launches"], "oracle_check": chk,
+            "what": "BASELINE configs[4]: ANM6Easy-v0, %d instances over %d GPU(s), closed loop with the MPC-constant agent "
+                    "(planning_steps 10, safety_margin 0.96): state tensor -> bounds -> batched dual simplex on the GPU "
+                    "(anm_lp_solve, one %s per program, tableaux resident in HBM, warm-started) -> action tensor -> "
+                    "anm_step; device-timed, max over ranks; counters and oracle check are rank 0's"
+                    % (envs_global, world, o5["lp_kernel"]),
+        }  # fmt: skip
+    else:
+        config5 = {"error": err or "the leg failed on another rank"}
+    try:
+        if leg is not None:
+            leg.close()
+    except Exception:  # noqa: BLE001
+        pass
+    return config5
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -614,49 +660,9 @@ def run_ours(args):
             barrier()
 
     # ---- BASELINE configs[4]: 16 384 instances (global) driven by the MPC-constant agent, LPs on the GPU ----------
-    # Every stage may fail on its own rank without costing the line its other numbers; the collectives (maxr) are outside
-    # the try blocks and a failed rank contributes +inf, so that all ranks take the same branches.
     config5 = None
     if args.config == 2 and not args.no_config5:
-        leg, err, est, ms, chk = None, None, float("inf"), float("inf"), None
-        try:
-            barrier()
-            leg = Config5Leg(args.config5_envs, world, rank, dev)
-            est = leg.estimate()
-        except Exception as e:  # noqa: BLE001
-            err = "%s: %s" % (type(e).__name__, e)
-        est = maxr([est])[0]
-        if math.isfinite(est):
-            n5 = int(max(10, min(400, math.ceil(args.min_timed_s / max(est, 1e-5)))))
-            try:
-                barrier()
-                ms = leg.timed(n5)
-                chk = leg.check()
-            except Exception as e:  # noqa: BLE001
-                ms, err = float("inf"), "%s: %s" % (type(e).__name__, e)
-            ms = maxr([ms])[0]
-        if math.isfinite(ms) and leg is not None:
-            g5, o5 = args.config5_envs, leg.out
-            config5 = {
-                "value": g5 * n5 / (ms / 1000.0), "unit": "env-steps/s", "n_gpus": world, "global_envs": g5,
-                "envs_per_gpu": o5["B"], "steps": n5, "ms_per_step": ms / n5, "timed_s": ms / 1000.0,
-                "lp_kernel": o5["lp_kernel"], "lp_bytes_per_gpu": o5["lp_bytes"],
-                "mean_pivots_per_solve": o5["mean_pivots_per_solve"], "lp_stats": o5["lp_stats"],
-                "mean_reward_last_step": o5["mean_reward"], "terminated_frac": o5["terminated_frac"],
-                "gpu_launches": o5["launches"], "oracle_check": chk,
-                "what": "BASELINE configs[4]: ANM6Easy-v0, %d instances over %d GPU(s), closed loop with the MPC-constant agent "
-                        "(planning_steps 10, safety_margin 0.96): state tensor -> bounds -> batched dual simplex on the GPU "
-                        "(anm_lp_solve, one %s per program, tableaux resident in HBM, warm-started) -> action tensor -> "
-                        "anm_step; device-timed, max over ranks; counters and oracle check are rank 0's"
-                        % (g5, world, o5["lp_kernel"]),
-            }  # fmt: skip
-        else:
-            config5 = {"error": err or "the leg failed on another rank"}
-        try:
-            if leg is not None:
-                leg.close()
-        except Exception:  # noqa: BLE001
-            pass
+        config5 = run_config5(args.config5_envs, args.min_timed_s, world, rank, dev, barrier, maxr)
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:

@@ -91,3 +91,101 @@ def test_config5_leg_logic_on_cpu(monkeypatch):
     # the two shards start from different instances (global index = seed offset)
     assert not np.array_equal(legs[0].chk0[0], legs[1].chk0[0]) or not np.array_equal(legs[0].chk0[1], legs[1].chk0[1])
     assert isinstance(types.SimpleNamespace(), object)
+
+
+class _StubLeg:
+    """A leg whose stages succeed or fail on demand (which rank, which stage)."""
+
+    fail = {}  # stage -> set of ranks
+
+    def __init__(self, envs_global, world, rank, dev):
+        self.rank, self.closed = rank, False
+        if rank in self.fail.get("init", ()):
+            raise RuntimeError("init failed on rank %d" % rank)
+
+    def estimate(self):
+        if self.rank in self.fail.get("estimate", ()):
+            raise RuntimeError("estimate failed on rank %d" % self.rank)
+        return 0.01 * (1 + self.rank)
+
+    def timed(self, n):
+        if self.rank in self.fail.get("timed", ()):
+            raise RuntimeError("timed failed on rank %d" % self.rank)
+        self.out = {"B": 8, "mean_pivots_per_solve": 2.0, "lp_kernel": "warp", "lp_bytes": 1, "lp_stats": {"solves": n},
+                    "mean_reward": -1.0, "terminated_frac": 0.0, "launches": 2 * n}
+        return 10.0 * n * (1 + self.rank)
+
+    def check(self):
+        return {"instances": 1, "steps": 1, "max_rel_err_obs": 0.0, "terminated_equal": True}
+
+    def close(self):
+        self.closed = True
+
+
+def test_run_config5_branches_single_process():
+    calls = {"barrier": 0}
+
+    def barrier():
+        calls["barrier"] += 1
+
+    maxr = lambda v: list(v)  # noqa: E731
+    _StubLeg.fail = {}
+    ok = bench.run_config5(16, 0.35, 1, 0, None, barrier, maxr, leg_factory=_StubLeg)
+    assert ok["steps"] == 35 and abs(ok["ms_per_step"] - 10.0) < 1e-12 and abs(ok["value"] - 16 / 0.010) < 1e-6
+    assert ok["oracle_check"]["terminated_equal"] and ok["lp_kernel"] == "warp" and calls["barrier"] == 2
+    for stage in ("init", "estimate", "timed"):
+        _StubLeg.fail = {stage: {0}}
+        bad = bench.run_config5(16, 0.35, 1, 0, None, barrier, maxr, leg_factory=_StubLeg)
+        assert set(bad) == {"error"} and stage in bad["error"]
+    _StubLeg.fail = {}
+
+
+_C5_WORKER = r"""
+import os, sys
+sys.path[:0] = [{root!r}, os.path.join({root!r}, "tests"), os.path.join({root!r}, "oracle")]
+import json
+import torch, torch.distributed as dist
+rank = int(sys.argv[1]); stage = sys.argv[2]
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="{port}")
+dist.init_process_group("gloo", rank=rank, world_size=2)
+import bench
+from test_bench_config5_leg import _StubLeg
+_StubLeg.fail = {{stage: {{1}}}} if stage != "none" else {{}}
+def maxr(vals):
+    t = torch.tensor(vals, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+out = bench.run_config5(16, 0.35, 2, rank, None, dist.barrier, maxr, leg_factory=_StubLeg)
+print("C5", rank, json.dumps(out))
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_run_config5_world2_a_failing_rank_does_not_hang_the_other(tmp_path):
+    """N > 1 (gloo, two processes): rank 1 fails in each stage in turn; both ranks return (no rank waits in a
+    collective for one that has given up), both report the error; with no failure the time is the max over ranks."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for stage in ("none", "init", "estimate", "timed"):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        script = tmp_path / ("w_%s.py" % stage)
+        script.write_text(_C5_WORKER.format(root=root, port=port))
+        procs = [subprocess.Popen([sys.executable, str(script), str(r), stage], stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT) for r in range(2)]
+        outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        res = [json.loads([ln for ln in o.splitlines() if ln.startswith("C5 ")][0].split(" ", 2)[2]) for o in outs]
+        if stage == "none":
+            # est = max(0.01, 0.02) -> 18 steps; rank 1 is the slow one: 20 ms per step
+            assert all(r["steps"] == 18 and abs(r["ms_per_step"] - 20.0) < 1e-9 for r in res), res
+        else:
+            assert all(set(r) == {"error"} for r in res), res
+            assert stage in res[1]["error"] and (stage in res[0]["error"] or "another rank" in res[0]["error"])
