@@ -468,9 +468,10 @@ def run_ours(args):
 
     def maxr(vals):
         """max over ranks of a list of floats (device-timed milliseconds)"""
+        if world == 1:
+            return [float(v) for v in vals]
         t = torch.tensor(vals, device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t]
 
     sampler = ClockSampler(local)
@@ -659,6 +660,18 @@ def run_ours(args):
             ex.close()
             barrier()
 
+    # ---- the fp64 FMA rate of this GPU (denominator of the roofline's fp64 leg), before the optional leg below ----
+    import ctypes as C
+
+    fp64_peak = None
+    if rank == 0:
+        try:
+            tf = C.c_double(0.0)
+            _capi.check(nb.lib.anm_debug_fp64_peak(local, C.byref(tf)), nb.lib)
+            fp64_peak = tf.value
+        except Exception:  # noqa: BLE001
+            pass
+
     # ---- BASELINE configs[4]: 16 384 instances (global) driven by the MPC-constant agent, LPs on the GPU ----------
     config5 = None
     if args.config == 2 and not args.no_config5:
@@ -684,15 +697,6 @@ def run_ours(args):
     launch_s = grp_s / launches_per_group                    # mean launch duration over the timed region (CUDA events)
     env_steps_per_launch = B * K / launches_per_block
     achieved = alg_bytes * env_steps_per_launch / launch_s / 1e9
-    import ctypes as C
-
-    tf = C.c_double(0.0)
-    fp64_peak = None
-    try:
-        _capi.check(nb.lib.anm_debug_fp64_peak(local, C.byref(tf)), nb.lib)
-        fp64_peak = tf.value
-    except Exception:  # noqa: BLE001
-        pass
     ncu = {}
     try:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
