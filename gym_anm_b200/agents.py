@@ -269,7 +269,9 @@ class MPCAgent:
 
         st = env.state
         B = st.shape[0]
-        if self._dev is None or self._dev.B != B:
+        if self._dev is None or self._dev.B != B or self._dev.lp.device != st.device:
+            if self._dev is not None:
+                self._dev.lp.close()  # another batch size / device: the old tableaux go
             self._dev = _DeviceProgram(self, B, st.device)
         dv = self._dev
         m = self.baseMVA
