@@ -311,3 +311,37 @@ def test_solutions_do_not_depend_on_the_batch_an_instance_is_in(kernel):
         P_des = (x @ red.A[red.row_pdes[:, 0]].T) * agent.baseMVA
         a = np.concatenate([P_gen, np.zeros_like(P_gen), P_des, np.zeros_like(P_des)], axis=1)
         env.step(np.clip(a, env.action_space.low, env.action_space.high))
+
+
+@pytest.mark.parametrize("N", [1, 3, 20])
+def test_dcopf_1000_step_rollouts_like_the_reference_test(N):
+    """The reference's own test of this path (tests/test_dcopf_agent.py:29-62): 1000-step closed-loop rollouts of
+    MPCAgentConstant with planning horizons 1, 3 and 20 on ANM6Easy, seed 2020, `gamma` = 0.9 (the reference passes its
+    safety margin into that slot, :31), DC-OPF constraints C1..C7 checked at every step -- here with the programs
+    solved by the warp kernel's code (host build), warm-started over the whole rollout without a single rebuild."""
+    spec = anm6easy_spec()
+    B = 2
+    env = tm._Env(spec, B, seed=2020)
+    agent = MPCAgentConstant(env.simulator, env.action_space, 0.9, planning_steps=N)
+    red = LP.reduce_dcopf(agent)
+    state, pivots = None, 0
+    steps = 1000
+    for t in range(steps):
+        p_load, p_gen_max, soc = agent.state_to_pu(env.state)
+        Lf, Gf = agent.forecast_batch(env, p_load, p_gen_max)
+        lo, up = LP.instance_bounds(red, agent, Lf, Gf, soc)
+        x, obj, status, iters, state = LP.solve_host(red, lo, up, state=state, kernel="warp")
+        assert (status == 0).all(), (t, status)
+        pivots += int(iters.sum())
+        for i in range(B):
+            tm._check_constraints(agent, spec, env.state[i], types.SimpleNamespace(x=_full_solution(red, x[i])), N)
+        if t % 100 == 0:  # the optimal value against HiGHS now and then
+            for i in range(B):
+                res = agent.solve_one(Lf[i], Gf[i], soc[i])[1]
+                assert abs(res.fun - obj[i]) <= 1e-9 * max(1.0, abs(res.fun))
+        P_gen = x[:, red.col_gen[:, 0]] * agent.baseMVA
+        P_des = (x @ red.A[red.row_pdes[:, 0]].T) * agent.baseMVA
+        a = np.concatenate([P_gen, np.zeros_like(P_gen), P_des, np.zeros_like(P_des)], axis=1)
+        _, _, term = env.step(np.clip(a, env.action_space.low, env.action_space.high))
+        assert not term.any()  # the MPC policy keeps the grid solvable
+    assert pivots / (steps * B) < 0.2 * (red.n + red.m)  # warm starts: a small fraction of a cold solve per step
