@@ -42,6 +42,9 @@ Keys of the line (all rates are whole-job env-steps/s over the N GPUs, timed on 
                       action tensor -> anm_step); device-timed, max over ranks, a sample replayed through the C oracle
                       after the timed region.  `--no-config5` skips it; a failure is reported as {"error": ...} and
                       leaves the rest of the line intact.
+  config4             BASELINE configs[3] beside the headline: the synthetic 30-bus feeder, 8192 instances per GPU, 20-step
+                      rollout launches back to back (what `--config 4` measures as its `value`, shortened);
+                      `--no-config4` skips it; failure-isolated like `config5`.
   cpu_baseline        the reference's own ANM6Easy (`oracle/_ref`, staged by oracle/build_ref.py; kind "reference")
                       on all usable host cores, one env per process; falls back to the NumPy/SciPy port (kind "port").
 `--impl reference` times that CPU implementation alone and prints the same line with "impl": "reference".
@@ -100,6 +103,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the closed-loop MPC leg (BASELINE configs[4])")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 30-bus leg (BASELINE configs[3])")
     ap.add_argument("--config5-envs", type=int, default=16384, help="global instances of the MPC leg")
     ap.add_argument("--cpu-steps", type=int, default=1500, help="CPU arms: timed env-steps per process")
     ap.add_argument("--min-timed-s", type=float, default=0.35, help="timed region of every rate (all groups together)")
@@ -398,30 +402,50 @@ class Config5Leg:
         torch.cuda.empty_cache()
 
 
-def run_config5(envs_global, min_timed_s, world, rank, dev, barrier, maxr, leg_factory=None):
-    """The `config5` key of the line.  Every stage may fail on its own rank without costing the line its other numbers:
-    the collectives (`barrier`, `maxr`) are outside the try blocks and a failed rank contributes +inf, so that all ranks
-    take the same branches and nobody waits for a rank that has given up."""
-    leg, err, est, ms, chk, n5 = None, None, float("inf"), float("inf"), None, 0
+def run_leg(make_leg, describe, min_timed_s, barrier, maxr, n_min=10, n_max=400):
+    """An optional leg of the line (a dict, or {"error": ...}).  Every stage may fail on its own rank without costing the
+    line its other numbers: the collectives (`barrier`, `maxr`) are outside the try blocks and a failed rank contributes
+    +inf, so that all ranks take the same branches and nobody waits for a rank that has given up.
+    `make_leg()` -> object with estimate() -> seconds per unit, timed(n) -> device ms (sets .out), check(), close();
+    `describe(leg, n, ms, chk)` -> the dict."""
+    leg, err, est, ms, chk, n = None, None, float("inf"), float("inf"), None, 0
     barrier()
     try:
-        leg = (leg_factory or Config5Leg)(envs_global, world, rank, dev)
+        leg = make_leg()
         est = leg.estimate()
     except Exception as e:  # noqa: BLE001
         err = "%s: %s" % (type(e).__name__, e)
     est = maxr([est])[0]
     if math.isfinite(est):
-        n5 = int(max(10, min(400, math.ceil(min_timed_s / max(est, 1e-5)))))
+        n = int(max(n_min, min(n_max, math.ceil(min_timed_s / max(est, 1e-5)))))
         barrier()
         try:
-            ms = leg.timed(n5)
+            ms = leg.timed(n)
             chk = leg.check()
         except Exception as e:  # noqa: BLE001
             ms, err = float("inf"), "%s: %s" % (type(e).__name__, e)
         ms = maxr([ms])[0]
     if math.isfinite(ms) and leg is not None:
+        try:
+            out = describe(leg, n, ms, chk)
+        except Exception as e:  # noqa: BLE001
+            out = {"error": "%s: %s" % (type(e).__name__, e)}
+    else:
+        out = {"error": err or "the leg failed on another rank"}
+    try:
+        if leg is not None:
+            leg.close()
+    except Exception:  # noqa: BLE001
+        pass
+    return out
+
+
+def run_config5(envs_global, min_timed_s, world, rank, dev, barrier, maxr, leg_factory=None):
+    """The `config5` key of the line (BASELINE configs[4])."""
+
+    def describe(leg, n5, ms, chk):
         o5 = leg.out
-        config5 = {
+        return {
             "value": envs_global * n5 / (ms / 1000.0), "unit": "env-steps/s", "n_gpus": world, "global_envs": envs_global,
             "envs_per_gpu": o5["B"], "steps": n5, "ms_per_step": ms / n5, "timed_s": ms / 1000.0,
             "lp_kernel": o5["lp_kernel"], "lp_bytes_per_gpu": o5["lp_bytes"],
@@ -434,14 +458,92 @@ def run_config5(envs_global, min_timed_s, world, rank, dev, barrier, maxr, leg_f
                     "anm_step; device-timed, max over ranks; counters and oracle check are rank 0's"
                     % (envs_global, world, o5["lp_kernel"]),
         }  # fmt: skip
-    else:
-        config5 = {"error": err or "the leg failed on another rank"}
-    try:
-        if leg is not None:
-            leg.close()
-    except Exception:  # noqa: BLE001
-        pass
-    return config5
+
+    return run_leg(lambda: (leg_factory or Config5Leg)(envs_global, world, rank, dev), describe, min_timed_s, barrier, maxr)
+
+
+class Config4Leg:
+    """BASELINE configs[3] beside the headline: the synthetic 30-bus feeder, `B` instances on this GPU, uniform-random
+    actions and caller-supplied next_vars, open-loop rollouts of 20 steps per launch, the blocks back to back (launches
+    chained per instance) -- the `value` measurement of `bench.py --config 4`, shortened.  Parity of this workload is the
+    test suite's business (test_synth30_env_vs_oracle, test_synth30_stressed_full_size_vs_oracle at 8192 instances)."""
+
+    T = 20
+
+    def __init__(self, B, world, rank, dev):
+        import torch
+
+        self.B, self.dev = B, dev
+        try:
+            self.wl, self.seed_rank = setup_config4(B, dev, rank), rank
+        except AssertionError:  # this rank's random initial states hold one without a power-flow solution: rank 0's draw
+            self.wl, self.seed_rank = setup_config4(B, dev, 0), 0
+        nb = self.nb = self.wl["nb"]
+        self.ring, self.ring_nv = self.wl["ring"], self.wl["ring_nv"]
+        self.NR = self.ring.shape[0]
+        self.outs = [(nb.empty(self.T, B, nb.O), nb.empty(self.T, B), nb.empty(self.T, B, dtype=torch.uint8))
+                     for _ in range(3)]
+        self.block = 0
+
+    def run_block(self, chained):
+        b, T = self.block, self.T
+        self.block += 1
+        o, r, d = self.outs[b % len(self.outs)]
+        a0 = (b * T) % (self.NR - T + 1)
+        self.nb.rollout(self.ring[a0:a0 + T], self.ring_nv[a0:a0 + T], out=(o, r, d), chained=chained)
+
+    def estimate(self):
+        import torch
+
+        self.run_block(False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(3):
+            self.run_block(i > 0)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / 3
+
+    def timed(self, n):
+        import torch
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = self.nb.launch_count
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(n):
+            self.run_block(i > 0)
+        ev1.record()
+        torch.cuda.synchronize()
+        last = self.outs[(self.block - 1) % len(self.outs)][2]
+        self.out = {"launches": self.nb.launch_count - launches0, "workload": self.wl["workload"],
+                    "terminated_frac_last_step": float((last[self.T - 1] != 0).double().mean()),
+                    "lanes_per_env": self.nb.sizes["lanes_per_env"], "seed_rank": self.seed_rank}
+        return ev0.elapsed_time(ev1)
+
+    def check(self):
+        return None
+
+    def close(self):
+        import torch
+
+        self.wl = self.nb = self.ring = self.ring_nv = self.outs = None
+        torch.cuda.empty_cache()
+
+
+def run_config4(B, min_timed_s, world, rank, dev, barrier, maxr, leg_factory=None):
+    """The `config4` key of the line (BASELINE configs[3]); weak scaling: `B` instances per GPU."""
+
+    def describe(leg, n, ms, chk):
+        o, T = leg.out, Config4Leg.T
+        return {"value": world * B * T * n / (ms / 1000.0), "unit": "env-steps/s", "n_gpus": world, "envs_per_gpu": B,
+                "steps": T * n, "steps_per_launch": T, "ms_per_step": ms / (T * n), "timed_s": ms / 1000.0,
+                "gpu_launches": o["launches"], "lanes_per_env": o["lanes_per_env"],
+                "terminated_frac_last_step": o["terminated_frac_last_step"],
+                "what": "BASELINE configs[3]: %s; %d-step anm_rollout launches back to back (chained per instance), "
+                        "device-timed, max over ranks" % (o["workload"], T)}  # fmt: skip
+
+    return run_leg(lambda: (leg_factory or Config4Leg)(B, world, rank, dev), describe, min_timed_s, barrier, maxr,
+                   n_min=3, n_max=2000)
 
 
 def run_ours(args):
@@ -676,6 +778,10 @@ def run_ours(args):
     config5 = None
     if args.config == 2 and not args.no_config5:
         config5 = run_config5(args.config5_envs, args.min_timed_s, world, rank, dev, barrier, maxr)
+    # ---- BASELINE configs[3]: the 30-bus feeder, 8192 instances per GPU, open-loop rollouts -----------------------
+    config4 = None
+    if args.config == 2 and not args.no_config4:
+        config4 = run_config4(8192, args.min_timed_s, world, rank, dev, barrier, maxr)
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -780,6 +886,8 @@ def run_ours(args):
     }
     if config5 is not None:
         line["config5"] = config5
+    if config4 is not None:
+        line["config4"] = config4
     if gather:
         if "value" in gather.get("p2p", {}):
             line["with_obs_allgather"] = dict(gather["p2p"], what="one launch per step; the kernel epilogue stores every "

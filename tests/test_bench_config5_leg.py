@@ -189,3 +189,35 @@ def test_run_config5_world2_a_failing_rank_does_not_hang_the_other(tmp_path):
         else:
             assert all(set(r) == {"error"} for r in res), res
             assert stage in res[1]["error"] and (stage in res[0]["error"] or "another rank" in res[0]["error"])
+
+
+class _StubLeg4:
+    def __init__(self, B, world, rank, dev):
+        self.B = B
+
+    def estimate(self):
+        return 0.02
+
+    def timed(self, n):
+        self.out = {"launches": n, "workload": "stub feeder", "terminated_frac_last_step": 0.0, "lanes_per_env": 32}
+        return 20.0 * n
+
+    def check(self):
+        return None
+
+    def close(self):
+        pass
+
+
+def test_run_config4_line():
+    out = bench.run_config4(8192, 0.35, 2, 0, None, lambda: None, lambda v: list(v), leg_factory=_StubLeg4)
+    # 18 blocks of 20 steps, 20 ms per block: 1 ms per step for 2 x 8192 instances
+    assert out["steps"] == 360 and out["steps_per_launch"] == 20 and abs(out["ms_per_step"] - 1.0) < 1e-12
+    assert abs(out["value"] - 2 * 8192 / 1e-3) < 1e-3 and out["gpu_launches"] == 18 and "stub feeder" in out["what"]
+
+    class Broken(_StubLeg4):
+        def timed(self, n):
+            raise MemoryError("out of memory")
+
+    bad = bench.run_config4(8192, 0.35, 1, 0, None, lambda: None, lambda v: list(v), leg_factory=Broken)
+    assert bad == {"error": "MemoryError: out of memory"}
