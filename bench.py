@@ -774,14 +774,20 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             pass
 
-    # ---- BASELINE configs[4]: 16 384 instances (global) driven by the MPC-constant agent, LPs on the GPU ----------
-    config5 = None
-    if args.config == 2 and not args.no_config5:
-        config5 = run_config5(args.config5_envs, args.min_timed_s, world, rank, dev, barrier, maxr)
     # ---- BASELINE configs[3]: the 30-bus feeder, 8192 instances per GPU, open-loop rollouts -----------------------
     config4 = None
     if args.config == 2 and not args.no_config4:
-        config4 = run_config4(8192, args.min_timed_s, world, rank, dev, barrier, maxr)
+        try:
+            config4 = run_config4(8192, args.min_timed_s, world, rank, dev, barrier, maxr)
+        except Exception as e:  # noqa: BLE001
+            config4 = {"error": "%s: %s" % (type(e).__name__, e)}
+    # ---- BASELINE configs[4]: 16 384 instances (global) driven by the MPC-constant agent, LPs on the GPU ----------
+    config5 = None
+    if args.config == 2 and not args.no_config5:
+        try:
+            config5 = run_config5(args.config5_envs, args.min_timed_s, world, rank, dev, barrier, maxr)
+        except Exception as e:  # noqa: BLE001  (e.g. a barrier that fails: the line keeps its other numbers)
+            config5 = {"error": "%s: %s" % (type(e).__name__, e)}
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
