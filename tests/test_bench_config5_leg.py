@@ -221,3 +221,47 @@ def test_run_config4_line():
 
     bad = bench.run_config4(8192, 0.35, 1, 0, None, lambda: None, lambda v: list(v), leg_factory=Broken)
     assert bad == {"error": "MemoryError: out of memory"}
+
+
+class _FakeNB:
+    O = 5
+    sizes = {"lanes_per_env": 32}
+
+    def __init__(self, B):
+        self.B, self.launch_count, self.calls = B, 0, []
+
+    def empty(self, *shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype)
+
+    def rollout(self, actions, next_vars, out, chained):
+        assert actions.shape[0] == next_vars.shape[0] == out[0].shape[0] == bench.Config4Leg.T
+        assert actions.is_contiguous() and next_vars.is_contiguous()
+        self.calls.append((int(actions[0, 0, 0]), chained))  # ring slot of the first step (the fake ring holds its index)
+        out[2][:] = 0
+        self.launch_count += 1
+
+
+def test_config4_leg_indexing_on_cpu(monkeypatch):
+    B, R = 6, 64
+
+    def fake_setup(Bx, dev, rank):
+        if rank == 1:
+            raise AssertionError("an initial state without a solution")
+        ring = torch.arange(R, dtype=torch.float64)[:, None, None].expand(R, Bx, 3).contiguous()
+        return {"nb": _FakeNB(Bx), "ring": ring, "ring_nv": ring.clone(), "workload": "fake feeder"}
+
+    monkeypatch.setattr(bench, "setup_config4", fake_setup)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    leg = bench.Config4Leg(B, 2, 1, torch.device("cpu"))  # rank 1's draw fails: rank 0's is used
+    assert leg.seed_rank == 0
+    assert leg.estimate() >= 0.0
+    nb = leg.nb
+    assert [c[1] for c in nb.calls] == [False, False, True, True]  # untimed block, then three with the 2nd / 3rd chained
+    ms = leg.timed(5)
+    assert ms >= 0.0 and leg.out["launches"] == 5 and leg.out["seed_rank"] == 0 and leg.out["workload"] == "fake feeder"
+    starts = [c[0] for c in nb.calls]
+    assert starts == [(b * 20) % (R - 20 + 1) for b in range(9)] and max(starts) + 20 <= R
+    assert [c[1] for c in nb.calls[4:]] == [False, True, True, True, True]
+    leg.close()
